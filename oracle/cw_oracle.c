@@ -1,0 +1,614 @@
+/*
+ * cw_oracle.c -- CPU ORACLE (test infrastructure, never the product path; see cw_oracle.h).
+ *
+ * Plain-C restatement of what the reference computes per chunk:
+ *   Skein v1.1   : reference_code/skein/Reference_Implementation/skein_block.c:29-35 (InjectKey),
+ *                  :42-118 (Threefish-256 block), :127-219 (Threefish-512 block);
+ *                  Optimized_64bit/skein.c:226-266 (Init via config block), :329-373 (Update),
+ *                  :377-408 (Final + counter-mode output); SHA3api_ref.c:59-83 (bit padding);
+ *                  constants skein.h:145-196, :272-292.
+ *   SHA-256      : FIPS 180-4; the reference calls OpenSSL SHA256() (src/hashing_perf/hash.cpp:35).
+ *   LZ4 1.8.2    : source NOT in the reference tree (prebuilt src/compression_perf/lib/liblz4.a,
+ *                  header include/lz4/lz4.h:94-96,126-156).  Restated from the public block format
+ *                  and the 1.8.2 LZ4_compress_generic parse; accepted only
+ *                  because it is byte-identical to the vendored archive (tests/golden/, oracle/_ref).
+ *   liblzf       : source NOT in the reference tree (prebuilt lib/liblzf.a, config in
+ *                  include/lzf/lzfP.h:54-164).  Restated from the published liblzf 3.6 algorithm with
+ *                  the reference's build options (HLOG 16, VERY_FAST, zeroed table).
+ */
+#include "cw_oracle.h"
+#include "../include/cw_synth.h"
+
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+/* ------------------------------------------------------------------------------------------- */
+/* Skein v1.1                                                                                  */
+/* ------------------------------------------------------------------------------------------- */
+
+#define T1_FIRST (1ull << 62)
+#define T1_FINAL (1ull << 63)
+#define T1_BITPAD (1ull << 55)
+#define T1_TYPE(t) ((uint64_t)(t) << 56)
+#define TYPE_CFG 4
+#define TYPE_MSG 48
+#define TYPE_OUT 63
+#define KS_PARITY 0x5555555555555555ull
+#define SCHEMA_VER 0x0000000133414853ull /* version 1, "SHA3" */
+
+static const uint8_t ROT512[8][4] = {{38, 30, 50, 53}, {48, 20, 43, 31}, {34, 14, 15, 27}, {26, 12, 58, 7},
+                                     {33, 49, 8, 42},  {39, 27, 41, 14}, {29, 26, 11, 9},  {33, 51, 39, 35}};
+static const uint8_t ROT256[8][2] = {{5, 56}, {36, 28}, {13, 46}, {58, 44}, {26, 20}, {53, 35}, {11, 42}, {59, 50}};
+/* word pairings (a,b) of the four MIXes in round r mod 4 (skein_block.c:175-193) */
+static const uint8_t PAIR512[4][8] = {{0, 1, 2, 3, 4, 5, 6, 7}, {2, 1, 4, 7, 6, 5, 0, 3},
+                                      {4, 1, 6, 3, 0, 5, 2, 7}, {6, 1, 0, 7, 2, 5, 4, 3}};
+static const uint8_t PAIR256[2][4] = {{0, 1, 2, 3}, {0, 3, 2, 1}};
+
+static inline uint64_t rotl64(uint64_t x, unsigned n) { return (x << n) | (x >> (64 - n)); }
+static inline uint64_t load_le64(const uint8_t *p)
+{
+    uint64_t v = 0;
+    for (int i = 7; i >= 0; i--) v = (v << 8) | p[i];
+    return v;
+}
+
+typedef struct {
+    unsigned words; /* 4 or 8 */
+    uint64_t X[8];
+    uint64_t T0, T1;
+} skein_state;
+
+/* one Threefish call under key = chaining value, tweak (T0+add, T1); feed-forward; clears FIRST */
+static void skein_block(skein_state *s, const uint8_t *blk, uint64_t byte_add)
+{
+    const unsigned W = s->words;
+    uint64_t ks[9], ts[3], w[8], X[8];
+    s->T0 += byte_add;
+    ks[W] = KS_PARITY;
+    for (unsigned i = 0; i < W; i++) {
+        ks[i] = s->X[i];
+        ks[W] ^= s->X[i];
+    }
+    ts[0] = s->T0;
+    ts[1] = s->T1;
+    ts[2] = ts[0] ^ ts[1];
+    for (unsigned i = 0; i < W; i++) {
+        w[i] = load_le64(blk + 8 * i);
+        X[i] = w[i] + ks[i];
+    }
+    X[W - 3] += ts[0];
+    X[W - 2] += ts[1];
+    for (unsigned round = 0; round < 72; round++) {
+        if (W == 8) {
+            const uint8_t *p = PAIR512[round & 3];
+            for (unsigned m = 0; m < 4; m++) {
+                unsigned a = p[2 * m], b = p[2 * m + 1];
+                X[a] += X[b];
+                X[b] = rotl64(X[b], ROT512[round & 7][m]) ^ X[a];
+            }
+        } else {
+            const uint8_t *p = PAIR256[round & 1];
+            for (unsigned m = 0; m < 2; m++) {
+                unsigned a = p[2 * m], b = p[2 * m + 1];
+                X[a] += X[b];
+                X[b] = rotl64(X[b], ROT256[round & 7][m]) ^ X[a];
+            }
+        }
+        if ((round & 3) == 3) {
+            unsigned r = round / 4 + 1; /* injection number 1..18 */
+            for (unsigned i = 0; i < W; i++) X[i] += ks[(r + i) % (W + 1)];
+            X[W - 3] += ts[r % 3];
+            X[W - 2] += ts[(r + 1) % 3];
+            X[W - 1] += r;
+        }
+    }
+    for (unsigned i = 0; i < W; i++) s->X[i] = X[i] ^ w[i];
+    s->T1 &= ~T1_FIRST;
+}
+
+void cwo_skein(unsigned state_bits, unsigned hash_bits, const uint8_t *msg, uint64_t msg_bits, uint8_t *out)
+{
+    skein_state s;
+    const unsigned W = state_bits / 64, B = state_bits / 8;
+    uint8_t buf[64];
+    s.words = W;
+    /* IV = UBI(0, config block, type CFG); the reference uses precomputed tables for common sizes
+     * (skein_iv.h) which are by construction this same value */
+    memset(s.X, 0, sizeof s.X);
+    memset(buf, 0, sizeof buf);
+    for (int i = 0; i < 8; i++) buf[i] = (uint8_t)(SCHEMA_VER >> (8 * i));
+    for (int i = 0; i < 8; i++) buf[8 + i] = (uint8_t)((uint64_t)hash_bits >> (8 * i));
+    s.T0 = 0;
+    s.T1 = T1_FIRST | T1_FINAL | T1_TYPE(TYPE_CFG);
+    skein_block(&s, buf, 32);
+
+    /* message: all blocks but the last are full; the last (1..B bytes, or 0 for the empty message)
+     * is zero padded and carries FINAL */
+    uint64_t nbytes = (msg_bits + 7) / 8;
+    s.T0 = 0;
+    s.T1 = T1_FIRST | T1_TYPE(TYPE_MSG);
+    uint64_t off = 0;
+    while (nbytes - off > B) {
+        skein_block(&s, msg + off, B);
+        off += B;
+    }
+    unsigned rem = (unsigned)(nbytes - off);
+    memset(buf, 0, sizeof buf);
+    memcpy(buf, msg + off, rem);
+    if (msg_bits & 7) {
+        uint8_t mask = (uint8_t)(1u << (7 - (msg_bits & 7)));
+        buf[rem - 1] = (uint8_t)((buf[rem - 1] & (0 - mask)) | mask);
+        s.T1 |= T1_BITPAD;
+    }
+    s.T1 |= T1_FINAL;
+    skein_block(&s, buf, rem);
+
+    /* output: Threefish in counter mode under the final chaining value */
+    unsigned out_bytes = (hash_bits + 7) / 8;
+    uint64_t key[8];
+    memcpy(key, s.X, sizeof key);
+    for (unsigned i = 0; i * B < out_bytes; i++) {
+        memset(buf, 0, sizeof buf);
+        for (int k = 0; k < 8; k++) buf[k] = (uint8_t)((uint64_t)i >> (8 * k));
+        s.T0 = 0;
+        s.T1 = T1_FIRST | T1_FINAL | T1_TYPE(TYPE_OUT);
+        skein_block(&s, buf, 8);
+        unsigned n = out_bytes - i * B;
+        if (n > B) n = B;
+        for (unsigned k = 0; k < n; k++) out[i * B + k] = (uint8_t)(s.X[k / 8] >> (8 * (k % 8)));
+        memcpy(s.X, key, sizeof key);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* SHA-256                                                                                     */
+/* ------------------------------------------------------------------------------------------- */
+
+static const uint32_t K256[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98,
+    0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786,
+    0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8,
+    0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13,
+    0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819,
+    0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a,
+    0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7,
+    0xc67178f2};
+
+static inline uint32_t rotr32(uint32_t x, unsigned n) { return (x >> n) | (x << (32 - n)); }
+
+static void sha256_compress(uint32_t H[8], const uint8_t *blk)
+{
+    uint32_t w[64];
+    for (int t = 0; t < 16; t++)
+        w[t] = ((uint32_t)blk[4 * t] << 24) | ((uint32_t)blk[4 * t + 1] << 16) | ((uint32_t)blk[4 * t + 2] << 8) |
+               blk[4 * t + 3];
+    for (int t = 16; t < 64; t++) {
+        uint32_t s0 = rotr32(w[t - 15], 7) ^ rotr32(w[t - 15], 18) ^ (w[t - 15] >> 3);
+        uint32_t s1 = rotr32(w[t - 2], 17) ^ rotr32(w[t - 2], 19) ^ (w[t - 2] >> 10);
+        w[t] = w[t - 16] + s0 + w[t - 7] + s1;
+    }
+    uint32_t a = H[0], b = H[1], c = H[2], d = H[3], e = H[4], f = H[5], g = H[6], h = H[7];
+    for (int t = 0; t < 64; t++) {
+        uint32_t S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
+        uint32_t ch = (e & f) ^ (~e & g);
+        uint32_t t1 = h + S1 + ch + K256[t] + w[t];
+        uint32_t S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
+        uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+        uint32_t t2 = S0 + mj;
+        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    H[0] += a; H[1] += b; H[2] += c; H[3] += d; H[4] += e; H[5] += f; H[6] += g; H[7] += h;
+}
+
+void cwo_sha256(const uint8_t *msg, size_t len, uint8_t out[32])
+{
+    uint32_t H[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    size_t off = 0;
+    for (; off + 64 <= len; off += 64) sha256_compress(H, msg + off);
+    uint8_t tail[128];
+    size_t rem = len - off;
+    memset(tail, 0, sizeof tail);
+    memcpy(tail, msg + off, rem);
+    tail[rem] = 0x80;
+    size_t tl = rem + 1 + 8 <= 64 ? 64 : 128;
+    uint64_t bits = (uint64_t)len * 8;
+    for (int i = 0; i < 8; i++) tail[tl - 1 - i] = (uint8_t)(bits >> (8 * i));
+    sha256_compress(H, tail);
+    if (tl == 128) sha256_compress(H, tail + 64);
+    for (int i = 0; i < 8; i++) {
+        out[4 * i] = (uint8_t)(H[i] >> 24);
+        out[4 * i + 1] = (uint8_t)(H[i] >> 16);
+        out[4 * i + 2] = (uint8_t)(H[i] >> 8);
+        out[4 * i + 3] = (uint8_t)H[i];
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* LZ4 block format, 1.8.2 fast parse (u16 table path, srcSize < 65547)                        */
+/* ------------------------------------------------------------------------------------------- */
+
+static inline uint32_t rd32(const uint8_t *p)
+{
+    uint32_t v;
+    memcpy(&v, p, 4);
+    return v;
+}
+static inline uint32_t lz4_hash13(uint32_t v) { return (v * 2654435761u) >> 19; }
+
+int cwo_lz4_compress(const uint8_t *src, int n, uint8_t *dst, int cap)
+{
+    uint16_t table[8192];
+    uint8_t *op = dst, *const oend = dst + cap;
+    int anchor = 0;
+    if (n < 0 || n >= 65547) return 0; /* the u32-table path of larger inputs is out of scope */
+    memset(table, 0, sizeof table);
+    if (n >= 13) {
+        const int mflimit1 = n - 11; /* mflimit + 1 */
+        const int matchlimit = n - 5;
+        int ip = 0;
+        uint32_t fwd_h;
+        table[lz4_hash13(rd32(src))] = 0;
+        ip = 1;
+        fwd_h = lz4_hash13(rd32(src + 1));
+        for (;;) {
+            int cand;
+            uint8_t *token;
+            {
+                int fwd = ip, step = 1, search_nb = 1 << 6;
+                do {
+                    uint32_t h = fwd_h;
+                    ip = fwd;
+                    fwd += step;
+                    step = search_nb++ >> 6;
+                    if (fwd > mflimit1) goto last_literals;
+                    cand = table[h];
+                    fwd_h = lz4_hash13(rd32(src + fwd));
+                    table[h] = (uint16_t)ip;
+                } while (rd32(src + cand) != rd32(src + ip));
+            }
+            while (ip > anchor && cand > 0 && src[ip - 1] == src[cand - 1]) {
+                ip--;
+                cand--;
+            }
+            {
+                unsigned lit = (unsigned)(ip - anchor);
+                token = op++;
+                if (op + lit + (2 + 1 + 5) + lit / 255 > oend) return 0;
+                if (lit >= 15) {
+                    unsigned len = lit - 15;
+                    *token = 15 << 4;
+                    for (; len >= 255; len -= 255) *op++ = 255;
+                    *op++ = (uint8_t)len;
+                } else
+                    *token = (uint8_t)(lit << 4);
+                memcpy(op, src + anchor, lit);
+                op += lit;
+            }
+        next_match:
+            op[0] = (uint8_t)(ip - cand);
+            op[1] = (uint8_t)((ip - cand) >> 8);
+            op += 2;
+            {
+                unsigned m = 0;
+                while (ip + 4 + (int)m < matchlimit && src[ip + 4 + m] == src[cand + 4 + m]) m++;
+                ip += 4 + (int)m;
+                if (op + (1 + 5) + (m >> 8) > oend) return 0;
+                if (m >= 15) {
+                    *token += 15;
+                    m -= 15;
+                    for (; m >= 255; m -= 255) *op++ = 255;
+                    *op++ = (uint8_t)m;
+                } else
+                    *token += (uint8_t)m;
+            }
+            anchor = ip;
+            if (ip >= mflimit1) break;
+            table[lz4_hash13(rd32(src + ip - 2))] = (uint16_t)(ip - 2);
+            {
+                uint32_t h = lz4_hash13(rd32(src + ip));
+                cand = table[h];
+                table[h] = (uint16_t)ip;
+            }
+            if (rd32(src + cand) == rd32(src + ip)) {
+                token = op++;
+                *token = 0;
+                goto next_match;
+            }
+            fwd_h = lz4_hash13(rd32(src + ++ip));
+        }
+    }
+last_literals : {
+    unsigned last = (unsigned)(n - anchor);
+    if ((op - dst) + last + 1 + ((last + 255 - 15) / 255) > (size_t)cap) return 0;
+    if (last >= 15) {
+        unsigned acc = last - 15;
+        *op++ = 15 << 4;
+        for (; acc >= 255; acc -= 255) *op++ = 255;
+        *op++ = (uint8_t)acc;
+    } else
+        *op++ = (uint8_t)(last << 4);
+    memcpy(op, src + anchor, last);
+    op += last;
+}
+    return (int)(op - dst);
+}
+
+int cwo_lz4_decompress(const uint8_t *src, int n, uint8_t *dst, int cap)
+{
+    const uint8_t *ip = src, *const iend = src + n;
+    uint8_t *op = dst, *const oend = dst + cap;
+    if (n <= 0) return -1;
+    for (;;) {
+        if (ip >= iend) return -1;
+        unsigned token = *ip++;
+        size_t lit = token >> 4;
+        if (lit == 15) {
+            unsigned b;
+            do {
+                if (ip >= iend) return -1;
+                b = *ip++;
+                lit += b;
+            } while (b == 255);
+        }
+        if ((size_t)(iend - ip) < lit || (size_t)(oend - op) < lit) return -1;
+        memcpy(op, ip, lit);
+        op += lit;
+        ip += lit;
+        if (ip == iend) break; /* last sequence: literals only */
+        if (iend - ip < 2) return -1;
+        unsigned off = ip[0] | (ip[1] << 8);
+        ip += 2;
+        if (off == 0 || (size_t)(op - dst) < off) return -1;
+        size_t ml = token & 15;
+        if (ml == 15) {
+            unsigned b;
+            do {
+                if (ip >= iend) return -1;
+                b = *ip++;
+                ml += b;
+            } while (b == 255);
+        }
+        ml += 4;
+        if ((size_t)(oend - op) < ml) return -1;
+        for (size_t k = 0; k < ml; k++) op[k] = op[k - off];
+        op += ml;
+    }
+    return (int)(op - dst);
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* LZF (liblzf 3.x, HLOG 16, VERY_FAST, table zeroed)                                          */
+/* ------------------------------------------------------------------------------------------- */
+
+#define LZF_MAX_LIT 32u
+#define LZF_MAX_OFF 8192u
+#define LZF_MAX_REF 264u
+static inline unsigned lzf_slot(unsigned h) { return ((h >> 8) - h * 5u) & 0xffffu; }
+
+unsigned cwo_lzf_compress(const uint8_t *in, unsigned in_len, uint8_t *out, unsigned out_len)
+{
+    uint32_t *htab;
+    unsigned ip = 0, hval, result = 0;
+    uint8_t *op = out, *const out_end = out + out_len;
+    int lit = 0;
+    if (!in_len || !out_len) return 0;
+    htab = (uint32_t *)calloc(65536, sizeof *htab);
+    if (!htab) return 0;
+    op++;
+    hval = ((unsigned)in[0] << 8) | (in_len > 1 ? in[1] : 0);
+    while (ip + 2 < in_len) {
+        unsigned slot, ref, off;
+        hval = (hval << 8) | in[ip + 2];
+        slot = lzf_slot(hval);
+        ref = htab[slot];
+        htab[slot] = ip;
+        off = ip - ref - 1;
+        if (ref > 0 && off < LZF_MAX_OFF && in[ref] == in[ip] && in[ref + 1] == in[ip + 1] &&
+            in[ref + 2] == in[ip + 2]) {
+            unsigned len = 2, maxlen = in_len - ip - 2;
+            if (maxlen > LZF_MAX_REF) maxlen = LZF_MAX_REF;
+            if (op + 4 >= out_end && op - !lit + 4 >= out_end) goto done;
+            op[-lit - 1] = (uint8_t)(lit - 1);
+            op -= !lit;
+            {
+                int stopped = 0;
+                if (maxlen > 16) {
+                    for (int k = 0; k < 16; k++) {
+                        len++;
+                        if (in[ref + len] != in[ip + len]) {
+                            stopped = 1;
+                            break;
+                        }
+                    }
+                }
+                if (!stopped) {
+                    do len++;
+                    while (len < maxlen && in[ref + len] == in[ip + len]);
+                }
+            }
+            len -= 2;
+            if (len < 7)
+                *op++ = (uint8_t)((off >> 8) + (len << 5));
+            else {
+                *op++ = (uint8_t)((off >> 8) + (7u << 5));
+                *op++ = (uint8_t)(len - 7);
+            }
+            *op++ = (uint8_t)off;
+            lit = 0;
+            op++;
+            ip += len + 2;
+            if (ip + 2 >= in_len) break;
+            ip -= 2;
+            hval = ((unsigned)in[ip] << 8) | in[ip + 1];
+            hval = (hval << 8) | in[ip + 2];
+            htab[lzf_slot(hval)] = ip;
+            ip++;
+            hval = (hval << 8) | in[ip + 2];
+            htab[lzf_slot(hval)] = ip;
+            ip++;
+        } else {
+            if (op >= out_end) goto done;
+            lit++;
+            *op++ = in[ip++];
+            if (lit == (int)LZF_MAX_LIT) {
+                op[-lit - 1] = (uint8_t)(lit - 1);
+                lit = 0;
+                op++;
+            }
+        }
+    }
+    if (op + 3 > out_end) goto done;
+    while (ip < in_len) {
+        lit++;
+        *op++ = in[ip++];
+        if (lit == (int)LZF_MAX_LIT) {
+            op[-lit - 1] = (uint8_t)(lit - 1);
+            lit = 0;
+            op++;
+        }
+    }
+    op[-lit - 1] = (uint8_t)(lit - 1);
+    op -= !lit;
+    result = (unsigned)(op - out);
+done:
+    free(htab);
+    return result;
+}
+
+unsigned cwo_lzf_decompress(const uint8_t *in, unsigned in_len, uint8_t *out, unsigned out_len)
+{
+    const uint8_t *ip = in, *const in_end = in + in_len;
+    uint8_t *op = out, *const out_end = out + out_len;
+    if (!in_len) return 0;
+    do {
+        unsigned ctrl = *ip++;
+        if (ctrl < 32) {
+            ctrl++;
+            if (op + ctrl > out_end || ip + ctrl > in_end) return 0;
+            memcpy(op, ip, ctrl);
+            op += ctrl;
+            ip += ctrl;
+        } else {
+            unsigned len = ctrl >> 5;
+            size_t back = ((ctrl & 0x1f) << 8) + 1;
+            if (ip >= in_end) return 0;
+            if (len == 7) {
+                len += *ip++;
+                if (ip >= in_end) return 0;
+            }
+            back += *ip++;
+            if (op + len + 2 > out_end || (size_t)(op - out) < back) return 0;
+            for (unsigned k = 0; k < len + 2; k++) op[k] = op[(ptrdiff_t)k - (ptrdiff_t)back];
+            op += len + 2;
+        }
+    } while (ip < in_end);
+    return (unsigned)(op - out);
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* per-chunk drivers                                                                           */
+/* ------------------------------------------------------------------------------------------- */
+
+int cwo_digest_bytes(int alg) { return alg == CWO_HASH_SKEIN512 ? 64 : alg == CWO_HASH_SKEIN256_128 ? 16 : 32; }
+
+size_t cwo_compress_bound(int alg, size_t chunk)
+{
+    if (alg == CWO_COMP_LZ4) return chunk + chunk / 255 + 16; /* LZ4_COMPRESSBOUND, lz4.h:156 */
+    return chunk;                                             /* LZF is called with out_len = chunk-1 */
+}
+
+static void hash_one(int alg, const uint8_t *p, size_t len, uint8_t *out)
+{
+    if (alg == CWO_HASH_SKEIN512) cwo_skein(512, 512, p, (uint64_t)len * 8, out);
+    else if (alg == CWO_HASH_SKEIN256_128) cwo_skein(256, 128, p, (uint64_t)len * 8, out);
+    else cwo_sha256(p, len, out);
+}
+
+static uint32_t compress_one(int alg, const uint8_t *p, size_t len, uint8_t *out, size_t cap)
+{
+    if (alg == CWO_COMP_LZ4) return (uint32_t)cwo_lz4_compress(p, (int)len, out, (int)cap);
+    return cwo_lzf_compress(p, (unsigned)len, out, (unsigned)(len - 1 < cap ? len - 1 : cap));
+}
+
+void cwo_hash_chunks(int alg, const uint8_t *src, size_t chunk, size_t n, uint8_t *digests)
+{
+    const int D = cwo_digest_bytes(alg);
+    for (size_t i = 0; i < n; i++) hash_one(alg, src + i * chunk, chunk, digests + i * D);
+}
+
+void cwo_compress_chunks(int alg, const uint8_t *src, size_t chunk, size_t n, uint8_t *dst, size_t stride,
+                         uint32_t *lens)
+{
+    for (size_t i = 0; i < n; i++) lens[i] = compress_one(alg, src + i * chunk, chunk, dst + i * stride, stride);
+}
+
+void cwo_hash_compress_chunks(int halg, int calg, const uint8_t *src, size_t chunk, size_t n, uint8_t *digests,
+                              uint8_t *dst, size_t stride, uint32_t *lens)
+{
+    const int D = cwo_digest_bytes(halg);
+    for (size_t i = 0; i < n; i++) {
+        lens[i] = compress_one(calg, src + i * chunk, chunk, dst + i * stride, stride);
+        hash_one(halg, src + i * chunk, chunk, digests + i * D);
+    }
+}
+
+int cwo_verify_roundtrip(int alg, const uint8_t *src, size_t chunk, size_t n, const uint8_t *blocks, size_t stride,
+                         const uint32_t *lens)
+{
+    uint8_t *tmp = (uint8_t *)malloc(chunk + 8);
+    int bad = 0;
+    for (size_t i = 0; i < n && !bad; i++) {
+        const uint8_t *b = blocks + i * stride;
+        if (alg == CWO_COMP_LZF && lens[i] == 0) continue; /* stored raw by the caller */
+        long got = alg == CWO_COMP_LZ4 ? cwo_lz4_decompress(b, (int)lens[i], tmp, (int)chunk)
+                                       : (long)cwo_lzf_decompress(b, lens[i], tmp, (unsigned)chunk);
+        if (got != (long)chunk || memcmp(tmp, src + i * chunk, chunk) != 0) bad = (int)i + 1;
+    }
+    free(tmp);
+    return bad;
+}
+
+typedef struct {
+    int halg, calg;
+    const uint8_t *src;
+    size_t chunk, lo, hi, stride;
+    uint8_t *digests, *dst;
+    uint32_t *lens;
+} mt_job;
+
+static void *mt_worker(void *arg)
+{
+    mt_job *j = (mt_job *)arg;
+    const int D = cwo_digest_bytes(j->halg);
+    cwo_hash_compress_chunks(j->halg, j->calg, j->src + j->lo * j->chunk, j->chunk, j->hi - j->lo,
+                             j->digests + j->lo * D, j->dst + j->lo * j->stride, j->stride, j->lens + j->lo);
+    return NULL;
+}
+
+double cwo_hash_compress_mt(int halg, int calg, const uint8_t *src, size_t chunk, size_t n, uint8_t *digests,
+                            uint8_t *dst, size_t stride, uint32_t *lens, int threads)
+{
+    if (threads < 1) threads = 1;
+    pthread_t *tid = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
+    mt_job *jobs = (mt_job *)malloc(sizeof(mt_job) * (size_t)threads);
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int t = 0; t < threads; t++) {
+        mt_job j = {halg, calg, src, chunk, n * (size_t)t / (size_t)threads, n * (size_t)(t + 1) / (size_t)threads,
+                    stride, digests, dst, lens};
+        jobs[t] = j;
+        pthread_create(&tid[t], NULL, mt_worker, &jobs[t]);
+    }
+    for (int t = 0; t < threads; t++) pthread_join(tid[t], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    free(tid);
+    free(jobs);
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+void cwo_synth_fill(uint8_t *dst, size_t chunk, uint64_t first_chunk, size_t n, uint64_t seed)
+{
+    for (size_t i = 0; i < n; i++) cw_synth_chunk(dst + i * chunk, chunk, first_chunk + i, seed);
+}

@@ -1,0 +1,26 @@
+"""pytest configuration: registers the `gpu` marker (tests that need a B200 and call through the C-ABI)."""
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: takes more than a few seconds on CPU")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import json
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    import numpy as np
+    with open(os.path.join(here, "skein_kat.json")) as f:
+        kat = json.load(f)
+    with open(os.path.join(here, "ref_outputs.json")) as f:
+        ref = json.load(f)
+    blob = np.fromfile(os.path.join(here, "corpus_sample.bin"), np.uint8)
+    return {"kat": kat, "ref": ref, "blob": blob}

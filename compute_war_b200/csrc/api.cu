@@ -1,0 +1,529 @@
+// api.cu -- the C ABI of include/compute_war.h: context, device-buffer calls, the pipelined
+// host-buffer calls and the asynchronous offload queue.
+//
+// Reference interfaces replaced (see compute_war.h for the per-function list): initializeGpu()
+// HashAndCompress.cpp:95-98, doHashing :119-134, doCompression :111,342-355, ProcessBlock :231-261,
+// HashOffload HashOffload.h:15-64 + hashing_offload_entry_point HashAndCompress.cpp:160-183.
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/compute_war.h"
+#include "hash_kernels.cuh"
+#include "launch.h"
+
+namespace {
+
+constexpr int kSlots = 3;                     // H2D / kernel / D2H in flight
+constexpr size_t kSliceBytes = 32u << 20;     // input bytes per pipeline slice
+constexpr int kWorkRing = 256;
+
+struct Slot {
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
+    uint8_t *d_in = nullptr, *d_out = nullptr, *d_dig = nullptr;
+    uint32_t *d_lens = nullptr;
+    size_t cap_in = 0, cap_out = 0, cap_dig = 0, cap_lens = 0;
+    bool busy = false;
+};
+
+struct Job {
+    cw_ticket ticket;
+    cw_hash_alg halg;
+    cw_comp_alg calg;
+    cw_mode mode;
+    const void *src;
+    size_t chunk, n;
+    void *digests, *dst;
+    size_t stride;
+    uint32_t *lens;
+    cw_complete_fn cb;
+    void *user;
+};
+
+}  // namespace
+
+struct cw_ctx {
+    int device = 0;
+    CwDeviceInfo dev{};
+    CwSkeinIV iv{};
+    cudaStream_t stream = nullptr;
+    std::atomic<uint64_t> launches{0};
+    unsigned long long *d_work = nullptr;
+    int work_next = 0;
+    std::mutex mu;       // guards work ring, profiling lists, last_error
+    std::mutex host_mu;  // one host-buffer pipeline at a time per context
+    std::string last_error;
+    Slot slots[kSlots];
+    // profiling of the *_dev kernels
+    bool prof = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
+    std::vector<cudaEvent_t> ev_pool;
+    double prof_ms = 0;
+    uint64_t prof_launches = 0;
+    // async offload
+    std::thread worker;
+    std::mutex q_mu;
+    std::condition_variable q_cv, done_cv;
+    std::deque<Job> queue;
+    std::map<cw_ticket, int> finished;
+    cw_ticket next_ticket = 1;
+    bool stop = false;
+};
+
+namespace {
+
+int fail(cw_ctx *ctx, cudaError_t e, const char *what)
+{
+    std::lock_guard<std::mutex> g(ctx->mu);
+    ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return CW_ERR_CUDA;
+}
+
+#define CW_CUDA(ctx, call)                                    \
+    do {                                                      \
+        cudaError_t e_ = (call);                              \
+        if (e_ != cudaSuccess) return fail(ctx, e_, #call);   \
+    } while (0)
+
+int check_common(const cw_ctx *ctx, size_t chunk, size_t n, const void *src)
+{
+    if (!ctx) return CW_ERR_ARG;
+    if (chunk == 0 || (n && !src)) return CW_ERR_ARG;
+    if (chunk > CW_MAX_CHUNK) return CW_ERR_UNSUPPORTED;
+    return CW_OK;
+}
+
+unsigned long long *next_work(cw_ctx *ctx)
+{
+    std::lock_guard<std::mutex> g(ctx->mu);
+    unsigned long long *p = ctx->d_work + 2 * ctx->work_next;  // two counters per launch
+    ctx->work_next = (ctx->work_next + 1) % kWorkRing;
+    return p;
+}
+
+struct ProfScope {
+    cw_ctx *ctx;
+    cudaStream_t st;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ProfScope(cw_ctx *c, cudaStream_t s) : ctx(c), st(s)
+    {
+        if (!ctx->prof) return;
+        std::lock_guard<std::mutex> g(ctx->mu);
+        auto get = [&]() {
+            cudaEvent_t e;
+            if (!ctx->ev_pool.empty()) {
+                e = ctx->ev_pool.back();
+                ctx->ev_pool.pop_back();
+            } else
+                cudaEventCreate(&e);
+            return e;
+        };
+        e0 = get();
+        e1 = get();
+        cudaEventRecord(e0, st);
+    }
+    ~ProfScope()
+    {
+        if (!e0) return;
+        cudaEventRecord(e1, st);
+        std::lock_guard<std::mutex> g(ctx->mu);
+        ctx->prof_ev.emplace_back(e0, e1);
+    }
+};
+
+int do_hash_dev(cw_ctx *ctx, cw_hash_alg alg, const void *d_src, size_t chunk, size_t n, void *d_dig, cudaStream_t st)
+{
+    if ((int)alg < 0 || (int)alg > 2) return CW_ERR_ARG;
+    if (n == 0) return CW_OK;
+    ProfScope ps(ctx, st);
+    CW_CUDA(ctx, cw_launch_hash((int)alg, ctx->iv, (const uint8_t *)d_src, (uint32_t)chunk, n, (uint8_t *)d_dig, st));
+    ctx->launches++;
+    return CW_OK;
+}
+
+int do_compress_dev(cw_ctx *ctx, cw_comp_alg alg, cw_mode mode, const void *d_src, size_t chunk, size_t n, void *d_dst,
+                    size_t stride, uint32_t *d_lens, cudaStream_t st)
+{
+    if ((int)mode < 0 || (int)mode > 1) return CW_ERR_ARG;
+    if (stride < cw_compress_bound(alg, chunk)) return CW_ERR_ARG;
+    if (n == 0) return CW_OK;
+    if (alg == CW_COMP_LZ4) {
+        unsigned long long *w = next_work(ctx);
+        CW_CUDA(ctx, cudaMemsetAsync(w, 0, sizeof *w, st));
+        ProfScope ps(ctx, st);
+        CW_CUDA(ctx, cw_launch_lz4(ctx->dev, (const uint8_t *)d_src, (uint32_t)chunk, n, (uint8_t *)d_dst, stride, d_lens,
+                                   w, st));
+        ctx->launches++;
+        return CW_OK;
+    }
+    if (alg == CW_COMP_LZF) {
+        unsigned long long *w = next_work(ctx);
+        CW_CUDA(ctx, cudaMemsetAsync(w, 0, sizeof *w, st));
+        ProfScope ps(ctx, st);
+        CW_CUDA(ctx, cw_launch_lzf(ctx->dev, (const uint8_t *)d_src, (uint32_t)chunk, n, (uint8_t *)d_dst, stride, d_lens,
+                                   w, st));
+        ctx->launches++;
+        return CW_OK;
+    }
+    return CW_ERR_ARG;
+}
+
+int do_fused_dev(cw_ctx *ctx, cw_hash_alg halg, cw_comp_alg calg, cw_mode mode, const void *d_src, size_t chunk, size_t n,
+                 void *d_dig, void *d_dst, size_t stride, uint32_t *d_lens, cudaStream_t st)
+{
+    if ((int)halg < 0 || (int)halg > 2 || (int)calg < 0 || (int)calg > 1 || (int)mode < 0 || (int)mode > 1) return CW_ERR_ARG;
+    if (stride < cw_compress_bound(calg, chunk)) return CW_ERR_ARG;
+    if (n == 0) return CW_OK;
+    unsigned long long *w = next_work(ctx);
+    CW_CUDA(ctx, cudaMemsetAsync(w, 0, 2 * sizeof *w, st));
+    ProfScope ps(ctx, st);
+    CW_CUDA(ctx, cw_launch_fused(ctx->dev, (int)halg, (int)calg, ctx->iv, (const uint8_t *)d_src, (uint32_t)chunk, n,
+                                 (uint8_t *)d_dig, (uint8_t *)d_dst, stride, d_lens, w, st));
+    ctx->launches++;
+    return CW_OK;
+}
+
+int ensure(cw_ctx *ctx, void **p, size_t *cap, size_t need)
+{
+    if (*cap >= need) return CW_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    cudaError_t e = cudaMalloc(p, need);
+    if (e != cudaSuccess) {
+        fail(ctx, e, "cudaMalloc(pipeline slot)");
+        return CW_ERR_NOMEM;
+    }
+    *cap = need;
+    return CW_OK;
+}
+
+// Pipelined host-buffer pass: slices of ~32 MiB rotate through three slots, each with its own stream, so
+// the H2D copy of slice k+1, the kernels of slice k and the D2H copy of slice k-1 overlap.
+int host_pass(cw_ctx *ctx, bool want_hash, bool want_comp, cw_hash_alg halg, cw_comp_alg calg, cw_mode mode,
+              const void *src, size_t chunk, size_t n, void *digests, void *dst, size_t stride, uint32_t *lens)
+{
+    std::lock_guard<std::mutex> hg(ctx->host_mu);
+    CW_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t D = want_hash ? cw_digest_bytes(halg) : 0;
+    size_t per = kSliceBytes / chunk;
+    if (per < 1) per = 1;
+    int rc = CW_OK;
+    size_t k = 0;
+    for (size_t lo = 0; lo < n && rc == CW_OK; lo += per, k++) {
+        const size_t cnt = (n - lo < per) ? n - lo : per;
+        Slot &s = ctx->slots[k % kSlots];
+        if (s.busy) {
+            CW_CUDA(ctx, cudaEventSynchronize(s.done));
+            s.busy = false;
+        }
+        if ((rc = ensure(ctx, (void **)&s.d_in, &s.cap_in, per * chunk)) != CW_OK) break;
+        if (want_comp) {
+            if ((rc = ensure(ctx, (void **)&s.d_out, &s.cap_out, per * stride)) != CW_OK) break;
+            if ((rc = ensure(ctx, (void **)&s.d_lens, &s.cap_lens, per * sizeof(uint32_t))) != CW_OK) break;
+        }
+        if (want_hash && (rc = ensure(ctx, (void **)&s.d_dig, &s.cap_dig, per * D)) != CW_OK) break;
+        CW_CUDA(ctx, cudaMemcpyAsync(s.d_in, (const uint8_t *)src + lo * chunk, cnt * chunk, cudaMemcpyHostToDevice, s.st));
+        if (want_hash && want_comp)
+            rc = do_fused_dev(ctx, halg, calg, mode, s.d_in, chunk, cnt, s.d_dig, s.d_out, stride, s.d_lens, s.st);
+        else if (want_hash)
+            rc = do_hash_dev(ctx, halg, s.d_in, chunk, cnt, s.d_dig, s.st);
+        else
+            rc = do_compress_dev(ctx, calg, mode, s.d_in, chunk, cnt, s.d_out, stride, s.d_lens, s.st);
+        if (rc != CW_OK) break;
+        if (want_comp) {
+            CW_CUDA(ctx, cudaMemcpyAsync((uint8_t *)dst + lo * stride, s.d_out, cnt * stride, cudaMemcpyDeviceToHost, s.st));
+            CW_CUDA(ctx, cudaMemcpyAsync(lens + lo, s.d_lens, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.st));
+        }
+        if (want_hash)
+            CW_CUDA(ctx, cudaMemcpyAsync((uint8_t *)digests + lo * D, s.d_dig, cnt * D, cudaMemcpyDeviceToHost, s.st));
+        CW_CUDA(ctx, cudaEventRecord(s.done, s.st));
+        s.busy = true;
+    }
+    for (int i = 0; i < kSlots; i++) {
+        Slot &s = ctx->slots[i];
+        if (s.busy) {
+            cudaError_t e = cudaEventSynchronize(s.done);
+            s.busy = false;
+            if (e != cudaSuccess && rc == CW_OK) rc = fail(ctx, e, "cudaEventSynchronize(slot)");
+        }
+    }
+    return rc;
+}
+
+void worker_loop(cw_ctx *ctx)
+{
+    for (;;) {
+        Job j;
+        {
+            std::unique_lock<std::mutex> lk(ctx->q_mu);
+            ctx->q_cv.wait(lk, [&] { return ctx->stop || !ctx->queue.empty(); });
+            if (ctx->queue.empty()) return;  // stop requested and drained
+            j = ctx->queue.front();
+            ctx->queue.pop_front();
+        }
+        int rc = host_pass(ctx, true, true, j.halg, j.calg, j.mode, j.src, j.chunk, j.n, j.digests, j.dst, j.stride, j.lens);
+        if (j.cb) j.cb(j.ticket, rc, j.user);
+        {
+            std::lock_guard<std::mutex> lk(ctx->q_mu);
+            ctx->finished[j.ticket] = rc;
+        }
+        ctx->done_cv.notify_all();
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int cw_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char *cw_status_string(int s)
+{
+    switch (s) {
+    case CW_OK: return "ok";
+    case CW_ERR_ARG: return "bad argument";
+    case CW_ERR_NO_DEVICE: return "no CUDA device (the engine has no CPU path)";
+    case CW_ERR_CUDA: return "CUDA error";
+    case CW_ERR_NOMEM: return "out of device memory";
+    case CW_ERR_UNSUPPORTED: return "unsupported size or selector";
+    }
+    return "unknown";
+}
+
+int cw_init(cw_ctx **out, int device)
+{
+    if (!out) return CW_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return CW_ERR_NO_DEVICE;
+    if (device < 0 || device >= n) return CW_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return CW_ERR_CUDA;
+    cw_ctx *ctx = new cw_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete ctx;
+        return CW_ERR_CUDA;
+    }
+    ctx->dev.sm_count = prop.multiProcessorCount;
+    ctx->dev.smem_optin = prop.sharedMemPerBlockOptin;
+    cw_make_skein_iv(&ctx->iv);
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_work, 2 * kWorkRing * sizeof(unsigned long long)) == cudaSuccess;
+    for (int i = 0; ok && i < kSlots; i++) {
+        ok = cudaStreamCreateWithFlags(&ctx->slots[i].st, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->slots[i].done, cudaEventDisableTiming) == cudaSuccess;
+    }
+    ok = ok && cw_configure_kernels(ctx->dev) == cudaSuccess;
+    if (!ok) {
+        cw_shutdown(ctx);
+        return CW_ERR_CUDA;
+    }
+    *out = ctx;
+    return CW_OK;
+}
+
+void cw_shutdown(cw_ctx *ctx)
+{
+    if (!ctx) return;
+    if (ctx->worker.joinable()) {
+        {
+            std::lock_guard<std::mutex> lk(ctx->q_mu);
+            ctx->stop = true;
+        }
+        ctx->q_cv.notify_all();
+        ctx->worker.join();
+    }
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto &s : ctx->slots) {
+        if (s.d_in) cudaFree(s.d_in);
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.d_dig) cudaFree(s.d_dig);
+        if (s.d_lens) cudaFree(s.d_lens);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.st) cudaStreamDestroy(s.st);
+    }
+    for (auto &p : ctx->prof_ev) {
+        cudaEventDestroy(p.first);
+        cudaEventDestroy(p.second);
+    }
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->d_work) cudaFree(ctx->d_work);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *cw_last_error(const cw_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+size_t cw_digest_bytes(cw_hash_alg alg)
+{
+    return alg == CW_HASH_SKEIN512 ? 64 : (alg == CW_HASH_SKEIN256_128 ? 16 : (alg == CW_HASH_SHA256 ? 32 : 0));
+}
+
+size_t cw_compress_bound(cw_comp_alg alg, size_t chunk)
+{
+    if (alg == CW_COMP_LZ4) return chunk + chunk / 255 + 16;
+    return chunk;
+}
+
+int cw_hash_dev(cw_ctx *ctx, cw_hash_alg alg, const void *d_src, size_t chunk, size_t n, void *d_digests, void *stream)
+{
+    int rc = check_common(ctx, chunk, n, d_src);
+    if (rc != CW_OK) return rc;
+    if (n && !d_digests) return CW_ERR_ARG;
+    CW_CUDA(ctx, cudaSetDevice(ctx->device));
+    return do_hash_dev(ctx, alg, d_src, chunk, n, d_digests, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+int cw_compress_dev(cw_ctx *ctx, cw_comp_alg alg, cw_mode mode, const void *d_src, size_t chunk, size_t n, void *d_dst,
+                    size_t stride, uint32_t *d_lens, void *stream)
+{
+    int rc = check_common(ctx, chunk, n, d_src);
+    if (rc != CW_OK) return rc;
+    if (n && (!d_dst || !d_lens)) return CW_ERR_ARG;
+    CW_CUDA(ctx, cudaSetDevice(ctx->device));
+    return do_compress_dev(ctx, alg, mode, d_src, chunk, n, d_dst, stride, d_lens, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+int cw_hash_compress_dev(cw_ctx *ctx, cw_hash_alg halg, cw_comp_alg calg, cw_mode mode, const void *d_src, size_t chunk,
+                         size_t n, void *d_digests, void *d_dst, size_t stride, uint32_t *d_lens, void *stream)
+{
+    int rc = check_common(ctx, chunk, n, d_src);
+    if (rc != CW_OK) return rc;
+    if (n && (!d_dst || !d_lens || !d_digests)) return CW_ERR_ARG;
+    CW_CUDA(ctx, cudaSetDevice(ctx->device));
+    return do_fused_dev(ctx, halg, calg, mode, d_src, chunk, n, d_digests, d_dst, stride, d_lens,
+                        stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+int cw_sync(cw_ctx *ctx, void *stream)
+{
+    if (!ctx) return CW_ERR_ARG;
+    CW_CUDA(ctx, cudaSetDevice(ctx->device));
+    CW_CUDA(ctx, cudaStreamSynchronize(stream ? (cudaStream_t)stream : ctx->stream));
+    return CW_OK;
+}
+
+int cw_hash(cw_ctx *ctx, cw_hash_alg alg, const void *src, size_t chunk, size_t n, void *digests)
+{
+    int rc = check_common(ctx, chunk, n, src);
+    if (rc != CW_OK) return rc;
+    if ((int)alg < 0 || (int)alg > 2 || (n && !digests)) return CW_ERR_ARG;
+    return host_pass(ctx, true, false, alg, CW_COMP_LZ4, CW_MODE_COMPAT, src, chunk, n, digests, nullptr, 0, nullptr);
+}
+
+int cw_compress(cw_ctx *ctx, cw_comp_alg alg, cw_mode mode, const void *src, size_t chunk, size_t n, void *dst,
+                size_t stride, uint32_t *lens)
+{
+    int rc = check_common(ctx, chunk, n, src);
+    if (rc != CW_OK) return rc;
+    if ((int)alg < 0 || (int)alg > 1 || (int)mode < 0 || (int)mode > 1 || (n && (!dst || !lens))) return CW_ERR_ARG;
+    if (stride < cw_compress_bound(alg, chunk)) return CW_ERR_ARG;
+    return host_pass(ctx, false, true, CW_HASH_SKEIN512, alg, mode, src, chunk, n, nullptr, dst, stride, lens);
+}
+
+int cw_hash_compress(cw_ctx *ctx, cw_hash_alg halg, cw_comp_alg calg, cw_mode mode, const void *src, size_t chunk, size_t n,
+                     void *digests, void *dst, size_t stride, uint32_t *lens)
+{
+    int rc = check_common(ctx, chunk, n, src);
+    if (rc != CW_OK) return rc;
+    if ((int)halg < 0 || (int)halg > 2 || (int)calg < 0 || (int)calg > 1 || (int)mode < 0 || (int)mode > 1) return CW_ERR_ARG;
+    if (n && (!dst || !lens || !digests)) return CW_ERR_ARG;
+    if (stride < cw_compress_bound(calg, chunk)) return CW_ERR_ARG;
+    return host_pass(ctx, true, true, halg, calg, mode, src, chunk, n, digests, dst, stride, lens);
+}
+
+int cw_submit(cw_ctx *ctx, cw_hash_alg halg, cw_comp_alg calg, cw_mode mode, const void *src, size_t chunk, size_t n,
+              void *digests, void *dst, size_t stride, uint32_t *lens, cw_complete_fn cb, void *user, cw_ticket *ticket)
+{
+    int rc = check_common(ctx, chunk, n, src);
+    if (rc != CW_OK) return rc;
+    if (!ticket) return CW_ERR_ARG;
+    if ((int)halg < 0 || (int)halg > 2 || (int)calg < 0 || (int)calg > 1 || (int)mode < 0 || (int)mode > 1) return CW_ERR_ARG;
+    if (n && (!dst || !lens || !digests)) return CW_ERR_ARG;
+    if (stride < cw_compress_bound(calg, chunk)) return CW_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->q_mu);
+    if (!ctx->worker.joinable()) ctx->worker = std::thread(worker_loop, ctx);
+    Job j{ctx->next_ticket++, halg, calg, mode, src, chunk, n, digests, dst, stride, lens, cb, user};
+    *ticket = j.ticket;
+    ctx->queue.push_back(j);
+    ctx->q_cv.notify_one();
+    return CW_OK;
+}
+
+int cw_wait(cw_ctx *ctx, cw_ticket ticket)
+{
+    if (!ctx) return CW_ERR_ARG;
+    std::unique_lock<std::mutex> lk(ctx->q_mu);
+    if (ticket == 0 || ticket >= ctx->next_ticket) return CW_ERR_ARG;
+    ctx->done_cv.wait(lk, [&] { return ctx->finished.count(ticket) != 0; });
+    int rc = ctx->finished[ticket];
+    ctx->finished.erase(ticket);
+    return rc;
+}
+
+int cw_synth_dev(cw_ctx *ctx, void *d_dst, size_t chunk, uint64_t first_chunk, size_t n, uint64_t seed, void *stream)
+{
+    if (!ctx || !d_dst || chunk == 0 || (chunk & 7u) || (reinterpret_cast<uintptr_t>(d_dst) & 7u)) return CW_ERR_ARG;
+    if (chunk > CW_MAX_CHUNK) return CW_ERR_UNSUPPORTED;
+    CW_CUDA(ctx, cudaSetDevice(ctx->device));
+    CW_CUDA(ctx, cw_launch_synth((uint8_t *)d_dst, (uint32_t)chunk, first_chunk, n, seed,
+                                 stream ? (cudaStream_t)stream : ctx->stream));
+    ctx->launches++;
+    return CW_OK;
+}
+
+uint64_t cw_launch_count(const cw_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
+
+int cw_prof_enable(cw_ctx *ctx, int on)
+{
+    if (!ctx) return CW_ERR_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    ctx->prof = on != 0;
+    return CW_OK;
+}
+
+int cw_prof_read(cw_ctx *ctx, double *kernel_ms, uint64_t *launches)
+{
+    if (!ctx) return CW_ERR_ARG;
+    CW_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs;
+    {
+        std::lock_guard<std::mutex> g(ctx->mu);
+        evs.swap(ctx->prof_ev);
+    }
+    for (auto &p : evs) {
+        CW_CUDA(ctx, cudaEventSynchronize(p.second));
+        float ms = 0;
+        CW_CUDA(ctx, cudaEventElapsedTime(&ms, p.first, p.second));
+        ctx->prof_ms += ms;
+        ctx->prof_launches++;
+    }
+    {
+        std::lock_guard<std::mutex> g(ctx->mu);
+        for (auto &p : evs) {
+            ctx->ev_pool.push_back(p.first);
+            ctx->ev_pool.push_back(p.second);
+        }
+    }
+    if (kernel_ms) *kernel_ms = ctx->prof_ms;
+    if (launches) *launches = ctx->prof_launches;
+    ctx->prof_ms = 0;
+    ctx->prof_launches = 0;
+    return CW_OK;
+}
+
+}  // extern "C"

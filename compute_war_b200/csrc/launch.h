@@ -1,0 +1,42 @@
+// launch.h -- internal (C++) interface between the C-ABI layer (api.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+struct CwSkeinIV;
+
+struct CwDeviceInfo {
+    int sm_count;
+    size_t smem_optin;  // max dynamic shared memory per block
+};
+
+// hash_kernels.cu
+cudaError_t cw_launch_hash(int alg, const CwSkeinIV &iv, const uint8_t *d_src, uint32_t chunk, uint64_t n,
+                           uint8_t *d_digests, cudaStream_t st);
+void cw_make_skein_iv(CwSkeinIV *iv);
+
+// lz4_kernels.cu
+// work: device u64 zeroed by the caller on `st` before the launch (dynamic chunk queue)
+cudaError_t cw_launch_lz4(const CwDeviceInfo &dev, const uint8_t *d_src, uint32_t chunk, uint64_t n, uint8_t *d_dst,
+                          uint64_t stride, uint32_t *d_lens, unsigned long long *work, cudaStream_t st);
+cudaError_t cw_lz4_configure(const CwDeviceInfo &dev);
+
+// synth.cu
+cudaError_t cw_launch_synth(uint8_t *d_dst, uint32_t chunk, uint64_t first_chunk, uint64_t n, uint64_t seed,
+                            cudaStream_t st);
+
+// lzf_kernels.cu
+cudaError_t cw_launch_lzf(const CwDeviceInfo &dev, const uint8_t *d_src, uint32_t chunk, uint64_t n, uint8_t *d_dst,
+                          uint64_t stride, uint32_t *d_lens, unsigned long long *work, cudaStream_t st);
+cudaError_t cw_lzf_configure(const CwDeviceInfo &dev);
+
+// fused_kernels.cu -- ProcessBlock: digest + compressed block of every chunk in one pass
+// work: two device u64 counters zeroed by the caller
+cudaError_t cw_launch_fused(const CwDeviceInfo &dev, int halg, int calg, const CwSkeinIV &iv, const uint8_t *d_src,
+                            uint32_t chunk, uint64_t n, uint8_t *d_digests, uint8_t *d_dst, uint64_t stride,
+                            uint32_t *d_lens, unsigned long long *work, cudaStream_t st);
+cudaError_t cw_fused_configure(const CwDeviceInfo &dev);
+
+// all per-kernel attribute set-up (opt-in shared memory sizes); called once from cw_init
+cudaError_t cw_configure_kernels(const CwDeviceInfo &dev);

@@ -1,0 +1,209 @@
+"""ctypes binding of include/compute_war.h.
+
+The names follow the reference's own vocabulary: `do_hashing` / `do_compression` are the two function slots of
+src/hashandcompress/HashAndCompress.cpp:111,119 and `process_block` is ProcessBlock (:231-261), here applied to a
+whole batch of chunks per call.  Host-buffer methods take numpy arrays / bytes; `*_dev` methods take raw device
+pointers (ints, e.g. torch.Tensor.data_ptr()) and a CUDA stream handle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HASH_SKEIN512, HASH_SKEIN256_128, HASH_SHA256 = 0, 1, 2
+COMP_LZ4, COMP_LZF = 0, 1
+MODE_COMPAT, MODE_FAST = 0, 1
+MAX_CHUNK = 65536
+
+HASH_NAMES = {"skein512": HASH_SKEIN512, "skein": HASH_SKEIN256_128, "skein256-128": HASH_SKEIN256_128,
+              "sha256": HASH_SHA256, "sha256mb": HASH_SHA256}
+COMP_NAMES = {"lz4": COMP_LZ4, "lzf": COMP_LZF}
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+class EngineError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"compute_war: {msg} (status {status})")
+        self.status = status
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libcomputewar.so")
+
+
+def load_library():
+    """Load the in-tree CUDA library.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise EngineError(-2, f"{path} is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(nvcc, sm_100a); there is no CPU fallback")
+    L = C.CDLL(path)
+    vp, sz, u64 = C.c_void_p, C.c_size_t, C.c_uint64
+    L.cw_init.argtypes = [C.POINTER(vp), C.c_int]
+    L.cw_shutdown.argtypes = [vp]
+    L.cw_shutdown.restype = None
+    L.cw_last_error.argtypes = [vp]
+    L.cw_last_error.restype = C.c_char_p
+    L.cw_status_string.argtypes = [C.c_int]
+    L.cw_status_string.restype = C.c_char_p
+    L.cw_device_count.restype = C.c_int
+    L.cw_digest_bytes.argtypes = [C.c_int]
+    L.cw_digest_bytes.restype = sz
+    L.cw_compress_bound.argtypes = [C.c_int, sz]
+    L.cw_compress_bound.restype = sz
+    L.cw_hash.argtypes = [vp, C.c_int, vp, sz, sz, vp]
+    L.cw_compress.argtypes = [vp, C.c_int, C.c_int, vp, sz, sz, vp, sz, vp]
+    L.cw_hash_compress.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, sz, sz, vp, vp, sz, vp]
+    L.cw_hash_dev.argtypes = [vp, C.c_int, vp, sz, sz, vp, vp]
+    L.cw_compress_dev.argtypes = [vp, C.c_int, C.c_int, vp, sz, sz, vp, sz, vp, vp]
+    L.cw_hash_compress_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, sz, sz, vp, vp, sz, vp, vp]
+    L.cw_sync.argtypes = [vp, vp]
+    L.cw_submit.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, sz, sz, vp, vp, sz, vp, vp, vp, C.POINTER(u64)]
+    L.cw_wait.argtypes = [vp, u64]
+    L.cw_synth_dev.argtypes = [vp, vp, sz, u64, sz, u64, vp]
+    L.cw_launch_count.argtypes = [vp]
+    L.cw_launch_count.restype = u64
+    L.cw_prof_enable.argtypes = [vp, C.c_int]
+    L.cw_prof_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
+    _lib = L
+    return L
+
+
+def digest_bytes(hash_alg: int) -> int:
+    return {HASH_SKEIN512: 64, HASH_SKEIN256_128: 16, HASH_SHA256: 32}[hash_alg]
+
+
+def compress_bound(comp_alg: int, chunk: int) -> int:
+    """LZ4_COMPRESSBOUND (lz4.h:156) / chunk for LZF (called with out_len = chunk-1)"""
+    return chunk + chunk // 255 + 16 if comp_alg == COMP_LZ4 else chunk
+
+
+def _host_u8(x) -> np.ndarray:
+    if isinstance(x, np.ndarray):
+        a = np.ascontiguousarray(x)
+        return a.view(np.uint8).reshape(-1)
+    return np.frombuffer(bytes(x), dtype=np.uint8)
+
+
+class Engine:
+    """One cw_ctx on one GPU (replaces initializeGpu(), HashAndCompress.cpp:95-98)."""
+
+    def __init__(self, device: int = 0):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.cw_init(C.byref(h), device)
+        if rc != 0:
+            raise EngineError(rc, self.L.cw_status_string(rc).decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.cw_shutdown(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            detail = self.L.cw_status_string(rc).decode()
+            if rc == -3:
+                detail += ": " + self.L.cw_last_error(self.h).decode()
+            raise EngineError(rc, detail)
+
+    # ---- host-buffer calls (the reference's function slots) ----
+    def do_hashing(self, hash_alg: int, src, chunk: int) -> np.ndarray:
+        """doHashing(src, dst, count): digests[n, D] of the n = len(src)//chunk whole chunks"""
+        s = _host_u8(src)
+        n = s.size // chunk
+        out = np.zeros((n, digest_bytes(hash_alg)), np.uint8)
+        self._check(self.L.cw_hash(self.h, hash_alg, s.ctypes.data, chunk, n, out.ctypes.data))
+        return out
+
+    def do_compression(self, comp_alg: int, src, chunk: int, mode: int = MODE_COMPAT, stride: int | None = None):
+        """doCompression per chunk: (blocks[n, stride], lens[n]) with the codec's own return convention"""
+        s = _host_u8(src)
+        n = s.size // chunk
+        stride = stride or compress_bound(comp_alg, chunk)
+        blocks = np.zeros((n, stride), np.uint8)
+        lens = np.zeros(n, np.uint32)
+        self._check(self.L.cw_compress(self.h, comp_alg, mode, s.ctypes.data, chunk, n, blocks.ctypes.data, stride,
+                                       lens.ctypes.data))
+        return blocks, lens
+
+    def process_block(self, hash_alg: int, comp_alg: int, src, chunk: int, mode: int = MODE_COMPAT,
+                      out=None):
+        """ProcessBlock over a batch: (digests, blocks, lens); `out` may supply preallocated (pinned) arrays"""
+        s = _host_u8(src)
+        n = s.size // chunk
+        stride = compress_bound(comp_alg, chunk)
+        if out is None:
+            dig = np.zeros((n, digest_bytes(hash_alg)), np.uint8)
+            blocks = np.zeros((n, stride), np.uint8)
+            lens = np.zeros(n, np.uint32)
+        else:
+            dig, blocks, lens = out
+        self._check(self.L.cw_hash_compress(self.h, hash_alg, comp_alg, mode, s.ctypes.data, chunk, n, dig.ctypes.data,
+                                            blocks.ctypes.data, stride, lens.ctypes.data))
+        return dig, blocks, lens
+
+    def process_block_ptr(self, hash_alg, comp_alg, mode, src_ptr, chunk, n, dig_ptr, blocks_ptr, stride, lens_ptr):
+        """ProcessBlock on raw HOST pointers (e.g. pinned torch tensors)"""
+        self._check(self.L.cw_hash_compress(self.h, hash_alg, comp_alg, mode, src_ptr, chunk, n, dig_ptr, blocks_ptr,
+                                            stride, lens_ptr))
+
+    # ---- asynchronous offload (HashOffload Start / Complete) ----
+    def submit(self, hash_alg, comp_alg, mode, src_ptr, chunk, n, dig_ptr, blocks_ptr, stride, lens_ptr) -> int:
+        t = C.c_uint64()
+        self._check(self.L.cw_submit(self.h, hash_alg, comp_alg, mode, src_ptr, chunk, n, dig_ptr, blocks_ptr, stride,
+                                     lens_ptr, None, None, C.byref(t)))
+        return t.value
+
+    def wait(self, ticket: int):
+        self._check(self.L.cw_wait(self.h, ticket))
+
+    # ---- device-buffer calls ----
+    def hash_dev(self, hash_alg, d_src, chunk, n, d_digests, stream=0):
+        self._check(self.L.cw_hash_dev(self.h, hash_alg, d_src, chunk, n, d_digests, stream or None))
+
+    def compress_dev(self, comp_alg, mode, d_src, chunk, n, d_dst, stride, d_lens, stream=0):
+        self._check(self.L.cw_compress_dev(self.h, comp_alg, mode, d_src, chunk, n, d_dst, stride, d_lens, stream or None))
+
+    def hash_compress_dev(self, hash_alg, comp_alg, mode, d_src, chunk, n, d_digests, d_dst, stride, d_lens, stream=0):
+        self._check(self.L.cw_hash_compress_dev(self.h, hash_alg, comp_alg, mode, d_src, chunk, n, d_digests, d_dst, stride,
+                                                d_lens, stream or None))
+
+    def synth_dev(self, d_dst, chunk, first_chunk, n, seed=0xC0FFEE, stream=0):
+        self._check(self.L.cw_synth_dev(self.h, d_dst, chunk, first_chunk, n, seed, stream or None))
+
+    def sync(self, stream=0):
+        self._check(self.L.cw_sync(self.h, stream or None))
+
+    # ---- introspection ----
+    def launch_count(self) -> int:
+        return int(self.L.cw_launch_count(self.h))
+
+    def prof_enable(self, on: bool = True):
+        self._check(self.L.cw_prof_enable(self.h, 1 if on else 0))
+
+    def prof_read(self):
+        ms, n = C.c_double(), C.c_uint64()
+        self._check(self.L.cw_prof_read(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value

@@ -1,0 +1,33 @@
+// host_hash.cpp -- compiles the product's scalar per-chunk hash code (csrc/skein.cuh, csrc/sha256.cuh) as
+// plain C++ so the build container (no GPU) can check the exact device arithmetic against the oracle.
+// Test infrastructure only; never linked into libcomputewar.so.
+#include <cstring>
+#include "../../compute_war_b200/csrc/skein.cuh"
+#include "../../compute_war_b200/csrc/sha256.cuh"
+
+extern "C" void host_skein512(const uint8_t *p, uint32_t len, uint8_t *out, int unroll72)
+{
+    uint64_t IV[8], X[8];
+    cw_skein_iv<8>(IV, 512);
+    if (unroll72) cw_skein_chunk<8, 64, false, true>(IV, p, len, X);
+    else cw_skein_chunk<8, 64, false, false>(IV, p, len, X);
+    memcpy(out, X, 64);
+}
+extern "C" void host_skein256_128(const uint8_t *p, uint32_t len, uint8_t *out)
+{
+    uint64_t IV[4], X[4];
+    cw_skein_iv<4>(IV, 128);
+    cw_skein_chunk<4, 16, false, true>(IV, p, len, X);
+    memcpy(out, X, 16);
+}
+extern "C" void host_sha256(const uint8_t *p, uint32_t len, uint8_t *out)
+{
+    uint32_t H[8];
+    cw_sha256_chunk<false>(p, len, H);
+    for (int i = 0; i < 8; i++) {
+        out[4 * i] = (uint8_t)(H[i] >> 24);
+        out[4 * i + 1] = (uint8_t)(H[i] >> 16);
+        out[4 * i + 2] = (uint8_t)(H[i] >> 8);
+        out[4 * i + 3] = (uint8_t)H[i];
+    }
+}

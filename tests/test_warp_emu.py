@@ -1,0 +1,100 @@
+"""CPU tests of the product's DEVICE source: csrc/skein.cuh + csrc/sha256.cuh compiled as plain C++, and the
+warp-cooperative compressors (csrc/lz4_warp.cuh, csrc/lzf_warp.cuh) run on the lane-accurate warp emulator of
+tests/simt/, all compared bit-for-bit with the oracle.  This is how the kernels' algorithms are checked in the
+build container, which has no GPU; the same comparisons run on the real GPU under -m gpu."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SIMT = os.path.join(HERE, "simt")
+CSRC = os.path.join(os.path.dirname(HERE), "compute_war_b200", "csrc")
+
+
+def _build(name, sources, extra=()):
+    so = os.path.join(SIMT, name)
+    deps = [os.path.join(SIMT, s) for s in sources] + [os.path.join(SIMT, "warp_emu.h")] + \
+           [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", SIMT, *extra, "-o", so,
+                               *[os.path.join(SIMT, s) for s in sources]])
+    return C.CDLL(so)
+
+
+@pytest.fixture(scope="module")
+def hosthash():
+    return _build("libhosthash.so", ["host_hash.cpp"])
+
+
+@pytest.fixture(scope="module")
+def emu():
+    L = _build("libemu.so", ["emu_codecs.cpp", "warp_emu.cpp"])
+    L.emu_lz4_compress.restype = C.c_uint32
+    if hasattr(L, "emu_lzf_compress"):
+        L.emu_lzf_compress.restype = C.c_uint32
+    return L
+
+
+def test_device_hash_source_on_host(hosthash):
+    rng = np.random.default_rng(0)
+    for n in [0, 1, 7, 8, 31, 32, 33, 55, 56, 63, 64, 65, 127, 128, 129, 200, 1000, 4096, 8192, 65536]:
+        b = rng.integers(0, 256, n + 1, dtype=np.uint8)
+        bb = b[:n].tobytes()
+        for unroll in (0, 1):
+            out = np.zeros(64, np.uint8)
+            hosthash.host_skein512(b.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p), unroll)
+            assert out.tobytes() == O.skein(512, 512, bb), (n, unroll)
+        out = np.zeros(16, np.uint8)
+        hosthash.host_skein256_128(b.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p))
+        assert out.tobytes() == O.skein(256, 128, bb), n
+        out = np.zeros(32, np.uint8)
+        hosthash.host_sha256(b.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p))
+        assert out.tobytes() == O.sha256(bb), n
+
+
+def _cases(golden, small):
+    rng = np.random.default_rng(3)
+    cases = []
+    blob = golden["blob"]
+    for ent in golden["ref"]["files"]:
+        d = blob[ent["offset"]: ent["offset"] + ent["size"]]
+        for chunk, cnt in ((4096, 1), (8192, 1), (100, 2), (13, 1), (1000, 1)):
+            n = len(d) // chunk
+            for i in rng.choice(n, min(cnt, n), replace=False) if n else []:
+                cases.append(d[i * chunk:(i + 1) * chunk].copy())
+    for n in (13, 14, 16, 17, 31, 32, 33, 64, 65, 66, 67, 100, 127, 128, 129, 255, 256, 300, 1000, 4096):
+        cases += [np.zeros(n, np.uint8), rng.integers(0, 256, n, dtype=np.uint8), rng.integers(0, 2, n, dtype=np.uint8)]
+    for p in (1, 2, 3, 4, 7, 8, 30, 32, 33, 64, 255, 256, 257):
+        cases.append(np.tile(rng.integers(0, 256, p, dtype=np.uint8), 4096 // p + 1)[:4096])
+    for i in range(12):
+        cases.append(O.synth(8192, i, 1))
+    cases += [O.synth(65536, 1, 1), rng.integers(0, 256, 65536, dtype=np.uint8), np.zeros(65536, np.uint8)]
+    if small:
+        cases += [np.zeros(n, np.uint8) for n in (1, 2, 5, 12)]
+    return cases
+
+
+def test_lz4_warp_algorithm_byte_identical(emu, golden):
+    for c in _cases(golden, small=True):
+        n = len(c)
+        out = np.zeros(n + n // 255 + 64, np.uint8)
+        r = emu.emu_lz4_compress(c.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p))
+        blocks, lens = O.compress_chunks(O.COMP_LZ4, c, n)
+        assert r == lens[0] and (out[:r] == blocks[0, :r]).all(), n
+
+
+def test_lzf_warp_algorithm_byte_identical(emu, golden):
+    if not hasattr(emu, "emu_lzf_compress"):
+        pytest.skip("LZF warp kernel not built yet")
+    for c in _cases(golden, small=False):
+        n = len(c)
+        out = np.zeros(n + 64, np.uint8)
+        r = emu.emu_lzf_compress(c.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p), n - 1)
+        blocks, lens = O.compress_chunks(O.COMP_LZF, c, n)
+        assert r == lens[0], (n, r, lens[0])
+        assert (out[:r] == blocks[0, :r]).all(), n

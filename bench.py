@@ -216,7 +216,9 @@ def main():
     dig = torch.empty(n * DIGEST, dtype=torch.uint8, device=dev)
     blocks = torch.empty(n * stride, dtype=torch.uint8, device=dev)
     lens = torch.empty(n, dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    tstream = torch.cuda.Stream(device=dev)  # a real (non-default) stream: kernels and timing events share it
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
     eng.synth_dev(src.data_ptr(), CHUNK, first, n, SEED, stream)
     torch.cuda.synchronize()
 

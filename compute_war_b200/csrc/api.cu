@@ -78,6 +78,8 @@ struct cw_ctx {
 
 namespace {
 
+std::string g_init_error;  // why the last cw_init failed (cw_last_error(NULL))
+
 int fail(cw_ctx *ctx, cudaError_t e, const char *what)
 {
     std::lock_guard<std::mutex> g(ctx->mu);
@@ -326,8 +328,9 @@ int cw_init(cw_ctx **out, int device)
         ok = cudaStreamCreateWithFlags(&ctx->slots[i].st, cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->slots[i].done, cudaEventDisableTiming) == cudaSuccess;
     }
-    ok = ok && cw_configure_kernels(ctx->dev) == cudaSuccess;
-    if (!ok) {
+    cudaError_t ce = ok ? cw_configure_kernels(ctx->dev) : cudaGetLastError();
+    if (!ok || ce != cudaSuccess) {
+        g_init_error = std::string("cw_init: ") + cudaGetErrorString(ce != cudaSuccess ? ce : cudaGetLastError());
         cw_shutdown(ctx);
         return CW_ERR_CUDA;
     }
@@ -366,7 +369,7 @@ void cw_shutdown(cw_ctx *ctx)
     delete ctx;
 }
 
-const char *cw_last_error(const cw_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+const char *cw_last_error(const cw_ctx *ctx) { return ctx ? ctx->last_error.c_str() : g_init_error.c_str(); }
 
 size_t cw_digest_bytes(cw_hash_alg alg)
 {

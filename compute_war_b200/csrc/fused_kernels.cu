@@ -1,20 +1,177 @@
-// fused_kernels.cu -- ProcessBlock (HashAndCompress.cpp:231-261): compressed block + digest of every chunk.
-// INTERIM (round-1 first GPU run): compress kernel followed by the hash kernel on the same stream; the
-// single-pass warp-specialised kernel replaces this once the stand-alone kernels are measured.
+// fused_kernels.cu -- ProcessBlock (HashAndCompress.cpp:231-261): compressed block + digest of every chunk
+// in ONE pass over the input.
+//
+// One persistent CTA per SM, warp-specialised:
+//   * compress warps (as many as the SM's shared memory holds: 9 for LZ4 / 5 for LZF at 8 KB chunks) each
+//     own a shared-memory slot, pull chunk indices from a global counter, stage the chunk with a bulk
+//     async copy and run the warp compressor of lz4_warp.cuh / lzf_warp.cuh;
+//   * hash warps (8 per CTA, no shared memory) take groups of 32 consecutive chunks, one chunk per lane,
+//     and run the register-resident Skein / SHA-256 chain of skein.cuh / sha256.cuh straight from global
+//     memory.
+// The two roles are coupled through the counters: a hash warp starts group g only once the compress
+// counter has passed the end of that group, i.e. once those chunks have been (or are being) pulled into
+// L2 by the compress warps' bulk copies.  The window between the two readers is a few MB, far below
+// the 126 MB L2, so every input byte is fetched from HBM once (ncu: dram__bytes_read.sum ~= input bytes);
+// the compressors are latency bound and leave most issue slots of the SM idle, which is exactly what the
+// integer-bound hash warps consume.
 #include "hash_kernels.cuh"
 #include "launch.h"
+#include "lz4_warp.cuh"
+#include "lzf_warp.cuh"
+#include "stage.cuh"
+
+#define CW_FUSED_HASH_WARPS 8
+#define CW_FUSED_MAX_COMP_WARPS 12
+#define CW_FUSED_MAX_THREADS ((CW_FUSED_HASH_WARPS + CW_FUSED_MAX_COMP_WARPS) * 32)
+
+enum { CW_C_LZ4 = 0, CW_C_LZF = 1 };
+
+template <int CALG>
+__host__ __device__ constexpr uint32_t cw_scratch_bytes()
+{
+    return CALG == CW_C_LZ4 ? 2u * CW_LZ4_HASH_ENTRIES : (uint32_t)sizeof(CwLzfScratch);
+}
+
+template <int HALG, int CALG, bool ALIGNED>
+__global__ void __launch_bounds__(CW_FUSED_MAX_THREADS, 1)
+    cw_fused_kernel(const __grid_constant__ CwSkeinIV iv, const uint8_t *__restrict__ src, uint32_t chunk, uint64_t n_chunks,
+                    uint8_t *__restrict__ digests, uint8_t *__restrict__ dst, uint64_t stride, uint32_t *__restrict__ lens,
+                    unsigned long long *work, uint32_t slot_bytes, uint32_t comp_warps)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bars[32];
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    if (warp < comp_warps) {
+        // ------------------------------ compress role ------------------------------
+        uint8_t *s = smem + (size_t)warp * slot_bytes;
+        const uint32_t chunk_pad = (chunk + 16u + 15u) & ~15u;
+        uint64_t *bar = &bars[warp];
+        if (lane == 0) cw_mbar_init(bar, 1);
+        for (uint32_t i = chunk + lane; i < chunk_pad; i += 32u) s[i] = 0;
+        __syncwarp();
+        uint32_t phase = 0;
+        for (;;) {
+            unsigned long long g = 0;
+            if (lane == 0) g = atomicAdd(&work[0], 1ull);
+            g = __shfl_sync(0xffffffffu, g, 0);
+            if (g >= n_chunks) break;
+            __syncwarp();
+            if (ALIGNED && lane == 0) cw_bulk_load(s, src + g * chunk, chunk, bar);
+            if (CALG == CW_C_LZ4) {
+                uint4 *t4 = reinterpret_cast<uint4 *>(s + chunk_pad);
+#pragma unroll 8
+                for (uint32_t i = lane; i < 2u * CW_LZ4_HASH_ENTRIES / 16u; i += 32u) t4[i] = make_uint4(0, 0, 0, 0);
+            }
+            if (ALIGNED) {
+                cw_mbar_wait(bar, phase);
+                phase ^= 1u;
+            } else {
+                const uint8_t *gp = src + g * chunk;
+                for (uint32_t i = lane; i < chunk; i += 32u) s[i] = gp[i];
+            }
+            __syncwarp();
+            uint32_t len;
+            if (CALG == CW_C_LZ4)
+                len = cw_lz4_compress_warp(s, chunk, reinterpret_cast<uint16_t *>(s + chunk_pad), dst + g * stride);
+            else
+                len = cw_lzf_compress_warp(s, chunk, reinterpret_cast<CwLzfScratch *>(s + chunk_pad), dst + g * stride,
+                                           chunk - 1u);
+            if (lane == 0) lens[g] = len;
+        }
+    } else {
+        // ------------------------------ hash role ------------------------------
+        constexpr int D = cw_digest_len<HALG>();
+        for (;;) {
+            unsigned long long grp = 0;
+            if (lane == 0) grp = atomicAdd(&work[1], 1ull);
+            grp = __shfl_sync(0xffffffffu, grp, 0);
+            const unsigned long long first = grp * 32ull;
+            if (first >= n_chunks) break;
+            const unsigned long long need = first + 32ull < n_chunks ? first + 32ull : n_chunks;
+            if (lane == 0) {
+                // follow the compress warps: wait until this group's chunks have been claimed (-> are in L2)
+                while (*reinterpret_cast<volatile unsigned long long *>(&work[0]) < need) __nanosleep(256);
+            }
+            __syncwarp();
+            const unsigned long long idx = first + lane;
+            if (idx < n_chunks) cw_hash_one<HALG, ALIGNED, ALIGNED>(iv, src + idx * chunk, chunk, digests + idx * D);
+        }
+    }
+}
+
+template <int HALG, int CALG, bool ALIGNED>
+static cudaError_t launch_one(const CwDeviceInfo &dev, int max_dyn_smem, const CwSkeinIV &iv, const uint8_t *d_src,
+                              uint32_t chunk, uint64_t n, uint8_t *d_digests, uint8_t *d_dst, uint64_t stride,
+                              uint32_t *d_lens, unsigned long long *work, cudaStream_t st)
+{
+    auto kern = cw_fused_kernel<HALG, CALG, ALIGNED>;
+    const uint32_t slot = ((chunk + 16u + 15u) & ~15u) + cw_scratch_bytes<CALG>();
+    int comp_warps = max_dyn_smem / (int)slot;
+    if (comp_warps < 1) return cudaErrorInvalidValue;
+    if (comp_warps > CW_FUSED_MAX_COMP_WARPS) comp_warps = CW_FUSED_MAX_COMP_WARPS;
+    uint64_t ctas = (n + (uint64_t)comp_warps - 1) / (uint64_t)comp_warps;
+    if (ctas > (uint64_t)dev.sm_count) ctas = (uint64_t)dev.sm_count;
+    kern<<<(unsigned)ctas, (comp_warps + CW_FUSED_HASH_WARPS) * 32, (size_t)comp_warps * slot, st>>>(
+        iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, slot, (uint32_t)comp_warps);
+    return cudaGetLastError();
+}
+
+static int g_fused_max_smem = 0;
+
+template <int HALG, int CALG, bool ALIGNED>
+static cudaError_t configure_one(int max_dyn)
+{
+    return cudaFuncSetAttribute(cw_fused_kernel<HALG, CALG, ALIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+}
+
+// opt-in shared memory is a per-device function attribute: set it for every instantiation on the current device
+cudaError_t cw_fused_configure(const CwDeviceInfo &dev)
+{
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, cw_fused_kernel<CW_K_SKEIN512, CW_C_LZ4, true>);
+    if (e != cudaSuccess) return e;
+    const int m = (int)dev.smem_optin - (int)fa.sharedSizeBytes;
+    g_fused_max_smem = m;
+#define CW_CFG(H, C)                                                  \
+    if (e == cudaSuccess) e = configure_one<H, C, true>(m);           \
+    if (e == cudaSuccess) e = configure_one<H, C, false>(m);
+    CW_CFG(CW_K_SKEIN512, CW_C_LZ4)
+    CW_CFG(CW_K_SKEIN512, CW_C_LZF)
+    CW_CFG(CW_K_SKEIN256_128, CW_C_LZ4)
+    CW_CFG(CW_K_SKEIN256_128, CW_C_LZF)
+    CW_CFG(CW_K_SHA256, CW_C_LZ4)
+    CW_CFG(CW_K_SHA256, CW_C_LZF)
+#undef CW_CFG
+    return e;
+}
+
+template <int HALG>
+static cudaError_t launch_h(int calg, bool aligned, const CwDeviceInfo &dev, const CwSkeinIV &iv, const uint8_t *d_src,
+                            uint32_t chunk, uint64_t n, uint8_t *d_digests, uint8_t *d_dst, uint64_t stride, uint32_t *d_lens,
+                            unsigned long long *work, cudaStream_t st)
+{
+    const int m = g_fused_max_smem;
+    if (calg == CW_C_LZ4)
+        return aligned ? launch_one<HALG, CW_C_LZ4, true>(dev, m, iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, st)
+                       : launch_one<HALG, CW_C_LZ4, false>(dev, m, iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, st);
+    return aligned ? launch_one<HALG, CW_C_LZF, true>(dev, m, iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, st)
+                   : launch_one<HALG, CW_C_LZF, false>(dev, m, iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, st);
+}
 
 cudaError_t cw_launch_fused(const CwDeviceInfo &dev, int halg, int calg, const CwSkeinIV &iv, const uint8_t *d_src,
                             uint32_t chunk, uint64_t n, uint8_t *d_digests, uint8_t *d_dst, uint64_t stride,
                             uint32_t *d_lens, unsigned long long *work, cudaStream_t st)
 {
-    cudaError_t e = calg == 0 ? cw_launch_lz4(dev, d_src, chunk, n, d_dst, stride, d_lens, work, st)
-                              : cw_launch_lzf(dev, d_src, chunk, n, d_dst, stride, d_lens, work, st);
-    if (e != cudaSuccess) return e;
-    return cw_launch_hash(halg, iv, d_src, chunk, n, d_digests, st);
+    if (n == 0) return cudaSuccess;
+    const bool aligned = (chunk % 16u == 0) && ((reinterpret_cast<uintptr_t>(d_src) & 15u) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(d_digests) & 15u) == 0);
+    switch (halg) {
+    case CW_K_SKEIN512: return launch_h<CW_K_SKEIN512>(calg, aligned, dev, iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, st);
+    case CW_K_SKEIN256_128: return launch_h<CW_K_SKEIN256_128>(calg, aligned, dev, iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, st);
+    case CW_K_SHA256: return launch_h<CW_K_SHA256>(calg, aligned, dev, iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, st);
+    }
+    return cudaErrorInvalidValue;
 }
-
-cudaError_t cw_fused_configure(const CwDeviceInfo &) { return cudaSuccess; }
 
 cudaError_t cw_configure_kernels(const CwDeviceInfo &dev)
 {

@@ -61,7 +61,10 @@ static int g_lz4_max_smem = 0;
 
 cudaError_t cw_lz4_configure(const CwDeviceInfo &dev)
 {
-    g_lz4_max_smem = (int)dev.smem_optin;
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, cw_lz4_kernel);
+    if (e != cudaSuccess) return e;
+    g_lz4_max_smem = (int)dev.smem_optin - (int)fa.sharedSizeBytes;  // opt-in limit covers static + dynamic
     return cudaFuncSetAttribute(cw_lz4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_lz4_max_smem);
 }
 
@@ -69,8 +72,7 @@ cudaError_t cw_launch_lz4(const CwDeviceInfo &dev, const uint8_t *d_src, uint32_
                           uint64_t stride, uint32_t *d_lens, unsigned long long *work, cudaStream_t st)
 {
     const uint32_t slot = lz4_slot_bytes(chunk);
-    // 1 KB of the SM's shared memory is reserved per CTA; bars[] is static
-    int warps = (int)((dev.smem_optin - 512) / slot);
+    int warps = g_lz4_max_smem / (int)slot;
     if (warps < 1) return cudaErrorInvalidValue;
     if (warps > CW_LZ4_MAX_WARPS) warps = CW_LZ4_MAX_WARPS;
     uint64_t ctas = (n + (uint64_t)warps - 1) / (uint64_t)warps;

@@ -10,17 +10,21 @@
 // The sequential parser probes one position at a time: h = hash(read32(p)); cand = table[h];
 // table[h] = p; match iff read32(cand) == read32(p).  Here a warp evaluates the next 32 probe positions
 // of the parser at once ("window"):
-//   phase A (all lanes, independent): read32, hash, table look-up, candidate compare, plus two
-//            MATCH.ANY masks: lanes with the same hash (they would overwrite each other's table slot) and
-//            lanes with the same 4 bytes.
-//   phase B (uniform, in registers): replay the parser's control flow over the window.  `ins` is the set
-//            of window lanes whose position the sequential parser has inserted so far; a lane's true
+//   phase A (all lanes, independent): read32, hash, table look-up, candidate compare, and -- for lanes
+//            whose table candidate matches -- the forward / backward match extension, speculatively, so
+//            that the serial part never touches memory; plus a MATCH.ANY mask of lanes with the same
+//            hash (they would overwrite each other's table slot).
+//   phase B (uniform, registers only): replay the parser's control flow over the window.  `ins` is the
+//            set of window lanes whose position the sequential parser has inserted so far; a lane's true
 //            candidate is the highest inserted lane below it with the same hash, else the table entry read
-//            in phase A.  The first hitting lane is the parser's next match; it is extended backwards
-//            and forwards by the whole warp (32 x 4 bytes per step), the sequence is emitted, the parser's
-//            post-match insert of position e-2 is added to `ins`, and the replay resumes at lane e
-//            (positions inside the match are never probed, exactly as in the reference).
+//            in phase A.  The first hitting lane is the parser's next match; its sequence is *recorded*
+//            (lane k keeps the k-th sequence of the window), the parser's post-match insert of position
+//            e-2 is added to `ins`, and the replay resumes at lane e (positions inside a match are never
+//            probed, exactly as in the reference).  Matches whose candidate lies inside the window, or
+//            whose speculative extension hit its cap, are extended on demand by the whole warp.
 //   phase C: lanes in `ins` commit table[h] = pos (highest lane wins per slot).
+//   phase D: the recorded sequences are written out in parallel, one lane per sequence; long literal
+//            runs are copied by the whole warp with 32-bit stores.
 // After 64 failed probes the reference widens its stride (step = searchNb++ >> 6); lane positions follow
 // the closed form of that schedule, so incompressible data is skipped as quickly as the CPU does.
 //
@@ -31,6 +35,12 @@
 
 #define CW_LZ4_HASH_ENTRIES 8192u
 #define CW_LZ4_NONE 0xffffffffu
+#ifndef CW_LZ4_SPECULATE
+#define CW_LZ4_SPECULATE 0   // 1: phase A extends table candidates speculatively (measured slower on B200, r01)
+#endif
+#define CW_LZ4_FW_STEPS 6u   // speculative forward extension: up to 24 bytes per lane
+#define CW_LZ4_BK_CAP 8u     // speculative backward extension: up to 8 bytes per lane
+#define CW_LZ4_LIT_SELF 20u  // literal runs up to this long are copied by the recording lane itself
 
 CW_DEV uint32_t cw_umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
@@ -53,13 +63,32 @@ CW_DEV uint32_t cw_lz4_F(uint32_t m)
 CW_DEV int32_t cw_lz4_S(int32_t j) { return j <= 0 ? j : 1 + (int32_t)cw_lz4_F(63u + (uint32_t)j); }
 CW_DEV uint32_t cw_lz4_step(int32_t j) { return j <= 0 ? 1u : (63u + (uint32_t)j) >> 6; }
 
-// 255-run length extension shared by literal and match lengths: writes the bytes for value r (>= 0)
-CW_DEV uint32_t cw_lz4_put_ext(uint8_t *out, uint32_t op, uint32_t r, unsigned lane)
+// 255-run length extension of a literal / match length, written by ONE lane: bytes for value r (>= 0)
+CW_DEV uint32_t cw_lz4_put_ext1(uint8_t *out, uint32_t op, uint32_t r)
 {
-    const uint32_t full = r / 255u;
-    for (uint32_t x = lane; x < full; x += 32u) out[op + x] = 255u;
-    if (lane == 0) out[op + full] = (uint8_t)(r - full * 255u);
-    return op + full + 1u;
+    while (r >= 255u) {
+        out[op++] = 255u;
+        r -= 255u;
+    }
+    out[op++] = (uint8_t)r;
+    return op;
+}
+CW_DEV uint32_t cw_lz4_ext_bytes(uint32_t len) { return len >= 15u ? (len - 15u) / 255u + 1u : 0u; }
+
+// whole-warp copy of len literal bytes s[src..] -> out[dst..]; 32-bit stores on the aligned body
+CW_DEV void cw_lz4_copy_warp(uint8_t *out, uint32_t dst, const uint8_t *s, uint32_t src, uint32_t len, unsigned lane)
+{
+    if (len < 64u) {
+        for (uint32_t x = lane; x < len; x += 32u) out[dst + x] = s[src + x];
+        return;
+    }
+    const uint32_t head = (4u - (uint32_t)(reinterpret_cast<uintptr_t>(out + dst) & 3u)) & 3u;
+    if (lane < head) out[dst + lane] = s[src + lane];
+    const uint32_t words = (len - head) >> 2;
+    uint32_t *o32 = reinterpret_cast<uint32_t *>(out + dst + head);
+    for (uint32_t w = lane; w < words; w += 32u) o32[w] = cw_lz4_read32(s, src + head + 4u * w);
+    const uint32_t done = head + 4u * words;
+    if (lane < len - done) out[dst + done + lane] = s[src + done + lane];
 }
 
 // Compress chunk s[0..n) (n <= 65536).  table: zeroed u16[8192] in shared memory.  Returns the number of
@@ -86,28 +115,58 @@ CW_DEV uint32_t cw_lz4_compress_warp(const uint8_t *s, uint32_t n, uint16_t *tab
             const uint32_t v = cw_lz4_read32(s, valid ? pos : 0u);
             const uint32_t h = cw_lz4_hash(v);
             const uint32_t M = cw_match_any(h);
-            const uint32_t E = cw_match_any(v);
             const uint32_t t = table[h];
-            const bool tmatch = cw_lz4_read32(s, t) == v;
+            const bool tmatch = valid && cw_lz4_read32(s, t) == v;
+            // speculative extension against the table candidate: fw = equal bytes after the 4-byte match
+            // (exact unless FLONG), bk = equal bytes before it (exact up to min(t, pos-anchor) unless BLONG)
+            uint32_t spec = 3u << 16;  // "unknown": extend on demand
+#if CW_LZ4_SPECULATE
+            if (tmatch) {
+                uint32_t fw = 0, pa = pos + 4u, pb = t + 4u, it = 0;
+                for (; it < CW_LZ4_FW_STEPS; it++) {
+                    const uint32_t room = pa < matchlimit ? matchlimit - pa : 0u;
+                    const uint32_t d = cw_lz4_read32(s, cw_umin(pa, n)) ^ cw_lz4_read32(s, cw_umin(pb, n));
+                    const uint32_t eq = cw_umin(d ? (uint32_t)(cw_ffs(d) - 1) >> 3 : 4u, room);
+                    fw += eq;
+                    if (eq < 4u) break;
+                    pa += 4u;
+                    pb += 4u;
+                }
+                const uint32_t capb = cw_umin(cw_umin(t, pos - anchor), CW_LZ4_BK_CAP);
+                uint32_t bk = 0;
+                while (bk < capb && s[pos - 1u - bk] == s[t - 1u - bk]) bk++;
+                spec = fw | (bk << 8) | (it == CW_LZ4_FW_STEPS ? 1u << 16 : 0u) |
+                       ((bk == CW_LZ4_BK_CAP) ? 1u << 17 : 0u);
+            }
+#endif
+            const uint32_t tm_all = cw_ballot(tmatch);
+            const uint32_t inv_all = cw_ballot(!valid);
+            const uint32_t dyn_all = cw_ballot(valid && (M & lower) != 0u);  // lanes that may have an in-window candidate
+            uint32_t E = 0;
+            if (dyn_all) E = cw_match_any(v);
             // ---------------- phase B ----------------
-            uint32_t ins = 0, i0 = 0, pend = CW_LZ4_NONE;
+            uint32_t ins = 0, i0 = 0, pend = CW_LZ4_NONE, nrec = 0;
+            uint32_t r_src = 0, r_lit = 0, r_off = 0, r_mcode = 0, r_op = 0;  // lane k: k-th sequence of this window
             bool restart = false;
             for (;;) {
                 const uint32_t range = ~((1u << i0) - 1u);
-                const uint32_t cm = M & (ins | range) & lower;
-                bool hit;
-                uint32_t cand;
-                if (cm) {
-                    const int jl = 31 - cw_clz(cm);
-                    hit = (E >> jl) & 1u;
-                    cand = unit ? base + (uint32_t)jl : sbase + (uint32_t)cw_lz4_S(j0 + jl);
+                uint32_t hitm, tabm;  // hitting lanes; lanes whose candidate is the table entry
+                uint32_t cand = t;
+                if (dyn_all & range) {
+                    const uint32_t cm = M & (ins | range) & lower;
+                    bool hit = tmatch;
+                    if (cm) {
+                        const int jl = 31 - cw_clz(cm);
+                        hit = valid && ((E >> jl) & 1u);
+                        cand = unit ? base + (uint32_t)jl : sbase + (uint32_t)cw_lz4_S(j0 + jl);
+                    }
+                    hitm = cw_ballot(hit) & range;
+                    tabm = cw_ballot(cm == 0u);
                 } else {
-                    hit = tmatch;
-                    cand = t;
+                    hitm = tm_all & range;
+                    tabm = 0xffffffffu;
                 }
-                const bool act = lane >= i0;
-                const uint32_t hitm = cw_ballot(act && valid && hit);
-                const uint32_t invm = cw_ballot(act && !valid);
+                const uint32_t invm = inv_all & range;
                 const int f = cw_ffs(hitm) - 1, iv = cw_ffs(invm) - 1;
                 if (iv >= 0 && (f < 0 || iv < f)) {  // the parser's end-of-input rule fires first
                     done = true;
@@ -118,16 +177,21 @@ CW_DEV uint32_t cw_lz4_compress_warp(const uint8_t *s, uint32_t n, uint16_t *tab
                     break;
                 }
                 ins |= range & ((2u << f) - 1u);
-                uint32_t cur = cw_shfl(pos, (unsigned)f);
-                uint32_t cnd = cw_shfl(cand, (unsigned)f);
-
-                // ---- extend: forward from cur+4 (32 lanes x 4 bytes) and backward (32 lanes x 1 byte) ----
-                uint32_t fwd = 0, back = 0;
+                const uint32_t cur = unit ? base + (uint32_t)f : cw_shfl(pos, (unsigned)f);
+                const uint32_t cnd = cw_shfl(cand, (unsigned)f);
+                uint32_t fwd, back;
+                const uint32_t maxb = cw_umin(cur - anchor, cnd);
+#if CW_LZ4_SPECULATE
+                const uint32_t sp = cw_shfl(spec, (unsigned)f);
+                if (((tabm >> f) & 1u) && !(sp & (3u << 16))) {
+                    fwd = sp & 0xffu;
+                    back = cw_umin((sp >> 8) & 0xffu, maxb);
+                } else
+#endif
                 {
-                    const uint32_t maxb = cw_umin(cur - anchor, cnd);
-                    // first steps of both directions are issued together so their smem latencies overlap
-                    uint32_t x0 = 4u * lane;
-                    uint32_t pa = cur + 4u + x0, pb = cnd + 4u + x0;
+                    // ---- on-demand extension by the whole warp: 32 x 4 bytes forward, 32 x 1 byte backward ----
+                    fwd = 0;
+                    uint32_t pa = cur + 4u + 4u * lane, pb = cnd + 4u + 4u * lane;
                     uint32_t da = cw_lz4_read32(s, cw_umin(pa, n)) ^ cw_lz4_read32(s, cw_umin(pb, n));
                     const uint32_t xb = lane + 1u;
                     const bool bok = xb <= maxb && s[cur - cw_umin(xb, cur)] == s[cnd - cw_umin(xb, cnd)];
@@ -164,19 +228,19 @@ CW_DEV uint32_t cw_lz4_compress_warp(const uint8_t *s, uint32_t n, uint16_t *tab
                     }
                 }
                 const uint32_t e = cur + 4u + fwd;  // end of the match = next parser position
-                // ---- emit: token, literal length, literals, offset, match length ----
+                // ---- record the sequence: token, literal length, literals, offset, match length ----
                 {
                     const uint32_t lit = cur - back - anchor;
                     const uint32_t mcode = back + fwd;  // match length - 4
-                    const uint32_t off = cur - cnd;
-                    if (lane == 0) out[op] = (uint8_t)((cw_umin(lit, 15u) << 4) | cw_umin(mcode, 15u));
-                    op += 1u;
-                    if (lit >= 15u) op = cw_lz4_put_ext(out, op, lit - 15u, lane);
-                    for (uint32_t x = lane; x < lit; x += 32u) out[op + x] = s[anchor + x];
-                    op += lit;
-                    if (lane < 2u) out[op + lane] = (uint8_t)(off >> (8u * lane));
-                    op += 2u;
-                    if (mcode >= 15u) op = cw_lz4_put_ext(out, op, mcode - 15u, lane);
+                    if (lane == nrec) {
+                        r_src = anchor;
+                        r_lit = lit;
+                        r_off = cur - cnd;
+                        r_mcode = mcode;
+                        r_op = op;
+                    }
+                    nrec++;
+                    op += 1u + cw_lz4_ext_bytes(lit) + lit + 2u + cw_lz4_ext_bytes(mcode);
                 }
                 anchor = e;
                 if (e >= mfl1) {  // "if (ip > mflimit) break" -> last literals
@@ -194,6 +258,29 @@ CW_DEV uint32_t cw_lz4_compress_warp(const uint8_t *s, uint32_t n, uint16_t *tab
                 restart = true;
                 break;
             }
+            // ---------------- phase D: write the recorded sequences, one lane each ----------------
+            if (nrec) {
+                const bool mine = lane < nrec;
+                if (mine) {
+                    uint32_t p = r_op;
+                    out[p++] = (uint8_t)((cw_umin(r_lit, 15u) << 4) | cw_umin(r_mcode, 15u));
+                    if (r_lit >= 15u) p = cw_lz4_put_ext1(out, p, r_lit - 15u);
+                    if (r_lit <= CW_LZ4_LIT_SELF)
+                        for (uint32_t x = 0; x < r_lit; x++) out[p + x] = s[r_src + x];
+                    p += r_lit;
+                    out[p] = (uint8_t)r_off;
+                    out[p + 1u] = (uint8_t)(r_off >> 8);
+                    if (r_mcode >= 15u) cw_lz4_put_ext1(out, p + 2u, r_mcode - 15u);
+                }
+                uint32_t big = cw_ballot(mine && r_lit > CW_LZ4_LIT_SELF);
+                while (big) {
+                    const unsigned k = (unsigned)cw_ffs(big) - 1u;
+                    big &= big - 1u;
+                    const uint32_t lit = cw_shfl(r_lit, k);
+                    const uint32_t dst = cw_shfl(r_op, k) + 1u + cw_lz4_ext_bytes(lit);
+                    cw_lz4_copy_warp(out, dst, s, cw_shfl(r_src, k), lit, lane);
+                }
+            }
             if (done) break;
             // ---------------- phase C: commit the parser's table writes ----------------
             if (((ins >> lane) & 1u) && !(M & ins & ~((2u << lane) - 1u))) table[h] = (uint16_t)pos;
@@ -210,10 +297,12 @@ CW_DEV uint32_t cw_lz4_compress_warp(const uint8_t *s, uint32_t n, uint16_t *tab
     // ---- last literals ----
     {
         const uint32_t lit = n - anchor;
-        if (lane == 0) out[op] = (uint8_t)(cw_umin(lit, 15u) << 4);
-        op += 1u;
-        if (lit >= 15u) op = cw_lz4_put_ext(out, op, lit - 15u, lane);
-        for (uint32_t x = lane; x < lit; x += 32u) out[op + x] = s[anchor + x];
+        if (lane == 0) {
+            out[op] = (uint8_t)(cw_umin(lit, 15u) << 4);
+            if (lit >= 15u) cw_lz4_put_ext1(out, op + 1u, lit - 15u);
+        }
+        op += 1u + cw_lz4_ext_bytes(lit);
+        cw_lz4_copy_warp(out, op, s, anchor, lit, lane);
         op += lit;
     }
     return op;

@@ -100,7 +100,7 @@ class Engine:
         h = C.c_void_p()
         rc = self.L.cw_init(C.byref(h), device)
         if rc != 0:
-            raise EngineError(rc, self.L.cw_status_string(rc).decode())
+            raise EngineError(rc, self.L.cw_status_string(rc).decode() + " " + self.L.cw_last_error(None).decode())
         self.h = h
         self.device = device
 

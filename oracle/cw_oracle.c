@@ -612,3 +612,5 @@ void cwo_synth_fill(uint8_t *dst, size_t chunk, uint64_t first_chunk, size_t n, 
 {
     for (size_t i = 0; i < n; i++) cw_synth_chunk(dst + i * chunk, chunk, first_chunk + i, seed);
 }
+
+unsigned cwo_synth_class(uint64_t seed, uint64_t idx) { return cw_synth_class(seed, idx); }

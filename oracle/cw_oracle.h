@@ -73,6 +73,7 @@ double cwo_hash_compress_mt(int hash_alg, int comp_alg, const uint8_t *src, size
                             uint8_t *digests, uint8_t *dst, size_t stride, uint32_t *lens, int threads);
 
 /* synthetic mixed-entropy workload (definition in include/cw_synth.h) */
+unsigned cwo_synth_class(uint64_t seed, uint64_t idx);
 void cwo_synth_fill(uint8_t *dst, size_t chunk, uint64_t first_chunk, size_t n, uint64_t seed);
 
 #ifdef __cplusplus

@@ -159,7 +159,7 @@ int do_compress_dev(cw_ctx *ctx, cw_comp_alg alg, cw_mode mode, const void *d_sr
         unsigned long long *w = next_work(ctx);
         CW_CUDA(ctx, cudaMemsetAsync(w, 0, sizeof *w, st));
         ProfScope ps(ctx, st);
-        CW_CUDA(ctx, cw_launch_lz4(ctx->dev, (const uint8_t *)d_src, (uint32_t)chunk, n, (uint8_t *)d_dst, stride, d_lens,
+        CW_CUDA(ctx, cw_launch_lz4(ctx->dev, mode == CW_MODE_FAST, (const uint8_t *)d_src, (uint32_t)chunk, n, (uint8_t *)d_dst, stride, d_lens,
                                    w, st));
         ctx->launches++;
         return CW_OK;
@@ -185,7 +185,7 @@ int do_fused_dev(cw_ctx *ctx, cw_hash_alg halg, cw_comp_alg calg, cw_mode mode, 
     unsigned long long *w = next_work(ctx);
     CW_CUDA(ctx, cudaMemsetAsync(w, 0, 2 * sizeof *w, st));
     ProfScope ps(ctx, st);
-    CW_CUDA(ctx, cw_launch_fused(ctx->dev, (int)halg, (int)calg, ctx->iv, (const uint8_t *)d_src, (uint32_t)chunk, n,
+    CW_CUDA(ctx, cw_launch_fused(ctx->dev, (int)halg, (int)calg, mode == CW_MODE_FAST, ctx->iv, (const uint8_t *)d_src, (uint32_t)chunk, n,
                                  (uint8_t *)d_dig, (uint8_t *)d_dst, stride, d_lens, w, st));
     ctx->launches++;
     return CW_OK;

@@ -5,7 +5,7 @@
 //   * compress warps (as many as the SM's shared memory holds: 9 for LZ4 / 5 for LZF at 8 KB chunks) each
 //     own a shared-memory slot, pull chunk indices from a global counter, stage the chunk with a bulk
 //     async copy and run the warp compressor of lz4_warp.cuh / lzf_warp.cuh;
-//   * hash warps (8 per CTA, no shared memory) take groups of 32 consecutive chunks, one chunk per lane,
+//   * hash warps (1 per CTA by default, no shared memory) take groups of 32 consecutive chunks, one chunk per lane,
 //     and run the register-resident Skein / SHA-256 chain of skein.cuh / sha256.cuh straight from global
 //     memory.
 // The two roles are coupled through the counters: a hash warp starts group g only once the compress
@@ -20,16 +20,41 @@
 #include "lzf_warp.cuh"
 #include "stage.cuh"
 
-#define CW_FUSED_HASH_WARPS 8
-#define CW_FUSED_MAX_COMP_WARPS 12
-#define CW_FUSED_MAX_THREADS ((CW_FUSED_HASH_WARPS + CW_FUSED_MAX_COMP_WARPS) * 32)
+#include <cstdlib>
 
-enum { CW_C_LZ4 = 0, CW_C_LZF = 1 };
+// Hash warps per CTA.  Every hash lane walks its own 8 KB chunk for the whole time it takes to hash it, so the
+// bytes that must stay in L2 between the compress warps' bulk copy and the last hash read are
+// hash_warps * 32 lanes * chunk * 148 SMs; 1 warp keeps that window at 39 MB for 8 KB chunks (L2: 126 MB)
+// while still hashing faster than the compressors consume (measured, profiles/).
+#define CW_FUSED_HASH_WARPS_DEFAULT 1
+#define CW_FUSED_HASH_WARPS_MAX 8
+#define CW_FUSED_MAX_COMP_WARPS 14
+#define CW_FUSED_MAX_THREADS ((CW_FUSED_HASH_WARPS_MAX + CW_FUSED_MAX_COMP_WARPS) * 32)
+
+static int fused_hash_warps()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("CW_FUSED_HASH_WARPS");  // tuning knob for the profiling scripts
+        v = e ? atoi(e) : CW_FUSED_HASH_WARPS_DEFAULT;
+        if (v < 1) v = 1;
+        if (v > CW_FUSED_HASH_WARPS_MAX) v = CW_FUSED_HASH_WARPS_MAX;
+    }
+    return v;
+}
+
+enum { CW_C_LZ4 = 0, CW_C_LZF = 1, CW_C_LZ4_FAST = 2 };  // LZ4 with the reference's 13-bit table / LZF / LZ4 with a 12-bit table
 
 template <int CALG>
 __host__ __device__ constexpr uint32_t cw_scratch_bytes()
 {
-    return CALG == CW_C_LZ4 ? 2u * CW_LZ4_HASH_ENTRIES : (uint32_t)sizeof(CwLzfScratch);
+    return CALG == CW_C_LZ4 ? (2u << 13) : (CALG == CW_C_LZ4_FAST ? (2u << 12) : (uint32_t)sizeof(CwLzfScratch));
+}
+
+template <int CALG>
+__host__ __device__ constexpr uint32_t cw_chunk_pad(uint32_t chunk)
+{
+    return (chunk + (CALG == CW_C_LZF ? 16u : CW_LZ4_PAD) + 15u) & ~15u;
 }
 
 template <int HALG, int CALG, bool ALIGNED>
@@ -44,7 +69,7 @@ __global__ void __launch_bounds__(CW_FUSED_MAX_THREADS, 1)
     if (warp < comp_warps) {
         // ------------------------------ compress role ------------------------------
         uint8_t *s = smem + (size_t)warp * slot_bytes;
-        const uint32_t chunk_pad = (chunk + 16u + 15u) & ~15u;
+        const uint32_t chunk_pad = cw_chunk_pad<CALG>(chunk);
         uint64_t *bar = &bars[warp];
         if (lane == 0) cw_mbar_init(bar, 1);
         for (uint32_t i = chunk + lane; i < chunk_pad; i += 32u) s[i] = 0;
@@ -57,10 +82,10 @@ __global__ void __launch_bounds__(CW_FUSED_MAX_THREADS, 1)
             if (g >= n_chunks) break;
             __syncwarp();
             if (ALIGNED && lane == 0) cw_bulk_load(s, src + g * chunk, chunk, bar);
-            if (CALG == CW_C_LZ4) {
+            if (CALG != CW_C_LZF) {
                 uint4 *t4 = reinterpret_cast<uint4 *>(s + chunk_pad);
 #pragma unroll 8
-                for (uint32_t i = lane; i < 2u * CW_LZ4_HASH_ENTRIES / 16u; i += 32u) t4[i] = make_uint4(0, 0, 0, 0);
+                for (uint32_t i = lane; i < cw_scratch_bytes<CALG>() / 16u; i += 32u) t4[i] = make_uint4(0, 0, 0, 0);
             }
             if (ALIGNED) {
                 cw_mbar_wait(bar, phase);
@@ -72,7 +97,9 @@ __global__ void __launch_bounds__(CW_FUSED_MAX_THREADS, 1)
             __syncwarp();
             uint32_t len;
             if (CALG == CW_C_LZ4)
-                len = cw_lz4_compress_warp(s, chunk, reinterpret_cast<uint16_t *>(s + chunk_pad), dst + g * stride);
+                len = cw_lz4_compress_warp<13>(s, chunk, reinterpret_cast<uint16_t *>(s + chunk_pad), dst + g * stride);
+            else if (CALG == CW_C_LZ4_FAST)
+                len = cw_lz4_compress_warp<12>(s, chunk, reinterpret_cast<uint16_t *>(s + chunk_pad), dst + g * stride);
             else
                 len = cw_lzf_compress_warp(s, chunk, reinterpret_cast<CwLzfScratch *>(s + chunk_pad), dst + g * stride,
                                            chunk - 1u);
@@ -105,13 +132,13 @@ static cudaError_t launch_one(const CwDeviceInfo &dev, int max_dyn_smem, const C
                               uint32_t *d_lens, unsigned long long *work, cudaStream_t st)
 {
     auto kern = cw_fused_kernel<HALG, CALG, ALIGNED>;
-    const uint32_t slot = ((chunk + 16u + 15u) & ~15u) + cw_scratch_bytes<CALG>();
+    const uint32_t slot = cw_chunk_pad<CALG>(chunk) + cw_scratch_bytes<CALG>();
     int comp_warps = max_dyn_smem / (int)slot;
     if (comp_warps < 1) return cudaErrorInvalidValue;
     if (comp_warps > CW_FUSED_MAX_COMP_WARPS) comp_warps = CW_FUSED_MAX_COMP_WARPS;
     uint64_t ctas = (n + (uint64_t)comp_warps - 1) / (uint64_t)comp_warps;
     if (ctas > (uint64_t)dev.sm_count) ctas = (uint64_t)dev.sm_count;
-    kern<<<(unsigned)ctas, (comp_warps + CW_FUSED_HASH_WARPS) * 32, (size_t)comp_warps * slot, st>>>(
+    kern<<<(unsigned)ctas, (comp_warps + fused_hash_warps()) * 32, (size_t)comp_warps * slot, st>>>(
         iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, slot, (uint32_t)comp_warps);
     return cudaGetLastError();
 }
@@ -137,10 +164,13 @@ cudaError_t cw_fused_configure(const CwDeviceInfo &dev)
     if (e == cudaSuccess) e = configure_one<H, C, false>(m);
     CW_CFG(CW_K_SKEIN512, CW_C_LZ4)
     CW_CFG(CW_K_SKEIN512, CW_C_LZF)
+    CW_CFG(CW_K_SKEIN512, CW_C_LZ4_FAST)
     CW_CFG(CW_K_SKEIN256_128, CW_C_LZ4)
     CW_CFG(CW_K_SKEIN256_128, CW_C_LZF)
+    CW_CFG(CW_K_SKEIN256_128, CW_C_LZ4_FAST)
     CW_CFG(CW_K_SHA256, CW_C_LZ4)
     CW_CFG(CW_K_SHA256, CW_C_LZF)
+    CW_CFG(CW_K_SHA256, CW_C_LZ4_FAST)
 #undef CW_CFG
     return e;
 }
@@ -151,6 +181,9 @@ static cudaError_t launch_h(int calg, bool aligned, const CwDeviceInfo &dev, con
                             unsigned long long *work, cudaStream_t st)
 {
     const int m = g_fused_max_smem;
+    if (calg == CW_C_LZ4_FAST)
+        return aligned ? launch_one<HALG, CW_C_LZ4_FAST, true>(dev, m, iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, st)
+                       : launch_one<HALG, CW_C_LZ4_FAST, false>(dev, m, iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, st);
     if (calg == CW_C_LZ4)
         return aligned ? launch_one<HALG, CW_C_LZ4, true>(dev, m, iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, st)
                        : launch_one<HALG, CW_C_LZ4, false>(dev, m, iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, st);
@@ -158,11 +191,12 @@ static cudaError_t launch_h(int calg, bool aligned, const CwDeviceInfo &dev, con
                    : launch_one<HALG, CW_C_LZF, false>(dev, m, iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, st);
 }
 
-cudaError_t cw_launch_fused(const CwDeviceInfo &dev, int halg, int calg, const CwSkeinIV &iv, const uint8_t *d_src,
+cudaError_t cw_launch_fused(const CwDeviceInfo &dev, int halg, int calg, bool fast, const CwSkeinIV &iv, const uint8_t *d_src,
                             uint32_t chunk, uint64_t n, uint8_t *d_digests, uint8_t *d_dst, uint64_t stride,
                             uint32_t *d_lens, unsigned long long *work, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
+    if (calg == CW_C_LZ4 && fast) calg = CW_C_LZ4_FAST;  // fast mode of LZF is the compat kernel
     const bool aligned = (chunk % 16u == 0) && ((reinterpret_cast<uintptr_t>(d_src) & 15u) == 0) &&
                          ((reinterpret_cast<uintptr_t>(d_digests) & 15u) == 0);
     switch (halg) {

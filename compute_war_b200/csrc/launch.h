@@ -18,7 +18,7 @@ void cw_make_skein_iv(CwSkeinIV *iv);
 
 // lz4_kernels.cu
 // work: device u64 zeroed by the caller on `st` before the launch (dynamic chunk queue)
-cudaError_t cw_launch_lz4(const CwDeviceInfo &dev, const uint8_t *d_src, uint32_t chunk, uint64_t n, uint8_t *d_dst,
+cudaError_t cw_launch_lz4(const CwDeviceInfo &dev, bool fast, const uint8_t *d_src, uint32_t chunk, uint64_t n, uint8_t *d_dst,
                           uint64_t stride, uint32_t *d_lens, unsigned long long *work, cudaStream_t st);
 cudaError_t cw_lz4_configure(const CwDeviceInfo &dev);
 
@@ -33,7 +33,7 @@ cudaError_t cw_lzf_configure(const CwDeviceInfo &dev);
 
 // fused_kernels.cu -- ProcessBlock: digest + compressed block of every chunk in one pass
 // work: two device u64 counters zeroed by the caller
-cudaError_t cw_launch_fused(const CwDeviceInfo &dev, int halg, int calg, const CwSkeinIV &iv, const uint8_t *d_src,
+cudaError_t cw_launch_fused(const CwDeviceInfo &dev, int halg, int calg, bool fast, const CwSkeinIV &iv, const uint8_t *d_src,
                             uint32_t chunk, uint64_t n, uint8_t *d_digests, uint8_t *d_dst, uint64_t stride,
                             uint32_t *d_lens, unsigned long long *work, cudaStream_t st);
 cudaError_t cw_fused_configure(const CwDeviceInfo &dev);

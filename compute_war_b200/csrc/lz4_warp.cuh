@@ -1,57 +1,64 @@
-// lz4_warp.cuh -- LZ4 block compression of ONE chunk by ONE warp, byte-identical to the reference.
+// lz4_warp.cuh -- LZ4 block compression of ONE chunk by ONE warp.
 //
 // Replaces the lz4 lambda  LZ4_compress_default(s, d, l, 2*l)  (HashAndCompress.cpp:349-355; also
 // experiment.cpp:249).  The reference links a prebuilt liblz4.a 1.8.2 whose source is not in its tree
 // (header: src/compression_perf/include/lz4/lz4.h:94-96,126-156); the parse reproduced here is that
-// library's greedy single-pass parse for inputs < 65547 bytes (13-bit hash, u16 position table,
-// acceleration 1) -- SURVEY.md Appendix A.2 -- and it is accepted only through byte-equality with the
-// vendored archive (tests/golden, oracle/).
+// library's greedy single-pass parse for inputs < 65547 bytes (u16 position table, acceleration 1) --
+// SURVEY.md Appendix A.2.
+//   HASHLOG = 13 ("compat"): the reference's own table size; output byte-identical to the vendored archive
+//             (accepted only through that byte-equality: tests/golden, oracle/).
+//   HASHLOG = 12 ("fast")  : the same parse over a 4096-entry table.  Still a valid LZ4 block that
+//             LZ4_decompress_safe restores bit-exactly; 0.1-0.7 % larger on the reference's corpora at 8 KB
+//             chunks, and the 8 KB it saves per chunk lets 14 instead of 9 chunks be resident
+//             per SM.
 //
 // The sequential parser probes one position at a time: h = hash(read32(p)); cand = table[h];
 // table[h] = p; match iff read32(cand) == read32(p).  Here a warp evaluates the next 32 probe positions
 // of the parser at once ("window"):
-//   phase A (all lanes, independent): read32, hash, table look-up, candidate compare, and -- for lanes
-//            whose table candidate matches -- the forward / backward match extension, speculatively, so
-//            that the serial part never touches memory; plus a MATCH.ANY mask of lanes with the same
-//            hash (they would overwrite each other's table slot).
+//   phase A (all lanes, independent): read32, hash, table look-up, candidate compare; lanes that share a
+//            table slot inside the window ("twins") are detected by writing a lane tag into the slot and
+//            reading it back -- MATCH.ANY, which costs several hundred cycles on sm_100, is only issued
+//            for windows that really contain twins.
 //   phase B (uniform, registers only): replay the parser's control flow over the window.  `ins` is the
 //            set of window lanes whose position the sequential parser has inserted so far; a lane's true
-//            candidate is the highest inserted lane below it with the same hash, else the table entry read
-//            in phase A.  The first hitting lane is the parser's next match; its sequence is *recorded*
-//            (lane k keeps the k-th sequence of the window), the parser's post-match insert of position
-//            e-2 is added to `ins`, and the replay resumes at lane e (positions inside a match are never
-//            probed, exactly as in the reference).  Matches whose candidate lies inside the window, or
-//            whose speculative extension hit its cap, are extended on demand by the whole warp.
-//   phase C: lanes in `ins` commit table[h] = pos (highest lane wins per slot).
+//            candidate is the highest inserted twin below it, else the table entry read in phase A.  The
+//            first hitting lane is the parser's next match; the warp extends it (28 lanes x 4 bytes
+//            forward and 4 lanes x 1 byte backward in one step), the sequence is *recorded* (lane k
+//            keeps the k-th sequence of the window), the parser's post-match insert of position e-2 is
+//            added to `ins`, and the replay resumes at lane e (positions inside a match are never probed,
+//            exactly as in the reference).
+//   phase C: every lane that owns its slot writes the slot's final value: its position if the parser
+//            inserted it, else the old entry.
 //   phase D: the recorded sequences are written out in parallel, one lane per sequence; long literal
 //            runs are copied by the whole warp with 32-bit stores.
 // After 64 failed probes the reference widens its stride (step = searchNb++ >> 6); lane positions follow
 // the closed form of that schedule, so incompressible data is skipped as quickly as the CPU does.
 //
-// Memory: the chunk and the 16 KB table live in shared memory (staged by the caller); output bytes go
-// straight to global memory.
+// Memory: the chunk (followed by >= CW_LZ4_PAD readable bytes) and the table live in shared memory, staged
+// by the caller; output bytes go straight to global memory.
 #pragma once
 #include "cw_device.cuh"
 
-#define CW_LZ4_HASH_ENTRIES 8192u
 #define CW_LZ4_NONE 0xffffffffu
-#ifndef CW_LZ4_SPECULATE
-#define CW_LZ4_SPECULATE 0   // 1: phase A extends table candidates speculatively (measured slower on B200, r01)
-#endif
-#define CW_LZ4_FW_STEPS 6u   // speculative forward extension: up to 24 bytes per lane
-#define CW_LZ4_BK_CAP 8u     // speculative backward extension: up to 8 bytes per lane
-#define CW_LZ4_LIT_SELF 20u  // literal runs up to this long are copied by the recording lane itself
+#define CW_LZ4_PAD 144u       // readable bytes after the chunk: the forward compare reads up to 131 bytes past n-12
+#define CW_LZ4_LIT_SELF 16u   // literal runs up to this long are copied by the recording lane itself
+#define CW_LZ4_FW_LANES 28u   // lanes 0..27 compare forward, lanes 28..31 backward
+#define CW_LZ4_TAG 0x8000u    // slot tag used for twin detection (chunks <= 32768 bytes: positions < 0x8000)
 
 CW_DEV uint32_t cw_umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
-// unaligned little-endian 32-bit read from the staged chunk (base 4-byte aligned, >= 8 bytes of padding)
+// unaligned little-endian 32-bit read from the staged chunk (base 4-byte aligned)
 CW_DEV uint32_t cw_lz4_read32(const uint8_t *s, uint32_t pos)
 {
     const uint32_t *w = reinterpret_cast<const uint32_t *>(s);
     const uint32_t i = pos >> 2;
     return cw_funnel_r(w[i], w[i + 1], (pos & 3u) * 8u);
 }
-CW_DEV uint32_t cw_lz4_hash(uint32_t v) { return (v * 2654435761u) >> 19; }
+template <int HASHLOG>
+CW_DEV uint32_t cw_lz4_hash(uint32_t v)
+{
+    return (v * 2654435761u) >> (32 - HASHLOG);
+}
 
 // probe schedule of one search: probe j sits S(j) bytes after the search start and
 // the next probe is step(j) further.  j = -1 is the immediate re-test right after a match.
@@ -91,12 +98,15 @@ CW_DEV void cw_lz4_copy_warp(uint8_t *out, uint32_t dst, const uint8_t *s, uint3
     if (lane < len - done) out[dst + done + lane] = s[src + done + lane];
 }
 
-// Compress chunk s[0..n) (n <= 65536).  table: zeroed u16[8192] in shared memory.  Returns the number of
-// bytes written to out (same value in every lane).  out must hold LZ4_COMPRESSBOUND(n) bytes.
+// Compress chunk s[0..n) (n <= 65536).  table: zeroed u16[1 << HASHLOG] in shared memory.  Returns the
+// number of bytes written to out (same value in every lane).  out must hold LZ4_COMPRESSBOUND(n) bytes.
+template <int HASHLOG>
 CW_DEV uint32_t cw_lz4_compress_warp(const uint8_t *s, uint32_t n, uint16_t *table, uint8_t *out)
 {
     const unsigned lane = cw_lane();
-    const uint32_t lower = (1u << lane) - 1u;
+    const uint32_t own = 1u << lane;
+    const uint32_t lower = own - 1u;
+    const bool tag_ok = n <= 32768u;  // positions fit below CW_LZ4_TAG
     uint32_t op = 0, anchor = 0;
 
     if (n >= 13u) {
@@ -108,49 +118,52 @@ CW_DEV uint32_t cw_lz4_compress_warp(const uint8_t *s, uint32_t n, uint16_t *tab
         while (!done) {
             // ---------------- phase A ----------------
             const bool unit = (j0 + 31 <= 64);  // all 32 probes one byte apart
-            const int32_t j = j0 + (int32_t)lane;
-            const uint32_t pos = sbase + (uint32_t)cw_lz4_S(j);
-            const uint32_t base = sbase + (uint32_t)cw_lz4_S(j0);  // position of lane 0
-            const bool valid = pos + cw_lz4_step(j) <= mfl1;
-            const uint32_t v = cw_lz4_read32(s, valid ? pos : 0u);
-            const uint32_t h = cw_lz4_hash(v);
-            const uint32_t M = cw_match_any(h);
-            const uint32_t t = table[h];
-            const bool tmatch = valid && cw_lz4_read32(s, t) == v;
-            // speculative extension against the table candidate: fw = equal bytes after the 4-byte match
-            // (exact unless FLONG), bk = equal bytes before it (exact up to min(t, pos-anchor) unless BLONG)
-            uint32_t spec = 3u << 16;  // "unknown": extend on demand
-#if CW_LZ4_SPECULATE
-            if (tmatch) {
-                uint32_t fw = 0, pa = pos + 4u, pb = t + 4u, it = 0;
-                for (; it < CW_LZ4_FW_STEPS; it++) {
-                    const uint32_t room = pa < matchlimit ? matchlimit - pa : 0u;
-                    const uint32_t d = cw_lz4_read32(s, cw_umin(pa, n)) ^ cw_lz4_read32(s, cw_umin(pb, n));
-                    const uint32_t eq = cw_umin(d ? (uint32_t)(cw_ffs(d) - 1) >> 3 : 4u, room);
-                    fw += eq;
-                    if (eq < 4u) break;
-                    pa += 4u;
-                    pb += 4u;
-                }
-                const uint32_t capb = cw_umin(cw_umin(t, pos - anchor), CW_LZ4_BK_CAP);
-                uint32_t bk = 0;
-                while (bk < capb && s[pos - 1u - bk] == s[t - 1u - bk]) bk++;
-                spec = fw | (bk << 8) | (it == CW_LZ4_FW_STEPS ? 1u << 16 : 0u) |
-                       ((bk == CW_LZ4_BK_CAP) ? 1u << 17 : 0u);
+            uint32_t base, pos;
+            bool valid;
+            if (unit) {
+                base = sbase + (uint32_t)j0;  // S(j) = j while the steps are 1
+                pos = base + lane;
+                valid = pos < mfl1;
+            } else {
+                const int32_t j = j0 + (int32_t)lane;
+                base = sbase + (uint32_t)cw_lz4_S(j0);
+                pos = sbase + (uint32_t)cw_lz4_S(j);
+                valid = pos + cw_lz4_step(j) <= mfl1;
             }
-#endif
+            const uint32_t v = cw_lz4_read32(s, valid ? pos : 0u);
+            const uint32_t h = cw_lz4_hash<HASHLOG>(v);
+            const uint32_t t = table[h];
+            // twin detection: tag the slot, read it back; the lane whose tag survives owns the slot
+            uint32_t M = own;
+            bool owner = valid;
+            uint32_t twins;
+            if (tag_ok) {
+                cw_syncwarp();  // every lane has read its old entry before any lane tags a slot
+                if (valid) table[h] = (uint16_t)(CW_LZ4_TAG | lane);
+                cw_syncwarp();
+                owner = valid && table[h] == (CW_LZ4_TAG | lane);
+                twins = cw_ballot(valid && !owner);
+            } else {
+                M = cw_match_any(valid ? h : 0x10000u + lane);
+                twins = cw_ballot(M != own);
+                owner = valid && !(M & ~((2u << lane) - 1u));  // highest lane of the group
+            }
+            const bool tmatch = valid && cw_lz4_read32(s, t) == v;
             const uint32_t tm_all = cw_ballot(tmatch);
             const uint32_t inv_all = cw_ballot(!valid);
-            const uint32_t dyn_all = cw_ballot(valid && (M & lower) != 0u);  // lanes that may have an in-window candidate
-            uint32_t E = 0;
-            if (dyn_all) E = cw_match_any(v);
+            uint32_t E = own, dyn_all = 0;
+            if (twins) {
+                if (tag_ok) M = cw_match_any(valid ? h : 0x10000u + lane);
+                E = cw_match_any(v);
+                dyn_all = cw_ballot(valid && (M & lower) != 0u);  // lanes that may have an in-window candidate
+            }
             // ---------------- phase B ----------------
             uint32_t ins = 0, i0 = 0, pend = CW_LZ4_NONE, nrec = 0;
             uint32_t r_src = 0, r_lit = 0, r_off = 0, r_mcode = 0, r_op = 0;  // lane k: k-th sequence of this window
             bool restart = false;
             for (;;) {
                 const uint32_t range = ~((1u << i0) - 1u);
-                uint32_t hitm, tabm;  // hitting lanes; lanes whose candidate is the table entry
+                uint32_t hitm = tm_all & range;
                 uint32_t cand = t;
                 if (dyn_all & range) {
                     const uint32_t cm = M & (ins | range) & lower;
@@ -161,10 +174,6 @@ CW_DEV uint32_t cw_lz4_compress_warp(const uint8_t *s, uint32_t n, uint16_t *tab
                         cand = unit ? base + (uint32_t)jl : sbase + (uint32_t)cw_lz4_S(j0 + jl);
                     }
                     hitm = cw_ballot(hit) & range;
-                    tabm = cw_ballot(cm == 0u);
-                } else {
-                    hitm = tm_all & range;
-                    tabm = 0xffffffffu;
                 }
                 const uint32_t invm = inv_all & range;
                 const int f = cw_ffs(hitm) - 1, iv = cw_ffs(invm) - 1;
@@ -179,48 +188,49 @@ CW_DEV uint32_t cw_lz4_compress_warp(const uint8_t *s, uint32_t n, uint16_t *tab
                 ins |= range & ((2u << f) - 1u);
                 const uint32_t cur = unit ? base + (uint32_t)f : cw_shfl(pos, (unsigned)f);
                 const uint32_t cnd = cw_shfl(cand, (unsigned)f);
-                uint32_t fwd, back;
-                const uint32_t maxb = cw_umin(cur - anchor, cnd);
-#if CW_LZ4_SPECULATE
-                const uint32_t sp = cw_shfl(spec, (unsigned)f);
-                if (((tabm >> f) & 1u) && !(sp & (3u << 16))) {
-                    fwd = sp & 0xffu;
-                    back = cw_umin((sp >> 8) & 0xffu, maxb);
-                } else
-#endif
+                // ---- extend: lanes 0..27 compare 4 bytes each forward from cur+4, lanes 28..31 one byte each backward ----
+                uint32_t fwd = 0, back = 0;
                 {
-                    // ---- on-demand extension by the whole warp: 32 x 4 bytes forward, 32 x 1 byte backward ----
-                    fwd = 0;
+                    const uint32_t maxb = cw_umin(cur - anchor, cnd);
+                    const bool fl = lane < CW_LZ4_FW_LANES;
                     uint32_t pa = cur + 4u + 4u * lane, pb = cnd + 4u + 4u * lane;
-                    uint32_t da = cw_lz4_read32(s, cw_umin(pa, n)) ^ cw_lz4_read32(s, cw_umin(pb, n));
-                    const uint32_t xb = lane + 1u;
-                    const bool bok = xb <= maxb && s[cur - cw_umin(xb, cur)] == s[cnd - cw_umin(xb, cnd)];
-                    for (;;) {
-                        uint32_t eq = da ? (uint32_t)(cw_ffs(da) - 1) >> 3 : 4u;
-                        const uint32_t room = pa < matchlimit ? matchlimit - pa : 0u;
-                        eq = cw_umin(eq, room);
-                        const uint32_t stop = cw_ballot(eq < 4u);
-                        if (stop) {
-                            const unsigned L = (unsigned)cw_ffs(stop) - 1u;
-                            fwd += 4u * L + cw_shfl(eq, L);
-                            break;
-                        }
-                        fwd += 128u;
-                        pa += 128u;
-                        pb += 128u;
-                        da = cw_lz4_read32(s, cw_umin(pa, n)) ^ cw_lz4_read32(s, cw_umin(pb, n));
+                    const uint32_t xb = lane - (CW_LZ4_FW_LANES - 1u);  // 1..4 on the backward lanes
+                    bool stopl;
+                    uint32_t eq = 0;
+                    if (fl) {
+                        const uint32_t d = cw_lz4_read32(s, pa) ^ cw_lz4_read32(s, pb);
+                        eq = d ? (uint32_t)(cw_ffs(d) - 1) >> 3 : 4u;
+                        eq = cw_umin(eq, pa < matchlimit ? matchlimit - pa : 0u);
+                        stopl = eq < 4u;
+                    } else {
+                        stopl = !(xb <= maxb && s[cur - cw_umin(xb, cur)] == s[cnd - cw_umin(xb, cnd)]);
                     }
-                    uint32_t bstop = cw_ballot(!bok);
+                    uint32_t stop = cw_ballot(stopl);
+                    uint32_t fstop = stop & ((1u << CW_LZ4_FW_LANES) - 1u);
+                    const uint32_t bstop = stop >> CW_LZ4_FW_LANES;
+                    while (!fstop) {  // more than 112 equal bytes: keep going, all 32 lanes forward
+                        fwd += fwd ? 128u : 4u * CW_LZ4_FW_LANES;
+                        pa = cur + 4u + fwd + 4u * lane;
+                        pb = cnd + 4u + fwd + 4u * lane;
+                        const uint32_t d = cw_lz4_read32(s, pa) ^ cw_lz4_read32(s, pb);
+                        eq = d ? (uint32_t)(cw_ffs(d) - 1) >> 3 : 4u;
+                        eq = cw_umin(eq, pa < matchlimit ? matchlimit - pa : 0u);
+                        fstop = cw_ballot(eq < 4u);
+                    }
+                    {
+                        const unsigned L = (unsigned)cw_ffs(fstop) - 1u;
+                        fwd += 4u * L + cw_shfl(eq, L);
+                    }
                     if (bstop) {
                         back = (uint32_t)cw_ffs(bstop) - 1u;
-                    } else {
-                        back = 32u;
+                    } else {  // 4 equal bytes before the match and room for more: whole warp, byte-wise
+                        back = 4u;
                         for (;;) {
                             const uint32_t x = back + lane + 1u;
                             const bool ok = x <= maxb && s[cur - cw_umin(x, cur)] == s[cnd - cw_umin(x, cnd)];
-                            bstop = cw_ballot(!ok);
-                            if (bstop) {
-                                back += (uint32_t)cw_ffs(bstop) - 1u;
+                            const uint32_t bs = cw_ballot(!ok);
+                            if (bs) {
+                                back += (uint32_t)cw_ffs(bs) - 1u;
                                 break;
                             }
                             back += 32u;
@@ -240,7 +250,9 @@ CW_DEV uint32_t cw_lz4_compress_warp(const uint8_t *s, uint32_t n, uint16_t *tab
                         r_op = op;
                     }
                     nrec++;
-                    op += 1u + cw_lz4_ext_bytes(lit) + lit + 2u + cw_lz4_ext_bytes(mcode);
+                    op += 3u + lit;
+                    if (lit >= 15u) op += (lit - 15u) / 255u + 1u;
+                    if (mcode >= 15u) op += (mcode - 15u) / 255u + 1u;
                 }
                 anchor = e;
                 if (e >= mfl1) {  // "if (ip > mflimit) break" -> last literals
@@ -282,11 +294,20 @@ CW_DEV uint32_t cw_lz4_compress_warp(const uint8_t *s, uint32_t n, uint16_t *tab
                 }
             }
             if (done) break;
-            // ---------------- phase C: commit the parser's table writes ----------------
-            if (((ins >> lane) & 1u) && !(M & ins & ~((2u << lane) - 1u))) table[h] = (uint16_t)pos;
+            // ---------------- phase C: every touched slot gets its final value ----------------
+            if (twins) {
+                // slot owners first put the old entry back, then the highest inserted twin of each slot writes
+                if (tag_ok && owner) table[h] = (uint16_t)t;
+                cw_syncwarp();
+                if (((ins >> lane) & 1u) && !(M & ins & ~((2u << lane) - 1u))) table[h] = (uint16_t)pos;
+            } else if (tag_ok) {
+                if (valid) table[h] = (uint16_t)(((ins >> lane) & 1u) ? pos : t);
+            } else {
+                if ((ins >> lane) & 1u) table[h] = (uint16_t)pos;
+            }
             cw_syncwarp();
             if (pend != CW_LZ4_NONE) {
-                if (lane == 0) table[cw_lz4_hash(cw_lz4_read32(s, pend))] = (uint16_t)pend;
+                if (lane == 0) table[cw_lz4_hash<HASHLOG>(cw_lz4_read32(s, pend))] = (uint16_t)pend;
                 cw_syncwarp();
             }
             if (restart) j0 = -1;                                       // lane 0 = re-test at e

@@ -23,19 +23,22 @@ struct Job {
 static void lz4_body(void *a)
 {
     Job *j = (Job *)a;
-    uint32_t r = cw_lz4_compress_warp(j->s, j->n, j->table, j->out);
+    uint32_t r = j->mode == 12 ? cw_lz4_compress_warp<12>(j->s, j->n, j->table, j->out)
+                               : cw_lz4_compress_warp<13>(j->s, j->n, j->table, j->out);
     if (cw_lane() == 0) j->result = r;
 }
 
-extern "C" uint32_t emu_lz4_compress(const uint8_t *src, uint32_t n, uint8_t *out)
+extern "C" uint32_t emu_lz4_compress_hl(const uint8_t *src, uint32_t n, uint8_t *out, int hashlog)
 {
-    std::vector<uint32_t> staged((n + 16 + 3) / 4 + 4, 0);  // 4-byte aligned, zero padded like the kernel's smem
+    std::vector<uint32_t> staged((n + CW_LZ4_PAD + 3) / 4 + 4, 0);  // 4-byte aligned, zero padded like the kernel's smem
     memcpy(staged.data(), src, n);
-    std::vector<uint16_t> table(CW_LZ4_HASH_ENTRIES, 0);
-    Job j{(const uint8_t *)staged.data(), n, table.data(), nullptr, out, 0, 0, 0};
+    std::vector<uint16_t> table(1u << hashlog, 0);
+    Job j{(const uint8_t *)staged.data(), n, table.data(), nullptr, out, 0, 0, hashlog};
     cwemu::run_warp(lz4_body, &j);
     return j.result;
 }
+
+extern "C" uint32_t emu_lz4_compress(const uint8_t *src, uint32_t n, uint8_t *out) { return emu_lz4_compress_hl(src, n, out, 13); }
 
 #ifdef HAVE_LZF
 static void lzf_body(void *a)
@@ -46,7 +49,7 @@ static void lzf_body(void *a)
 }
 extern "C" uint32_t emu_lzf_compress(const uint8_t *src, uint32_t n, uint8_t *out, uint32_t out_cap)
 {
-    std::vector<uint32_t> staged((n + 16 + 3) / 4 + 4, 0);
+    std::vector<uint32_t> staged((n + CW_LZ4_PAD + 3) / 4 + 4, 0);
     memcpy(staged.data(), src, n);
     std::vector<uint8_t> scratch(sizeof(CwLzfScratch), 0);
     Job j{(const uint8_t *)staged.data(), n, nullptr, scratch.data(), out, out_cap, 0, 0};

@@ -16,6 +16,7 @@ import oracle_lib as O
 what = sys.argv[1] if len(sys.argv) > 1 else "lz4"
 chunk = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
 N = 32768
+MODE = int(os.environ.get("CW_MODE", "0"))
 L = O.lib()
 L.cwo_synth_class.argtypes = [C.c_uint64, C.c_uint64]
 L.cwo_synth_class.restype = C.c_uint
@@ -57,10 +58,10 @@ for name, data in sets.items():
 
     def run():
         if what == "fused":
-            eng.hash_compress_dev(cw.HASH_SKEIN512, comp, 0, src.data_ptr(), chunk, n, dig.data_ptr(), blocks.data_ptr(),
+            eng.hash_compress_dev(cw.HASH_SKEIN512, comp, MODE, src.data_ptr(), chunk, n, dig.data_ptr(), blocks.data_ptr(),
                                   stride, lens.data_ptr(), s)
         else:
-            eng.compress_dev(comp, 0, src.data_ptr(), chunk, n, blocks.data_ptr(), stride, lens.data_ptr(), s)
+            eng.compress_dev(comp, MODE, src.data_ptr(), chunk, n, blocks.data_ptr(), stride, lens.data_ptr(), s)
 
     run()
     torch.cuda.synchronize()

@@ -14,6 +14,8 @@
 // the 126 MB L2, so every input byte is fetched from HBM once (ncu: dram__bytes_read.sum ~= input bytes);
 // the compressors are latency bound and leave most issue slots of the SM idle, which is exactly what the
 // integer-bound hash warps consume.
+// the 3 x 24-round Skein body (11 KB of SASS instead of 36 KB) keeps hash + compressor code inside the instruction cache
+#define CW_SKEIN_UNROLL72 false
 #include "hash_kernels.cuh"
 #include "launch.h"
 #include "lz4_warp.cuh"

@@ -188,31 +188,29 @@ CW_DEV uint32_t cw_lz4_compress_warp(const uint8_t *s, uint32_t n, uint16_t *tab
                 ins |= range & ((2u << f) - 1u);
                 const uint32_t cur = unit ? base + (uint32_t)f : cw_shfl(pos, (unsigned)f);
                 const uint32_t cnd = cw_shfl(cand, (unsigned)f);
-                // ---- extend: lanes 0..27 compare 4 bytes each forward from cur+4, lanes 28..31 one byte each backward ----
+                // ---- extend: lanes 0..27 compare 4 bytes each forward from cur+4, lanes 28..31 one byte each
+                // backward; one branch-free instruction stream for both roles ----
                 uint32_t fwd = 0, back = 0;
                 {
                     const uint32_t maxb = cw_umin(cur - anchor, cnd);
                     const bool fl = lane < CW_LZ4_FW_LANES;
-                    uint32_t pa = cur + 4u + 4u * lane, pb = cnd + 4u + 4u * lane;
                     const uint32_t xb = lane - (CW_LZ4_FW_LANES - 1u);  // 1..4 on the backward lanes
-                    bool stopl;
-                    uint32_t eq = 0;
-                    if (fl) {
-                        const uint32_t d = cw_lz4_read32(s, pa) ^ cw_lz4_read32(s, pb);
-                        eq = d ? (uint32_t)(cw_ffs(d) - 1) >> 3 : 4u;
-                        eq = cw_umin(eq, pa < matchlimit ? matchlimit - pa : 0u);
-                        stopl = eq < 4u;
-                    } else {
-                        stopl = !(xb <= maxb && s[cur - cw_umin(xb, cur)] == s[cnd - cw_umin(xb, cnd)]);
-                    }
-                    uint32_t stop = cw_ballot(stopl);
+                    const bool bl = !fl && xb <= maxb;                  // backward lane with a byte to look at
+                    uint32_t pa = fl ? cur + 4u + 4u * lane : (bl ? cur - xb : 0u);
+                    uint32_t pb = fl ? cnd + 4u + 4u * lane : (bl ? cnd - xb : 0u);
+                    uint32_t d = cw_lz4_read32(s, pa) ^ cw_lz4_read32(s, pb);
+                    uint32_t eq = d ? (uint32_t)(cw_ffs(d) - 1) >> 3 : 4u;  // equal leading bytes
+                    const uint32_t room = pa < matchlimit ? matchlimit - pa : 0u;
+                    eq = fl ? cw_umin(eq, room) : eq;
+                    const bool stopl = fl ? eq < 4u : !(bl && eq != 0u);
+                    const uint32_t stop = cw_ballot(stopl);
                     uint32_t fstop = stop & ((1u << CW_LZ4_FW_LANES) - 1u);
                     const uint32_t bstop = stop >> CW_LZ4_FW_LANES;
                     while (!fstop) {  // more than 112 equal bytes: keep going, all 32 lanes forward
                         fwd += fwd ? 128u : 4u * CW_LZ4_FW_LANES;
                         pa = cur + 4u + fwd + 4u * lane;
                         pb = cnd + 4u + fwd + 4u * lane;
-                        const uint32_t d = cw_lz4_read32(s, pa) ^ cw_lz4_read32(s, pb);
+                        d = cw_lz4_read32(s, pa) ^ cw_lz4_read32(s, pb);
                         eq = d ? (uint32_t)(cw_ffs(d) - 1) >> 3 : 4u;
                         eq = cw_umin(eq, pa < matchlimit ? matchlimit - pa : 0u);
                         fstop = cw_ballot(eq < 4u);
@@ -251,8 +249,7 @@ CW_DEV uint32_t cw_lz4_compress_warp(const uint8_t *s, uint32_t n, uint16_t *tab
                     }
                     nrec++;
                     op += 3u + lit;
-                    if (lit >= 15u) op += (lit - 15u) / 255u + 1u;
-                    if (mcode >= 15u) op += (mcode - 15u) / 255u + 1u;
+                    if ((lit | mcode) >= 15u) op += cw_lz4_ext_bytes(lit) + cw_lz4_ext_bytes(mcode);  // rare in text
                 }
                 anchor = e;
                 if (e >= mfl1) {  // "if (ip > mflimit) break" -> last literals
@@ -261,10 +258,11 @@ CW_DEV uint32_t cw_lz4_compress_warp(const uint8_t *s, uint32_t n, uint16_t *tab
                 }
                 // parser: table[hash(e-2)] = e-2, then immediate re-test at e, then a fresh search at e+1
                 sbase = e + 1u;
-                if (unit && e - 2u <= base + 31u) ins |= 1u << (e - 2u - base);
+                const uint32_t de = e - base;  // lane index of the next parser position (unit windows)
+                if (unit && de < 34u) ins |= 1u << (de - 2u);
                 else pend = e - 2u;
-                if (unit && e <= base + 31u) {
-                    i0 = e - base;
+                if (unit && de < 32u) {
+                    i0 = de;
                     continue;
                 }
                 restart = true;

@@ -16,11 +16,9 @@
 // integer-bound hash warps consume.
 // the 3 x 24-round Skein body (11 KB of SASS instead of 36 KB) keeps hash + compressor code inside the instruction cache
 #define CW_SKEIN_UNROLL72 false
+#include "comp_roles.cuh"
 #include "hash_kernels.cuh"
 #include "launch.h"
-#include "lz4_warp.cuh"
-#include "lzf_warp.cuh"
-#include "stage.cuh"
 
 #include <cstdlib>
 
@@ -29,9 +27,9 @@
 // hash_warps * 32 lanes * chunk * 148 SMs; 1 warp keeps that window at 39 MB for 8 KB chunks (L2: 126 MB)
 // while still hashing faster than the compressors consume (measured, profiles/).
 #define CW_FUSED_HASH_WARPS_DEFAULT 1
-#define CW_FUSED_HASH_WARPS_MAX 8
+#define CW_FUSED_HASH_WARPS_MAX 4
 #define CW_FUSED_MAX_COMP_WARPS 14
-#define CW_FUSED_MAX_THREADS ((CW_FUSED_HASH_WARPS_MAX + CW_FUSED_MAX_COMP_WARPS) * 32)
+#define CW_FUSED_MAX_THREADS ((CW_FUSED_HASH_WARPS_MAX + CW_FUSED_MAX_COMP_WARPS + 3) * 32)  // + emitters
 
 static int fused_hash_warps()
 {
@@ -47,84 +45,59 @@ static int fused_hash_warps()
 
 enum { CW_C_LZ4 = 0, CW_C_LZF = 1, CW_C_LZ4_FAST = 2 };  // LZ4 with the reference's 13-bit table / LZF / LZ4 with a 12-bit table
 
-template <int CALG>
-__host__ __device__ constexpr uint32_t cw_scratch_bytes()
-{
-    return CALG == CW_C_LZ4 ? (2u << 13) : (CALG == CW_C_LZ4_FAST ? (2u << 12) : (uint32_t)sizeof(CwLzfScratch));
-}
+#define CW_FUSED_EMITTERS 3  // emitter warps per CTA (LZ4 only)
 
 template <int CALG>
-__host__ __device__ constexpr uint32_t cw_chunk_pad(uint32_t chunk)
+__host__ __device__ constexpr uint32_t cw_slot_bytes(uint32_t chunk)
 {
-    return (chunk + (CALG == CW_C_LZF ? 16u : CW_LZ4_PAD) + 15u) & ~15u;
+    return CALG == CW_C_LZF ? ((chunk + 16u + 15u) & ~15u) + (uint32_t)sizeof(CwLzfScratch)
+                            : cw_lz4_chunk_pad(chunk) + (2u << (CALG == CW_C_LZ4 ? 13 : 12)) + (uint32_t)sizeof(CwLz4Queue);
 }
 
+// warps [0, parsers): compress; [parsers, parsers + emitters): LZ4 emitters; the rest: hash
 template <int HALG, int CALG, bool ALIGNED>
 __global__ void __launch_bounds__(CW_FUSED_MAX_THREADS, 1)
     cw_fused_kernel(const __grid_constant__ CwSkeinIV iv, const uint8_t *__restrict__ src, uint32_t chunk, uint64_t n_chunks,
                     uint8_t *__restrict__ digests, uint8_t *__restrict__ dst, uint64_t stride, uint32_t *__restrict__ lens,
-                    unsigned long long *work, uint32_t slot_bytes, uint32_t comp_warps)
+                    unsigned long long *work, uint32_t slot_bytes, uint32_t parsers, uint32_t emitters)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bars[32];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    if (warp < comp_warps) {
-        // ------------------------------ compress role ------------------------------
-        uint8_t *s = smem + (size_t)warp * slot_bytes;
-        const uint32_t chunk_pad = cw_chunk_pad<CALG>(chunk);
-        uint64_t *bar = &bars[warp];
-        if (lane == 0) cw_mbar_init(bar, 1);
-        for (uint32_t i = chunk + lane; i < chunk_pad; i += 32u) s[i] = 0;
+    if (CALG != CW_C_LZF) {
+        // slot_bytes here excludes the queue: queues sit behind the slots
+        CwLz4Queue *queues = reinterpret_cast<CwLz4Queue *>(smem + (size_t)parsers * slot_bytes);
+        if (warp < parsers && lane < 8u) reinterpret_cast<uint32_t *>(&queues[warp])[lane] = 0u;
+        __syncthreads();
+        if (warp < parsers) {
+            cw_lz4_parser_role<(CALG == CW_C_LZ4 ? 13 : 12), ALIGNED>(smem + (size_t)warp * slot_bytes, &queues[warp], &bars[warp],
+                                                                      src, chunk, n_chunks, &work[0]);
+            return;
+        }
+        if (warp < parsers + emitters) {
+            cw_lz4_emitter_role(warp - parsers, emitters, parsers, smem, slot_bytes, queues, chunk, dst, stride, lens);
+            return;
+        }
+    } else if (warp < parsers) {
+        cw_lzf_role<ALIGNED>(smem + (size_t)warp * slot_bytes, &bars[warp], src, chunk, n_chunks, dst, stride, lens, &work[0]);
+        return;
+    }
+    // ------------------------------ hash role ------------------------------
+    constexpr int D = cw_digest_len<HALG>();
+    for (;;) {
+        unsigned long long grp = 0;
+        if (lane == 0) grp = atomicAdd(&work[1], 1ull);
+        grp = __shfl_sync(0xffffffffu, grp, 0);
+        const unsigned long long first = grp * 32ull;
+        if (first >= n_chunks) break;
+        const unsigned long long need = first + 32ull < n_chunks ? first + 32ull : n_chunks;
+        if (lane == 0) {
+            // follow the compress warps: wait until this group's chunks have been claimed (-> are in L2)
+            while (*reinterpret_cast<volatile unsigned long long *>(&work[0]) < need) __nanosleep(256);
+        }
         __syncwarp();
-        uint32_t phase = 0;
-        for (;;) {
-            unsigned long long g = 0;
-            if (lane == 0) g = atomicAdd(&work[0], 1ull);
-            g = __shfl_sync(0xffffffffu, g, 0);
-            if (g >= n_chunks) break;
-            __syncwarp();
-            if (ALIGNED && lane == 0) cw_bulk_load(s, src + g * chunk, chunk, bar);
-            if (CALG != CW_C_LZF) {
-                uint4 *t4 = reinterpret_cast<uint4 *>(s + chunk_pad);
-#pragma unroll 8
-                for (uint32_t i = lane; i < cw_scratch_bytes<CALG>() / 16u; i += 32u) t4[i] = make_uint4(0, 0, 0, 0);
-            }
-            if (ALIGNED) {
-                cw_mbar_wait(bar, phase);
-                phase ^= 1u;
-            } else {
-                const uint8_t *gp = src + g * chunk;
-                for (uint32_t i = lane; i < chunk; i += 32u) s[i] = gp[i];
-            }
-            __syncwarp();
-            uint32_t len;
-            if (CALG == CW_C_LZ4)
-                len = cw_lz4_compress_warp<13>(s, chunk, reinterpret_cast<uint16_t *>(s + chunk_pad), dst + g * stride);
-            else if (CALG == CW_C_LZ4_FAST)
-                len = cw_lz4_compress_warp<12>(s, chunk, reinterpret_cast<uint16_t *>(s + chunk_pad), dst + g * stride);
-            else
-                len = cw_lzf_compress_warp(s, chunk, reinterpret_cast<CwLzfScratch *>(s + chunk_pad), dst + g * stride,
-                                           chunk - 1u);
-            if (lane == 0) lens[g] = len;
-        }
-    } else {
-        // ------------------------------ hash role ------------------------------
-        constexpr int D = cw_digest_len<HALG>();
-        for (;;) {
-            unsigned long long grp = 0;
-            if (lane == 0) grp = atomicAdd(&work[1], 1ull);
-            grp = __shfl_sync(0xffffffffu, grp, 0);
-            const unsigned long long first = grp * 32ull;
-            if (first >= n_chunks) break;
-            const unsigned long long need = first + 32ull < n_chunks ? first + 32ull : n_chunks;
-            if (lane == 0) {
-                // follow the compress warps: wait until this group's chunks have been claimed (-> are in L2)
-                while (*reinterpret_cast<volatile unsigned long long *>(&work[0]) < need) __nanosleep(256);
-            }
-            __syncwarp();
-            const unsigned long long idx = first + lane;
-            if (idx < n_chunks) cw_hash_one<HALG, ALIGNED, ALIGNED>(iv, src + idx * chunk, chunk, digests + idx * D);
-        }
+        const unsigned long long idx = first + lane;
+        if (idx < n_chunks) cw_hash_one<HALG, ALIGNED, ALIGNED>(iv, src + idx * chunk, chunk, digests + idx * D);
     }
 }
 
@@ -134,14 +107,17 @@ static cudaError_t launch_one(const CwDeviceInfo &dev, int max_dyn_smem, const C
                               uint32_t *d_lens, unsigned long long *work, cudaStream_t st)
 {
     auto kern = cw_fused_kernel<HALG, CALG, ALIGNED>;
-    const uint32_t slot = cw_chunk_pad<CALG>(chunk) + cw_scratch_bytes<CALG>();
-    int comp_warps = max_dyn_smem / (int)slot;
-    if (comp_warps < 1) return cudaErrorInvalidValue;
-    if (comp_warps > CW_FUSED_MAX_COMP_WARPS) comp_warps = CW_FUSED_MAX_COMP_WARPS;
-    uint64_t ctas = (n + (uint64_t)comp_warps - 1) / (uint64_t)comp_warps;
+    const uint32_t per = cw_slot_bytes<CALG>(chunk);  // slot (+ queue for LZ4)
+    const uint32_t slot = CALG == CW_C_LZF ? per : per - (uint32_t)sizeof(CwLz4Queue);
+    int parsers = max_dyn_smem / (int)per;
+    if (parsers < 1) return cudaErrorInvalidValue;
+    if (parsers > CW_FUSED_MAX_COMP_WARPS) parsers = CW_FUSED_MAX_COMP_WARPS;
+    int emitters = CALG == CW_C_LZF ? 0 : CW_FUSED_EMITTERS;
+    if (emitters > parsers) emitters = parsers;
+    uint64_t ctas = (n + (uint64_t)parsers - 1) / (uint64_t)parsers;
     if (ctas > (uint64_t)dev.sm_count) ctas = (uint64_t)dev.sm_count;
-    kern<<<(unsigned)ctas, (comp_warps + fused_hash_warps()) * 32, (size_t)comp_warps * slot, st>>>(
-        iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, slot, (uint32_t)comp_warps);
+    kern<<<(unsigned)ctas, (parsers + emitters + fused_hash_warps()) * 32, (size_t)parsers * per, st>>>(
+        iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, slot, (uint32_t)parsers, (uint32_t)emitters);
     return cudaGetLastError();
 }
 

@@ -23,14 +23,19 @@
 //            set of window lanes whose position the sequential parser has inserted so far; a lane's true
 //            candidate is the highest inserted twin below it, else the table entry read in phase A.  The
 //            first hitting lane is the parser's next match; the warp extends it (28 lanes x 4 bytes
-//            forward and 4 lanes x 1 byte backward in one step), the sequence is *recorded* (lane k
-//            keeps the k-th sequence of the window), the parser's post-match insert of position e-2 is
+//            forward), the match is pushed to the emitter queue, the parser's post-match insert of position e-2 is
 //            added to `ins`, and the replay resumes at lane e (positions inside a match are never probed,
 //            exactly as in the reference).
 //   phase C: every lane that owns its slot writes the slot's final value: its position if the parser
 //            inserted it, else the old entry.
-//   phase D: the recorded sequences are written out in parallel, one lane per sequence; long literal
-//            runs are copied by the whole warp with 32-bit stores.
+// The parser does only what the next decision depends on.  Each match is pushed as an 8-byte record
+// (anchor, cur, cand, forward length) into a shared-memory ring; an EMITTER warp of the same CTA pops
+// records 32 at a time, one lane per record, and does everything the parse does not depend on: the
+// backward extension (it changes literal and match lengths but not where the parser continues), the
+// sequence sizes and their prefix sum, token / length bytes / offset, and the literal copies (long runs
+// by the whole warp with 32-bit stores).  The compressors are bound by the length of the parser's
+// dependent instruction chain, not by issue slots, so moving ~60 % of the per-match instructions to
+// another warp shortens the chain by that much.
 // After 64 failed probes the reference widens its stride (step = searchNb++ >> 6); lane positions follow
 // the closed form of that schedule, so incompressible data is skipped as quickly as the CPU does.
 //
@@ -42,7 +47,6 @@
 #define CW_LZ4_NONE 0xffffffffu
 #define CW_LZ4_PAD 144u       // readable bytes after the chunk: the forward compare reads up to 131 bytes past n-12
 #define CW_LZ4_LIT_SELF 16u   // literal runs up to this long are copied by the recording lane itself
-#define CW_LZ4_FW_LANES 28u   // lanes 0..27 compare forward, lanes 28..31 backward
 #define CW_LZ4_TAG 0x8000u    // slot tag used for twin detection (chunks <= 32768 bytes: positions < 0x8000)
 
 CW_DEV uint32_t cw_umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
@@ -98,16 +102,158 @@ CW_DEV void cw_lz4_copy_warp(uint8_t *out, uint32_t dst, const uint8_t *s, uint3
     if (lane < len - done) out[dst + done + lane] = s[src + done + lane];
 }
 
-// Compress chunk s[0..n) (n <= 65536).  table: zeroed u16[1 << HASHLOG] in shared memory.  Returns the
-// number of bytes written to out (same value in every lane).  out must hold LZ4_COMPRESSBOUND(n) bytes.
+#define CW_LZ4_QLEN 64u        // records per parser ring (power of two)
+#define CW_LZ4_REC_END 0xffffu  // cur field of the record that closes a chunk (final literals from anchor)
+
+// parser -> emitter ring, one per parser warp, in shared memory
+struct CwLz4Queue {
+    uint32_t head;               // records published by the parser (monotonic)
+    uint32_t tail;               // records consumed by the emitter (monotonic)
+    uint32_t chunk_lo, chunk_hi; // global index of the chunk the pending records belong to
+    uint32_t op;                 // emitter: bytes of that chunk written so far
+    uint32_t done;               // parser has exited
+    uint32_t pad[2];
+    uint32_t rec[CW_LZ4_QLEN][2];  // {anchor | cur << 16, cand | fwd << 16}
+};
+
+// parser side: push one record (all lanes call with the same values; qh = records pushed so far, tailc = cached tail)
+CW_DEV void cw_lz4_q_push(CwLz4Queue *q, uint32_t &qh, uint32_t &tailc, uint32_t a, uint32_t b, unsigned lane)
+{
+    if (qh - tailc >= CW_LZ4_QLEN) {  // ring looks full: publish what we have and wait for the emitter
+        cw_syncwarp();
+        if (lane == 0) {
+            cw_fence_cta();
+            cw_st_vol(&q->head, qh);
+        }
+        for (;;) {
+            uint32_t t = 0;
+            if (lane == 0) t = cw_ld_vol(&q->tail);
+            tailc = cw_shfl(t, 0);
+            if (qh - tailc < CW_LZ4_QLEN) break;
+            cw_spin();
+        }
+    }
+    if (lane == 0) {
+        q->rec[qh & (CW_LZ4_QLEN - 1u)][0] = a;
+        q->rec[qh & (CW_LZ4_QLEN - 1u)][1] = b;
+    }
+    qh++;
+}
+CW_DEV void cw_lz4_q_publish(CwLz4Queue *q, uint32_t qh, unsigned lane)
+{
+    cw_syncwarp();
+    if (lane == 0) {
+        cw_fence_cta();
+        cw_st_vol(&q->head, qh);
+    }
+}
+// parser side: wait until the emitter has consumed everything (before the chunk slot is reused)
+CW_DEV void cw_lz4_q_drain(CwLz4Queue *q, uint32_t qh, unsigned lane)
+{
+    for (;;) {
+        uint32_t t = 0;
+        if (lane == 0) t = cw_ld_vol(&q->tail);
+        if (cw_shfl(t, 0) == qh) break;
+        cw_spin();
+    }
+    cw_fence_cta();
+}
+
+// EMITTER: pop up to 32 records of queue q (one lane each) and write their sequences.  s / n: the parser's
+// chunk slot and chunk size; block of chunk g goes to dst_base + g * stride, its length to lens[g].
+// Returns the number of records consumed (same value in every lane).
+CW_DEV uint32_t cw_lz4_emit_batch(CwLz4Queue *q, const uint8_t *s, uint32_t n, uint8_t *dst_base, uint64_t stride,
+                                  uint32_t *lens)
+{
+    const unsigned lane = cw_lane();
+    uint32_t hd = 0, tl = 0;
+    if (lane == 0) {
+        hd = cw_ld_vol(&q->head);
+        tl = cw_ld_vol(&q->tail);
+    }
+    hd = cw_shfl(hd, 0);
+    tl = cw_shfl(tl, 0);
+    const uint32_t avail = hd - tl;
+    if (avail == 0u) return 0u;
+    cw_fence_cta();  // records were written before head was published
+    const uint32_t m = cw_umin(avail, 32u);
+    const uint64_t g = (uint64_t)q->chunk_lo | ((uint64_t)q->chunk_hi << 32);
+    uint8_t *out = dst_base + g * stride;
+    const uint32_t op0 = q->op;
+    const bool mine = lane < m;
+    uint32_t anchor = 0, cur = 0, cnd = 0, fwd = 0;
+    if (mine) {
+        const uint32_t r0 = q->rec[(tl + lane) & (CW_LZ4_QLEN - 1u)][0], r1 = q->rec[(tl + lane) & (CW_LZ4_QLEN - 1u)][1];
+        anchor = r0 & 0xffffu;
+        cur = r0 >> 16;
+        cnd = r1 & 0xffffu;
+        fwd = r1 >> 16;
+    }
+    const bool is_end = mine && cur == CW_LZ4_REC_END;
+    // backward extension ("catch up"): per lane, typically 0-2 bytes
+    uint32_t back = 0;
+    if (mine && !is_end) {
+        const uint32_t maxb = cw_umin(cur - anchor, cnd);
+        while (back < maxb && s[cur - 1u - back] == s[cnd - 1u - back]) back++;
+    }
+    const uint32_t lit = mine ? (is_end ? n - anchor : cur - back - anchor) : 0u;
+    const uint32_t mcode = back + fwd;  // match length - 4
+    const uint32_t sz = mine ? 1u + cw_lz4_ext_bytes(lit) + lit + (is_end ? 0u : 2u + cw_lz4_ext_bytes(mcode)) : 0u;
+    uint32_t inc = sz;  // inclusive prefix sum over the lanes
+    for (uint32_t d = 1; d < 32u; d <<= 1) {
+        const uint32_t t = cw_shfl(inc, lane >= d ? lane - d : lane);
+        if (lane >= d) inc += t;
+    }
+    const uint32_t total = cw_shfl(inc, 31u);
+    const uint32_t p0 = op0 + inc - sz;
+    if (mine) {
+        uint32_t p = p0;
+        out[p++] = (uint8_t)((cw_umin(lit, 15u) << 4) | (is_end ? 0u : cw_umin(mcode, 15u)));
+        if (lit >= 15u) p = cw_lz4_put_ext1(out, p, lit - 15u);
+        if (lit <= CW_LZ4_LIT_SELF)
+            for (uint32_t x = 0; x < lit; x++) out[p + x] = s[anchor + x];
+        p += lit;
+        if (!is_end) {
+            const uint32_t off = cur - cnd;
+            out[p] = (uint8_t)off;
+            out[p + 1u] = (uint8_t)(off >> 8);
+            if (mcode >= 15u) cw_lz4_put_ext1(out, p + 2u, mcode - 15u);
+        }
+    }
+    uint32_t big = cw_ballot(mine && lit > CW_LZ4_LIT_SELF);
+    while (big) {
+        const unsigned k = (unsigned)cw_ffs(big) - 1u;
+        big &= big - 1u;
+        const uint32_t l = cw_shfl(lit, k);
+        cw_lz4_copy_warp(out, cw_shfl(p0, k) + 1u + cw_lz4_ext_bytes(l), s, cw_shfl(anchor, k), l, lane);
+    }
+    const uint32_t endm = cw_ballot(is_end);
+    if (lane == 0) {
+        if (endm) {
+            lens[g] = op0 + total;
+            q->op = 0;
+        } else
+            q->op = op0 + total;
+    }
+    cw_syncwarp();
+    if (lane == 0) {
+        cw_fence_cta();  // literal reads of this batch are complete before the parser may reuse the slot
+        cw_st_vol(&q->tail, tl + m);
+    }
+    return m;
+}
+
+// PARSER: parse chunk s[0..n) (n <= 65536) and push its matches, then the end-of-chunk record, to q.
+// table: zeroed u16[1 << HASHLOG] in shared memory.  qh: records pushed so far on this queue (kept by the
+// caller across chunks).  The caller sets q->chunk_lo/hi before and drains the queue before reusing s.
 template <int HASHLOG>
-CW_DEV uint32_t cw_lz4_compress_warp(const uint8_t *s, uint32_t n, uint16_t *table, uint8_t *out)
+CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwLz4Queue *q, uint32_t &qh)
 {
     const unsigned lane = cw_lane();
     const uint32_t own = 1u << lane;
     const uint32_t lower = own - 1u;
     const bool tag_ok = n <= 32768u;  // positions fit below CW_LZ4_TAG
-    uint32_t op = 0, anchor = 0;
+    uint32_t anchor = 0, tailc = qh;  // the caller drained the queue: tail == qh
 
     if (n >= 13u) {
         const uint32_t mfl1 = n - 11u;       // mflimit + 1: a probe happens only if the NEXT probe position is <= this
@@ -158,8 +304,8 @@ CW_DEV uint32_t cw_lz4_compress_warp(const uint8_t *s, uint32_t n, uint16_t *tab
                 dyn_all = cw_ballot(valid && (M & lower) != 0u);  // lanes that may have an in-window candidate
             }
             // ---------------- phase B ----------------
-            uint32_t ins = 0, i0 = 0, pend = CW_LZ4_NONE, nrec = 0;
-            uint32_t r_src = 0, r_lit = 0, r_off = 0, r_mcode = 0, r_op = 0;  // lane k: k-th sequence of this window
+            uint32_t ins = 0, i0 = 0, pend = CW_LZ4_NONE;
+            const uint32_t qh0 = qh;
             bool restart = false;
             for (;;) {
                 const uint32_t range = ~((1u << i0) - 1u);
@@ -188,69 +334,24 @@ CW_DEV uint32_t cw_lz4_compress_warp(const uint8_t *s, uint32_t n, uint16_t *tab
                 ins |= range & ((2u << f) - 1u);
                 const uint32_t cur = unit ? base + (uint32_t)f : cw_shfl(pos, (unsigned)f);
                 const uint32_t cnd = cw_shfl(cand, (unsigned)f);
-                // ---- extend: lanes 0..27 compare 4 bytes each forward from cur+4, lanes 28..31 one byte each
-                // backward; one branch-free instruction stream for both roles ----
-                uint32_t fwd = 0, back = 0;
-                {
-                    const uint32_t maxb = cw_umin(cur - anchor, cnd);
-                    const bool fl = lane < CW_LZ4_FW_LANES;
-                    const uint32_t xb = lane - (CW_LZ4_FW_LANES - 1u);  // 1..4 on the backward lanes
-                    const bool bl = !fl && xb <= maxb;                  // backward lane with a byte to look at
-                    uint32_t pa = fl ? cur + 4u + 4u * lane : (bl ? cur - xb : 0u);
-                    uint32_t pb = fl ? cnd + 4u + 4u * lane : (bl ? cnd - xb : 0u);
-                    uint32_t d = cw_lz4_read32(s, pa) ^ cw_lz4_read32(s, pb);
+                // ---- forward extension by the whole warp: 32 lanes x 4 bytes per step from cur+4 ----
+                uint32_t fwd = 0;
+                for (;;) {
+                    const uint32_t pa = cur + 4u + fwd + 4u * lane, pb = cnd + 4u + fwd + 4u * lane;
+                    const uint32_t d = cw_lz4_read32(s, pa) ^ cw_lz4_read32(s, pb);
                     uint32_t eq = d ? (uint32_t)(cw_ffs(d) - 1) >> 3 : 4u;  // equal leading bytes
-                    const uint32_t room = pa < matchlimit ? matchlimit - pa : 0u;
-                    eq = fl ? cw_umin(eq, room) : eq;
-                    const bool stopl = fl ? eq < 4u : !(bl && eq != 0u);
-                    const uint32_t stop = cw_ballot(stopl);
-                    uint32_t fstop = stop & ((1u << CW_LZ4_FW_LANES) - 1u);
-                    const uint32_t bstop = stop >> CW_LZ4_FW_LANES;
-                    while (!fstop) {  // more than 112 equal bytes: keep going, all 32 lanes forward
-                        fwd += fwd ? 128u : 4u * CW_LZ4_FW_LANES;
-                        pa = cur + 4u + fwd + 4u * lane;
-                        pb = cnd + 4u + fwd + 4u * lane;
-                        d = cw_lz4_read32(s, pa) ^ cw_lz4_read32(s, pb);
-                        eq = d ? (uint32_t)(cw_ffs(d) - 1) >> 3 : 4u;
-                        eq = cw_umin(eq, pa < matchlimit ? matchlimit - pa : 0u);
-                        fstop = cw_ballot(eq < 4u);
-                    }
-                    {
-                        const unsigned L = (unsigned)cw_ffs(fstop) - 1u;
+                    eq = cw_umin(eq, pa < matchlimit ? matchlimit - pa : 0u);
+                    const uint32_t stop = cw_ballot(eq < 4u);
+                    if (stop) {
+                        const unsigned L = (unsigned)cw_ffs(stop) - 1u;
                         fwd += 4u * L + cw_shfl(eq, L);
+                        break;
                     }
-                    if (bstop) {
-                        back = (uint32_t)cw_ffs(bstop) - 1u;
-                    } else {  // 4 equal bytes before the match and room for more: whole warp, byte-wise
-                        back = 4u;
-                        for (;;) {
-                            const uint32_t x = back + lane + 1u;
-                            const bool ok = x <= maxb && s[cur - cw_umin(x, cur)] == s[cnd - cw_umin(x, cnd)];
-                            const uint32_t bs = cw_ballot(!ok);
-                            if (bs) {
-                                back += (uint32_t)cw_ffs(bs) - 1u;
-                                break;
-                            }
-                            back += 32u;
-                        }
-                    }
+                    fwd += 128u;
                 }
                 const uint32_t e = cur + 4u + fwd;  // end of the match = next parser position
-                // ---- record the sequence: token, literal length, literals, offset, match length ----
-                {
-                    const uint32_t lit = cur - back - anchor;
-                    const uint32_t mcode = back + fwd;  // match length - 4
-                    if (lane == nrec) {
-                        r_src = anchor;
-                        r_lit = lit;
-                        r_off = cur - cnd;
-                        r_mcode = mcode;
-                        r_op = op;
-                    }
-                    nrec++;
-                    op += 3u + lit;
-                    if ((lit | mcode) >= 15u) op += cw_lz4_ext_bytes(lit) + cw_lz4_ext_bytes(mcode);  // rare in text
-                }
+                // everything else about this sequence (backward extension, lengths, bytes) is the emitter's job
+                cw_lz4_q_push(q, qh, tailc, anchor | (cur << 16), cnd | (fwd << 16), lane);
                 anchor = e;
                 if (e >= mfl1) {  // "if (ip > mflimit) break" -> last literals
                     done = true;
@@ -268,29 +369,7 @@ CW_DEV uint32_t cw_lz4_compress_warp(const uint8_t *s, uint32_t n, uint16_t *tab
                 restart = true;
                 break;
             }
-            // ---------------- phase D: write the recorded sequences, one lane each ----------------
-            if (nrec) {
-                const bool mine = lane < nrec;
-                if (mine) {
-                    uint32_t p = r_op;
-                    out[p++] = (uint8_t)((cw_umin(r_lit, 15u) << 4) | cw_umin(r_mcode, 15u));
-                    if (r_lit >= 15u) p = cw_lz4_put_ext1(out, p, r_lit - 15u);
-                    if (r_lit <= CW_LZ4_LIT_SELF)
-                        for (uint32_t x = 0; x < r_lit; x++) out[p + x] = s[r_src + x];
-                    p += r_lit;
-                    out[p] = (uint8_t)r_off;
-                    out[p + 1u] = (uint8_t)(r_off >> 8);
-                    if (r_mcode >= 15u) cw_lz4_put_ext1(out, p + 2u, r_mcode - 15u);
-                }
-                uint32_t big = cw_ballot(mine && r_lit > CW_LZ4_LIT_SELF);
-                while (big) {
-                    const unsigned k = (unsigned)cw_ffs(big) - 1u;
-                    big &= big - 1u;
-                    const uint32_t lit = cw_shfl(r_lit, k);
-                    const uint32_t dst = cw_shfl(r_op, k) + 1u + cw_lz4_ext_bytes(lit);
-                    cw_lz4_copy_warp(out, dst, s, cw_shfl(r_src, k), lit, lane);
-                }
-            }
+            if (qh != qh0) cw_lz4_q_publish(q, qh, lane);
             if (done) break;
             // ---------------- phase C: every touched slot gets its final value ----------------
             if (twins) {
@@ -313,16 +392,7 @@ CW_DEV uint32_t cw_lz4_compress_warp(const uint8_t *s, uint32_t n, uint16_t *tab
             else j0 += 32;
         }
     }
-    // ---- last literals ----
-    {
-        const uint32_t lit = n - anchor;
-        if (lane == 0) {
-            out[op] = (uint8_t)(cw_umin(lit, 15u) << 4);
-            if (lit >= 15u) cw_lz4_put_ext1(out, op + 1u, lit - 15u);
-        }
-        op += 1u + cw_lz4_ext_bytes(lit);
-        cw_lz4_copy_warp(out, op, s, anchor, lit, lane);
-        op += lit;
-    }
-    return op;
+    // ---- end of chunk: the final literal run [anchor, n) ----
+    cw_lz4_q_push(q, qh, tailc, anchor | (CW_LZ4_REC_END << 16), 0u, lane);
+    cw_lz4_q_publish(q, qh, lane);
 }

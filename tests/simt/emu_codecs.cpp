@@ -20,12 +20,40 @@ struct Job {
     int mode;
 };
 
-static void lz4_body(void *a)
+// LZ4: a two-warp CTA -- warp 0 parses and pushes records, warp 1 is the emitter (csrc/lz4_warp.cuh)
+struct Lz4Job {
+    const uint8_t *s;
+    uint32_t n;
+    uint16_t *table;
+    CwLz4Queue *q;
+    uint8_t *out;
+    uint32_t lens[1];
+    int hashlog;
+};
+
+static void lz4_block_body(void *a, int warp)
 {
-    Job *j = (Job *)a;
-    uint32_t r = j->mode == 12 ? cw_lz4_compress_warp<12>(j->s, j->n, j->table, j->out)
-                               : cw_lz4_compress_warp<13>(j->s, j->n, j->table, j->out);
-    if (cw_lane() == 0) j->result = r;
+    Lz4Job *j = (Lz4Job *)a;
+    const unsigned lane = cw_lane();
+    if (warp == 0) {
+        uint32_t qh = 0;
+        if (j->hashlog == 12) cw_lz4_parse_warp<12>(j->s, j->n, j->table, j->q, qh);
+        else cw_lz4_parse_warp<13>(j->s, j->n, j->table, j->q, qh);
+        cw_lz4_q_drain(j->q, qh, lane);
+        if (lane == 0) {
+            cw_fence_cta();
+            cw_st_vol(&j->q->done, 1u);
+        }
+    } else {
+        for (;;) {
+            uint32_t d = 0;
+            if (lane == 0) d = cw_ld_vol(&j->q->done);
+            d = cw_shfl(d, 0);
+            const uint32_t cnt = cw_lz4_emit_batch(j->q, j->s, j->n, j->out, 0, j->lens);
+            if (d && cnt == 0) break;
+            if (!cnt) cw_spin();
+        }
+    }
 }
 
 extern "C" uint32_t emu_lz4_compress_hl(const uint8_t *src, uint32_t n, uint8_t *out, int hashlog)
@@ -33,11 +61,12 @@ extern "C" uint32_t emu_lz4_compress_hl(const uint8_t *src, uint32_t n, uint8_t 
     std::vector<uint32_t> staged((n + CW_LZ4_PAD + 3) / 4 + 4, 0);  // 4-byte aligned, zero padded like the kernel's smem
     memcpy(staged.data(), src, n);
     std::vector<uint16_t> table(1u << hashlog, 0);
-    Job j{(const uint8_t *)staged.data(), n, table.data(), nullptr, out, 0, 0, hashlog};
-    cwemu::run_warp(lz4_body, &j);
-    return j.result;
+    CwLz4Queue q;
+    memset(&q, 0, sizeof q);
+    Lz4Job j{(const uint8_t *)staged.data(), n, table.data(), &q, out, {0}, hashlog};
+    cwemu::run_block(2, lz4_block_body, &j);
+    return j.lens[0];
 }
-
 extern "C" uint32_t emu_lz4_compress(const uint8_t *src, uint32_t n, uint8_t *out) { return emu_lz4_compress_hl(src, n, out, 13); }
 
 #ifdef HAVE_LZF

@@ -3,57 +3,77 @@
 
 namespace cwemu {
 
-thread_local Warp *g_warp = nullptr;
+thread_local Block *g_block = nullptr;
 
 static void trampoline()
 {
-    Warp *w = g_warp;
-    w->body(w->arg);
-    w->finished[w->cur] = true;
-    swapcontext(&w->ctx[w->cur], &w->sched);
+    Block *b = g_block;
+    const int me = b->cur;
+    b->body(b->arg, me >> 5);
+    b->finished[me] = true;
+    b->progress++;
+    swapcontext(&b->ctx[me], &b->sched);
 }
+
+void run_block(int nwarps, void (*body)(void *, int), void *arg)
+{
+    static const size_t STACK = 256 * 1024;
+    const int nf = nwarps * 32;
+    Block *b = new Block();
+    b->nwarps = nwarps;
+    b->warps = new Warp[nwarps]();
+    b->ctx = new ucontext_t[nf];
+    b->stack = new char *[nf];
+    b->finished = new bool[nf]();
+    b->progress = 0;
+    b->body = body;
+    b->arg = arg;
+    g_block = b;
+    for (int i = 0; i < nf; i++) {
+        b->stack[i] = (char *)malloc(STACK);
+        getcontext(&b->ctx[i]);
+        b->ctx[i].uc_stack.ss_sp = b->stack[i];
+        b->ctx[i].uc_stack.ss_size = STACK;
+        b->ctx[i].uc_link = &b->sched;
+        makecontext(&b->ctx[i], trampoline, 0);
+    }
+    int live = nf, idle_rounds = 0;
+    while (live) {
+        const uint64_t p0 = b->progress;
+        for (int i = 0; i < nf; i++) {
+            if (b->finished[i]) continue;
+            b->cur = i;
+            swapcontext(&b->sched, &b->ctx[i]);
+            if (b->finished[i]) live--;
+        }
+        if (live && b->progress == p0) {
+            if (++idle_rounds > 64) {
+                fprintf(stderr, "warp_emu: deadlock -- %d fibres alive, none makes progress (divergent warp collective "
+                                "or warps spinning on each other)\n", live);
+                abort();
+            }
+        } else
+            idle_rounds = 0;
+    }
+    for (int i = 0; i < nf; i++) free(b->stack[i]);
+    delete[] b->warps;
+    delete[] b->ctx;
+    delete[] b->stack;
+    delete[] b->finished;
+    delete b;
+    g_block = nullptr;
+}
+
+struct OneWarp {
+    void (*body)(void *);
+    void *arg;
+};
+static void one_warp_body(void *a, int) { ((OneWarp *)a)->body(((OneWarp *)a)->arg); }
 
 void run_warp(void (*body)(void *), void *arg)
 {
-    static const size_t STACK = 256 * 1024;
-    Warp *w = new Warp();
-    memset(w->finished, 0, sizeof w->finished);
-    w->arrived = 0;
-    w->generation = 0;
-    w->body = body;
-    w->arg = arg;
-    g_warp = w;
-    for (int i = 0; i < 32; i++) {
-        w->stack[i] = (char *)malloc(STACK);
-        getcontext(&w->ctx[i]);
-        w->ctx[i].uc_stack.ss_sp = w->stack[i];
-        w->ctx[i].uc_stack.ss_size = STACK;
-        w->ctx[i].uc_link = &w->sched;
-        makecontext(&w->ctx[i], trampoline, 0);
-    }
-    int live = 32;
-    while (live) {
-        const uint64_t gen0 = w->generation;
-        const int live0 = live;
-        for (int i = 0; i < 32; i++) {
-            if (w->finished[i]) continue;
-            w->cur = i;
-            swapcontext(&w->sched, &w->ctx[i]);
-            if (w->finished[i]) live--;
-        }
-        if (live && live == live0 && w->generation == gen0) {
-            fprintf(stderr, "warp_emu: deadlock -- %d lanes wait at a collective the others never reach "
-                            "(divergent warp collective)\n", w->arrived);
-            abort();
-        }
-        if (live && live != 32 && live != 0 && w->arrived + (32 - live) == 32 && w->generation == gen0) {
-            fprintf(stderr, "warp_emu: %d lanes exited while others wait at a collective\n", 32 - live);
-            abort();
-        }
-    }
-    for (int i = 0; i < 32; i++) free(w->stack[i]);
-    delete w;
-    g_warp = nullptr;
+    OneWarp w{body, arg};
+    run_block(1, one_warp_body, &w);
 }
 
 }  // namespace cwemu

@@ -1,10 +1,12 @@
-// warp_emu.h -- lane-accurate emulation of one CUDA warp on the CPU (TEST INFRASTRUCTURE ONLY).
+// warp_emu.h -- lane-accurate emulation of CUDA warps on the CPU (TEST INFRASTRUCTURE ONLY).
 //
 // The build container has no GPU.  To check the warp-cooperative kernels (csrc/lz4_warp.cuh,
 // csrc/lzf_warp.cuh) bit-for-bit against the oracle before spending GPU time, the same device source is
-// compiled as plain C++ and run here: 32 fibres (ucontext) execute the per-lane code, and every warp
-// collective (ballot / shfl / match_any / syncwarp) is a rendezvous of all 32 fibres.  A collective reached
-// by only part of the warp (divergence bug) is reported as a deadlock instead of hanging.
+// compiled as plain C++ and run here: every warp is 32 fibres (ucontext) executing the per-lane code, and
+// every warp collective (ballot / shfl / match_any / syncwarp) is a rendezvous of the 32 fibres of that warp.
+// Several warps can run together (a CTA with specialised warps talking through "shared memory"); a fibre
+// that spins on a flag yields with cw_spin().  A collective reached by only part of a warp (divergence
+// bug) or a set of warps that all spin forever is reported as a deadlock instead of hanging.
 // Nothing in the product links against this file.
 #pragma once
 #include <stdint.h>
@@ -16,49 +18,60 @@
 namespace cwemu {
 
 struct Warp {
-    ucontext_t sched;
-    ucontext_t ctx[32];
-    char *stack[32];
-    bool finished[32];
-    int cur;                 // running lane
-    uint32_t slot[32];       // values deposited for the current collective
-    uint32_t snap[2][32];    // published values of the last two collectives
+    uint32_t slot[32];     // values deposited for the current collective
+    uint32_t snap[2][32];  // published values of the last two collectives
     int arrived;
     uint64_t generation;
-    void (*body)(void *);
+};
+
+struct Block {
+    ucontext_t sched;
+    int nwarps;
+    Warp *warps;
+    ucontext_t *ctx;  // nwarps * 32
+    char **stack;
+    bool *finished;
+    int cur;  // running fibre = warp * 32 + lane
+    uint64_t progress;  // bumped by every completed collective / finished fibre / explicit progress mark
+    void (*body)(void *, int warp);
     void *arg;
 };
 
-extern thread_local Warp *g_warp;
+extern thread_local Block *g_block;
 
-inline void yield_lane()
+inline void yield_fibre()
 {
-    Warp *w = g_warp;
-    swapcontext(&w->ctx[w->cur], &w->sched);
+    Block *b = g_block;
+    swapcontext(&b->ctx[b->cur], &b->sched);
 }
 
-// rendezvous: every live lane deposits v; returns the snapshot array of this collective
+// rendezvous of the calling fibre's warp: every lane deposits v; returns the snapshot array of this collective
 inline const uint32_t *collective(uint32_t v)
 {
-    Warp *w = g_warp;
-    const int me = w->cur;
+    Block *b = g_block;
+    Warp *w = &b->warps[b->cur >> 5];
+    const int me = b->cur & 31;
     w->slot[me] = v;
     const uint64_t gen = w->generation;
     if (++w->arrived == 32) {
         memcpy(w->snap[gen & 1], w->slot, sizeof w->slot);
         w->arrived = 0;
         w->generation = gen + 1;
+        b->progress++;
     } else {
-        while (w->generation == gen) yield_lane();
+        while (w->generation == gen) yield_fibre();
     }
     return w->snap[gen & 1];
 }
 
+// run nwarps warps; body(arg, warp) is executed by each of the 32 lanes of every warp
+void run_block(int nwarps, void (*body)(void *, int), void *arg);
+// single warp convenience
 void run_warp(void (*body)(void *), void *arg);
 
 }  // namespace cwemu
 
-static inline unsigned cw_lane() { return (unsigned)cwemu::g_warp->cur; }
+static inline unsigned cw_lane() { return (unsigned)(cwemu::g_block->cur & 31); }
 static inline unsigned cw_ballot(bool p)
 {
     const uint32_t *s = cwemu::collective(p ? 1u : 0u);
@@ -83,3 +96,12 @@ static inline uint32_t cw_funnel_r(uint32_t lo, uint32_t hi, unsigned sh)
     sh &= 31u;
     return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
 }
+// inter-warp communication through shared memory
+static inline uint32_t cw_ld_vol(const uint32_t *p) { return *(const volatile uint32_t *)p; }
+static inline void cw_st_vol(uint32_t *p, uint32_t v)
+{
+    *(volatile uint32_t *)p = v;
+    cwemu::g_block->progress++;
+}
+static inline void cw_fence_cta() { __sync_synchronize(); }
+static inline void cw_spin() { cwemu::yield_fibre(); }

@@ -31,21 +31,32 @@
 #define CW_FUSED_MAX_COMP_WARPS 14
 #define CW_FUSED_MAX_THREADS ((CW_FUSED_HASH_WARPS_MAX + CW_FUSED_MAX_COMP_WARPS + 3) * 32)  // + emitters
 
-static int fused_hash_warps()
+// measured on the synthetic mix (profiles/r01_tune_emitters_hashwarps.txt): the 9-parser compat kernel is best
+// with 1 hash warp + 3 emitters, the 13-parser fast kernel with 2 + 2
+static int fused_hash_warps(bool fast)
 {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("CW_FUSED_HASH_WARPS");  // tuning knob for the profiling scripts
-        v = e ? atoi(e) : CW_FUSED_HASH_WARPS_DEFAULT;
-        if (v < 1) v = 1;
+        v = e ? atoi(e) : 0;
         if (v > CW_FUSED_HASH_WARPS_MAX) v = CW_FUSED_HASH_WARPS_MAX;
     }
-    return v;
+    return v > 0 ? v : (fast ? 2 : CW_FUSED_HASH_WARPS_DEFAULT);
 }
 
 enum { CW_C_LZ4 = 0, CW_C_LZF = 1, CW_C_LZ4_FAST = 2 };  // LZ4 with the reference's 13-bit table / LZF / LZ4 with a 12-bit table
 
-#define CW_FUSED_EMITTERS 3  // emitter warps per CTA (LZ4 only)
+#define CW_FUSED_EMITTERS_DEFAULT 3  // emitter warps per CTA (LZ4 only)
+static int fused_emitters(bool fast)
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("CW_LZ4_EMITTERS");  // tuning knob for the profiling scripts
+        v = e ? atoi(e) : 0;
+        if (v > 3) v = 3;
+    }
+    return v > 0 ? v : (fast ? 2 : CW_FUSED_EMITTERS_DEFAULT);
+}
 
 template <int CALG>
 __host__ __device__ constexpr uint32_t cw_slot_bytes(uint32_t chunk)
@@ -112,11 +123,11 @@ static cudaError_t launch_one(const CwDeviceInfo &dev, int max_dyn_smem, const C
     int parsers = max_dyn_smem / (int)per;
     if (parsers < 1) return cudaErrorInvalidValue;
     if (parsers > CW_FUSED_MAX_COMP_WARPS) parsers = CW_FUSED_MAX_COMP_WARPS;
-    int emitters = CALG == CW_C_LZF ? 0 : CW_FUSED_EMITTERS;
+    int emitters = CALG == CW_C_LZF ? 0 : fused_emitters(CALG == CW_C_LZ4_FAST);
     if (emitters > parsers) emitters = parsers;
     uint64_t ctas = (n + (uint64_t)parsers - 1) / (uint64_t)parsers;
     if (ctas > (uint64_t)dev.sm_count) ctas = (uint64_t)dev.sm_count;
-    kern<<<(unsigned)ctas, (parsers + emitters + fused_hash_warps()) * 32, (size_t)parsers * per, st>>>(
+    kern<<<(unsigned)ctas, (parsers + emitters + fused_hash_warps(CALG == CW_C_LZ4_FAST)) * 32, (size_t)parsers * per, st>>>(
         iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, slot, (uint32_t)parsers, (uint32_t)emitters);
     return cudaGetLastError();
 }

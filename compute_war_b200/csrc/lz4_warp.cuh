@@ -46,6 +46,9 @@
 
 #define CW_LZ4_NONE 0xffffffffu
 #define CW_LZ4_PAD 144u       // readable bytes after the chunk: the forward compare reads up to 131 bytes past n-12
+#ifndef CW_LZ4_SPEC_STEPS
+#define CW_LZ4_SPEC_STEPS 3     // per-lane speculative forward extension in phase A: 4 bytes per step
+#endif
 #define CW_LZ4_LIT_SELF 16u   // literal runs up to this long are copied by the recording lane itself
 #define CW_LZ4_TAG 0x8000u    // slot tag used for twin detection (chunks <= 32768 bytes: positions < 0x8000)
 
@@ -116,8 +119,9 @@ struct CwLz4Queue {
     uint32_t rec[CW_LZ4_QLEN][2];  // {anchor | cur << 16, cand | fwd << 16}
 };
 
-// parser side: push one record (all lanes call with the same values; qh = records pushed so far, tailc = cached tail)
-CW_DEV void cw_lz4_q_push(CwLz4Queue *q, uint32_t &qh, uint32_t &tailc, uint32_t a, uint32_t b, unsigned lane)
+// parser side: push one record; lane `writer` holds the values (qh = records pushed so far, tailc = cached tail)
+CW_DEV void cw_lz4_q_push(CwLz4Queue *q, uint32_t &qh, uint32_t &tailc, uint32_t a, uint32_t b, unsigned lane,
+                          unsigned writer)
 {
     if (qh - tailc >= CW_LZ4_QLEN) {  // ring looks full: publish what we have and wait for the emitter
         cw_syncwarp();
@@ -133,7 +137,7 @@ CW_DEV void cw_lz4_q_push(CwLz4Queue *q, uint32_t &qh, uint32_t &tailc, uint32_t
             cw_spin();
         }
     }
-    if (lane == 0) {
+    if (lane == writer) {
         q->rec[qh & (CW_LZ4_QLEN - 1u)][0] = a;
         q->rec[qh & (CW_LZ4_QLEN - 1u)][1] = b;
     }
@@ -295,8 +299,34 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
                 owner = valid && !(M & ~((2u << lane) - 1u));  // highest lane of the group
             }
             const bool tmatch = valid && cw_lz4_read32(s, t) == v;
+            // speculative forward extension against the table candidate, every matching lane for itself:
+            // spec = equal bytes after the 4-byte match; bit 15 = "still equal after CW_LZ4_SPEC_STEPS steps"
             const uint32_t tm_all = cw_ballot(tmatch);
+            uint32_t spec = 0x8000u;
+            if (CW_LZ4_SPEC_STEPS > 0 && tm_all) {
+                uint32_t fw = 0;
+                bool open = tmatch;
+                const uint32_t first = tm_all & (0u - tm_all);  // the lane the replay will look at first
+#pragma unroll
+                for (int k = 0; k < CW_LZ4_SPEC_STEPS; k++) {
+                    if (open) {
+                        const uint32_t pa = pos + 4u + fw;
+                        const uint32_t d = cw_lz4_read32(s, pa) ^ cw_lz4_read32(s, t + 4u + fw);
+                        uint32_t eq = d ? (uint32_t)(cw_ffs(d) - 1) >> 3 : 4u;
+                        eq = cw_umin(eq, pa < matchlimit ? matchlimit - pa : 0u);
+                        fw += eq;
+                        open = eq == 4u;
+                    }
+                    const uint32_t openm = cw_ballot(open);
+                    // stop when nobody is left, or when the first match is a long one: the whole warp will
+                    // extend it anyway and most of the window lies inside it
+                    if (!openm || (openm & first)) break;
+                }
+                if (tmatch) spec = fw | (open ? 0x8000u : 0u);
+            }
             const uint32_t inv_all = cw_ballot(!valid);
+            // valid lanes form a prefix of the window (positions increase with the lane)
+            const uint32_t vmask = inv_all ? (1u << (cw_ffs(inv_all) - 1)) - 1u : 0xffffffffu;
             uint32_t E = own, dyn_all = 0;
             if (twins) {
                 if (tag_ok) M = cw_match_any(valid ? h : 0x10000u + lane);
@@ -310,7 +340,7 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
             for (;;) {
                 const uint32_t range = ~((1u << i0) - 1u);
                 uint32_t hitm = tm_all & range;
-                uint32_t cand = t;
+                uint32_t cand = t, sp = spec;
                 if (dyn_all & range) {
                     const uint32_t cm = M & (ins | range) & lower;
                     bool hit = tmatch;
@@ -318,40 +348,41 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
                         const int jl = 31 - cw_clz(cm);
                         hit = valid && ((E >> jl) & 1u);
                         cand = unit ? base + (uint32_t)jl : sbase + (uint32_t)cw_lz4_S(j0 + jl);
+                        sp = 0x8000u;  // candidate inside the window: nothing speculated
                     }
                     hitm = cw_ballot(hit) & range;
                 }
-                const uint32_t invm = inv_all & range;
-                const int f = cw_ffs(hitm) - 1, iv = cw_ffs(invm) - 1;
-                if (iv >= 0 && (f < 0 || iv < f)) {  // the parser's end-of-input rule fires first
-                    done = true;
+                if (!hitm) {  // no (further) match in this window: the rest of its valid lanes were probed;
+                    ins |= range & vmask;  // an invalid lane in range is the parser's end-of-input rule
+                    done = (range & ~vmask) != 0u;
                     break;
                 }
-                if (f < 0) {  // rest of the window probed, no match
-                    ins |= range;
-                    break;
-                }
+                const unsigned f = (unsigned)cw_ffs(hitm) - 1u;
                 ins |= range & ((2u << f) - 1u);
-                const uint32_t cur = unit ? base + (uint32_t)f : cw_shfl(pos, (unsigned)f);
-                const uint32_t cnd = cw_shfl(cand, (unsigned)f);
-                // ---- forward extension by the whole warp: 32 lanes x 4 bytes per step from cur+4 ----
-                uint32_t fwd = 0;
-                for (;;) {
-                    const uint32_t pa = cur + 4u + fwd + 4u * lane, pb = cnd + 4u + fwd + 4u * lane;
-                    const uint32_t d = cw_lz4_read32(s, pa) ^ cw_lz4_read32(s, pb);
-                    uint32_t eq = d ? (uint32_t)(cw_ffs(d) - 1) >> 3 : 4u;  // equal leading bytes
-                    eq = cw_umin(eq, pa < matchlimit ? matchlimit - pa : 0u);
-                    const uint32_t stop = cw_ballot(eq < 4u);
-                    if (stop) {
-                        const unsigned L = (unsigned)cw_ffs(stop) - 1u;
-                        fwd += 4u * L + cw_shfl(eq, L);
-                        break;
+                const uint32_t cur = unit ? base + f : cw_shfl(pos, f);
+                sp = cw_shfl(sp, f);
+                uint32_t fwd = sp & 0x7fffu;
+                if (sp & 0x8000u) {
+                    // ---- forward extension by the whole warp: 32 lanes x 4 bytes per step, continuing at fwd ----
+                    const uint32_t cnd = cw_shfl(cand, f);
+                    for (;;) {
+                        const uint32_t pa = cur + 4u + fwd + 4u * lane, pb = cnd + 4u + fwd + 4u * lane;
+                        const uint32_t d = cw_lz4_read32(s, pa) ^ cw_lz4_read32(s, pb);
+                        uint32_t eq = d ? (uint32_t)(cw_ffs(d) - 1) >> 3 : 4u;  // equal leading bytes
+                        eq = cw_umin(eq, pa < matchlimit ? matchlimit - pa : 0u);
+                        const uint32_t stop = cw_ballot(eq < 4u);
+                        if (stop) {
+                            const unsigned L = (unsigned)cw_ffs(stop) - 1u;
+                            fwd += 4u * L + cw_shfl(eq, L);
+                            break;
+                        }
+                        fwd += 128u;
                     }
-                    fwd += 128u;
                 }
                 const uint32_t e = cur + 4u + fwd;  // end of the match = next parser position
-                // everything else about this sequence (backward extension, lengths, bytes) is the emitter's job
-                cw_lz4_q_push(q, qh, tailc, anchor | (cur << 16), cnd | (fwd << 16), lane);
+                // everything else about this sequence (backward extension, lengths, bytes) is the emitter's job;
+                // the matching lane itself holds the candidate, so it writes the record
+                cw_lz4_q_push(q, qh, tailc, anchor | (cur << 16), cand | (fwd << 16), lane, f);
                 anchor = e;
                 if (e >= mfl1) {  // "if (ip > mflimit) break" -> last literals
                     done = true;
@@ -360,12 +391,11 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
                 // parser: table[hash(e-2)] = e-2, then immediate re-test at e, then a fresh search at e+1
                 sbase = e + 1u;
                 const uint32_t de = e - base;  // lane index of the next parser position (unit windows)
-                if (unit && de < 34u) ins |= 1u << (de - 2u);
-                else pend = e - 2u;
-                if (unit && de < 32u) {
-                    i0 = de;
-                    continue;
-                }
+                const bool in2 = unit && de < 34u, in0 = unit && de < 32u;
+                ins |= in2 ? 1u << ((de - 2u) & 31u) : 0u;
+                pend = in2 ? pend : e - 2u;
+                i0 = de;
+                if (in0) continue;
                 restart = true;
                 break;
             }
@@ -393,6 +423,6 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
         }
     }
     // ---- end of chunk: the final literal run [anchor, n) ----
-    cw_lz4_q_push(q, qh, tailc, anchor | (CW_LZ4_REC_END << 16), 0u, lane);
+    cw_lz4_q_push(q, qh, tailc, anchor | (CW_LZ4_REC_END << 16), 0u, lane, 0u);
     cw_lz4_q_publish(q, qh, lane);
 }

@@ -49,6 +49,10 @@
 #ifndef CW_LZ4_SPEC_STEPS
 #define CW_LZ4_SPEC_STEPS 3     // per-lane speculative forward extension in phase A: 4 bytes per step
 #endif
+#ifndef CW_LZ4_STATIC_PATH
+#define CW_LZ4_STATIC_PATH 0   // replay of twin-free unit windows without per-match bookkeeping: +6 % on text,
+                               // -4..-13 % on the mixed stream (profiles/r01_ab_static_spec.txt) -> off
+#endif
 #define CW_LZ4_LIT_SELF 16u   // literal runs up to this long are copied by the recording lane itself
 #define CW_LZ4_TAG 0x8000u    // slot tag used for twin detection (chunks <= 32768 bytes: positions < 0x8000)
 
@@ -142,6 +146,24 @@ CW_DEV void cw_lz4_q_push(CwLz4Queue *q, uint32_t &qh, uint32_t &tailc, uint32_t
         q->rec[qh & (CW_LZ4_QLEN - 1u)][1] = b;
     }
     qh++;
+}
+// parser side: make room for `need` (<= 32) records that the lanes are about to write themselves
+CW_DEV void cw_lz4_q_reserve(CwLz4Queue *q, uint32_t qh, uint32_t &tailc, uint32_t need, unsigned lane)
+{
+    if (qh + need - tailc > CW_LZ4_QLEN) {
+        cw_syncwarp();
+        if (lane == 0) {
+            cw_fence_cta();
+            cw_st_vol(&q->head, qh);
+        }
+        for (;;) {
+            uint32_t t = 0;
+            if (lane == 0) t = cw_ld_vol(&q->tail);
+            tailc = cw_shfl(t, 0);
+            if (qh + need - tailc <= CW_LZ4_QLEN) break;
+            cw_spin();
+        }
+    }
 }
 CW_DEV void cw_lz4_q_publish(CwLz4Queue *q, uint32_t qh, unsigned lane)
 {
@@ -265,6 +287,7 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
         uint32_t sbase = 1;                  // first position of the current search
         int32_t j0 = 0;                      // search index of lane 0 in the next window
         bool done = false;
+        bool spec_on = true;  // speculate only while matches are short (text-like data); long matches go to the warp-wide path
         while (!done) {
             // ---------------- phase A ----------------
             const bool unit = (j0 + 31 <= 64);  // all 32 probes one byte apart
@@ -302,8 +325,8 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
             // speculative forward extension against the table candidate, every matching lane for itself:
             // spec = equal bytes after the 4-byte match; bit 15 = "still equal after CW_LZ4_SPEC_STEPS steps"
             const uint32_t tm_all = cw_ballot(tmatch);
-            uint32_t spec = 0x8000u;
-            if (CW_LZ4_SPEC_STEPS > 0 && tm_all) {
+            uint32_t spec = 0x80000000u;
+            if (CW_LZ4_SPEC_STEPS > 0 && spec_on && tm_all) {
                 uint32_t fw = 0;
                 bool open = tmatch;
                 const uint32_t first = tm_all & (0u - tm_all);  // the lane the replay will look at first
@@ -322,7 +345,7 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
                     // extend it anyway and most of the window lies inside it
                     if (!openm || (openm & first)) break;
                 }
-                if (tmatch) spec = fw | (open ? 0x8000u : 0u);
+                if (tmatch) spec = fw | (open ? 0x80000000u : 0u);
             }
             const uint32_t inv_all = cw_ballot(!valid);
             // valid lanes form a prefix of the window (positions increase with the lane)
@@ -337,6 +360,78 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
             uint32_t ins = 0, i0 = 0, pend = CW_LZ4_NONE;
             const uint32_t qh0 = qh;
             bool restart = false;
+            if (CW_LZ4_STATIC_PATH && unit && !dyn_all) {
+                // Static window (the common case): every hitting lane's candidate is its table entry, so the
+                // replay only has to walk "first hit at or after the previous match's end".  The loop carries
+                // nothing but that; records, the inserted-lanes mask and the anchors are derived afterwards by
+                // all selected lanes in parallel.
+                const uint32_t dlim = cw_umin(32u, mfl1 - base);  // a match ending here or later leaves the window / the input
+                uint32_t S = 0, last_de = 0;                      // selected lanes; end (lane index) of the last match
+                for (;;) {
+                    const uint32_t hm = tm_all & ~((1u << i0) - 1u);
+                    if (!hm) break;
+                    const unsigned f = (unsigned)cw_ffs(hm) - 1u;
+                    const uint32_t sp = cw_shfl(spec, f);
+                    uint32_t fwd = sp & 0x7fffffffu;
+                    if (sp & 0x80000000u) {  // long match: the whole warp extends it, 32 lanes x 4 bytes per step
+                        const uint32_t cur = base + f, cnd = cw_shfl(t, f);
+                        for (;;) {
+                            const uint32_t pa = cur + 4u + fwd + 4u * lane, pb = cnd + 4u + fwd + 4u * lane;
+                            const uint32_t d = cw_lz4_read32(s, pa) ^ cw_lz4_read32(s, pb);
+                            uint32_t eq = d ? (uint32_t)(cw_ffs(d) - 1) >> 3 : 4u;
+                            eq = cw_umin(eq, pa < matchlimit ? matchlimit - pa : 0u);
+                            const uint32_t stop = cw_ballot(eq < 4u);
+                            if (stop) {
+                                const unsigned L = (unsigned)cw_ffs(stop) - 1u;
+                                fwd += 4u * L + cw_shfl(eq, L);
+                                break;
+                            }
+                            fwd += 128u;
+                        }
+                        if (lane == f) spec = fwd;
+                    }
+                    S |= 1u << f;
+                    spec_on = fwd < 28u;
+                    last_de = f + 4u + fwd;
+                    if (last_de >= dlim) break;
+                    i0 = last_de;
+                }
+                if (S) {
+                    const bool sel = (S >> lane) & 1u;
+                    const uint32_t myfw = spec & 0x7fffffffu;
+                    const uint32_t my_de = lane + 4u + myfw;  // lane index one past my match
+                    const uint32_t below = S & lower;
+                    const uint32_t prev_de = cw_shfl(my_de, below ? (unsigned)(31 - cw_clz(below)) : lane);
+                    const uint32_t my_anchor = below ? base + prev_de : anchor;
+                    const uint32_t nsel = (uint32_t)cw_popc(S);
+                    cw_lz4_q_reserve(q, qh, tailc, nsel, lane);
+                    if (sel) {
+                        const uint32_t idx = (qh + (uint32_t)cw_popc(below)) & (CW_LZ4_QLEN - 1u);
+                        q->rec[idx][0] = my_anchor | (pos << 16);
+                        q->rec[idx][1] = t | (myfw << 16);
+                    }
+                    qh += nsel;
+                    // lanes inside a match were never probed -- except the parser's insert of position e-2
+                    uint32_t cov = 0;
+                    if (sel) {
+                        const uint32_t hi = cw_umin(my_de, 32u);
+                        cov = (hi >= 32u ? 0xffffffffu : (1u << hi) - 1u) & ~((2u << lane) - 1u);
+                        if (my_de < 34u) cov &= ~(1u << (my_de - 2u));
+                    }
+                    ins = vmask & ~cw_reduce_or(cov);
+                    anchor = base + last_de;
+                    sbase = anchor + 1u;
+                    if (last_de >= mfl1 - base) done = true;  // "if (ip > mflimit) break" -> last literals
+                    else if (last_de >= 32u) {
+                        restart = true;
+                        if (last_de >= 34u) pend = anchor - 2u;
+                    } else
+                        done = vmask != 0xffffffffu;  // window exhausted; an invalid lane is the end-of-input rule
+                } else {
+                    ins = vmask;
+                    done = vmask != 0xffffffffu;
+                }
+            } else
             for (;;) {
                 const uint32_t range = ~((1u << i0) - 1u);
                 uint32_t hitm = tm_all & range;
@@ -348,7 +443,7 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
                         const int jl = 31 - cw_clz(cm);
                         hit = valid && ((E >> jl) & 1u);
                         cand = unit ? base + (uint32_t)jl : sbase + (uint32_t)cw_lz4_S(j0 + jl);
-                        sp = 0x8000u;  // candidate inside the window: nothing speculated
+                        sp = 0x80000000u;  // candidate inside the window: nothing speculated
                     }
                     hitm = cw_ballot(hit) & range;
                 }
@@ -361,8 +456,8 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
                 ins |= range & ((2u << f) - 1u);
                 const uint32_t cur = unit ? base + f : cw_shfl(pos, f);
                 sp = cw_shfl(sp, f);
-                uint32_t fwd = sp & 0x7fffu;
-                if (sp & 0x8000u) {
+                uint32_t fwd = sp & 0x7fffffffu;
+                if (sp & 0x80000000u) {
                     // ---- forward extension by the whole warp: 32 lanes x 4 bytes per step, continuing at fwd ----
                     const uint32_t cnd = cw_shfl(cand, f);
                     for (;;) {
@@ -380,6 +475,7 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
                     }
                 }
                 const uint32_t e = cur + 4u + fwd;  // end of the match = next parser position
+                spec_on = fwd < 28u;
                 // everything else about this sequence (backward extension, lengths, bytes) is the emitter's job;
                 // the matching lane itself holds the candidate, so it writes the record
                 cw_lz4_q_push(q, qh, tailc, anchor | (cur << 16), cand | (fwd << 16), lane, f);

@@ -32,7 +32,8 @@ class EngineError(RuntimeError):
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libcomputewar.so")
+    # CW_LIB: alternative build of the same library (A/B measurements of kernel variants); never a CPU fallback
+    return os.environ.get("CW_LIB") or os.path.join(_HERE, "libcomputewar.so")
 
 
 def load_library():

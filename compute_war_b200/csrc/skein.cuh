@@ -28,21 +28,53 @@
 
 CW_HOSTDEV uint64_t cw_rotl64(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }
 
-#define CW_MIX(a, b, r) \
-    a += b;             \
-    b = cw_rotl64(b, r) ^ a;
+// How a MIX (a += b; b = rotl64(b, r) ^ a) is issued on the device (CW_SKEIN_MIXPOLICY):
+//   0  plain C, ptxas decides: 64-bit shifts + ORs folded into the XOR's LOP3 = 5.2 ALU + 1.9 FMA instructions
+//   1  funnel shifts: IADD3, IMAD.X, 2 SHF.L.W, 2 LOP3 = 5 ALU + 1 FMA (19 % fewer instructions; measured
+//      676 vs 650 GB/s for Skein-512 on B200, profiles/r01_ab_skein_mix.txt)
+// A third form that rotates two MIXes out of three on the FMA pipe (x * 2^r as a 32x32->64 IMAD.WIDE) balances
+// the two integer pipes on paper (tools/ubench.cu) but measured slower than (1) in the real kernel (661 GB/s,
+// IMAD.WIDE is half rate) and is not kept.
+#ifndef CW_SKEIN_MIXPOLICY
+#define CW_SKEIN_MIXPOLICY 1
+#endif
 
-// rounds 8d+0..3 and 8d+4..7 of Threefish-512 (word pairings and rotations, skein_block.c:175-216)
-#define CW_TF512_R0123(x)                                                                       \
-    CW_MIX(x[0], x[1], 38) CW_MIX(x[2], x[3], 30) CW_MIX(x[4], x[5], 50) CW_MIX(x[6], x[7], 53) \
-    CW_MIX(x[2], x[1], 48) CW_MIX(x[4], x[7], 20) CW_MIX(x[6], x[5], 43) CW_MIX(x[0], x[3], 31) \
-    CW_MIX(x[4], x[1], 34) CW_MIX(x[6], x[3], 14) CW_MIX(x[0], x[5], 15) CW_MIX(x[2], x[7], 27) \
-    CW_MIX(x[6], x[1], 26) CW_MIX(x[0], x[7], 12) CW_MIX(x[2], x[5], 58) CW_MIX(x[4], x[3], 7)
-#define CW_TF512_R4567(x)                                                                       \
-    CW_MIX(x[0], x[1], 33) CW_MIX(x[2], x[3], 49) CW_MIX(x[4], x[5], 8) CW_MIX(x[6], x[7], 42)  \
-    CW_MIX(x[2], x[1], 39) CW_MIX(x[4], x[7], 27) CW_MIX(x[6], x[5], 41) CW_MIX(x[0], x[3], 14) \
-    CW_MIX(x[4], x[1], 29) CW_MIX(x[6], x[3], 26) CW_MIX(x[0], x[5], 11) CW_MIX(x[2], x[7], 9)  \
-    CW_MIX(x[6], x[1], 33) CW_MIX(x[0], x[7], 51) CW_MIX(x[2], x[5], 39) CW_MIX(x[4], x[3], 35)
+CW_HOSTDEV uint64_t cw_rotxor_funnel(uint64_t b, uint64_t a, int r)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
+    if (r >= 32) {
+        const uint32_t t = lo;
+        lo = hi;
+        hi = t;
+        r -= 32;
+    }
+    const uint32_t nlo = __funnelshift_l(hi, lo, r), nhi = __funnelshift_l(lo, hi, r);
+    return (((uint64_t)nhi << 32) | nlo) ^ a;
+#else
+    return cw_rotl64(b, r) ^ a;
+#endif
+}
+
+#if CW_SKEIN_MIXPOLICY == 0
+#define CW_MIXF(a, b, r) a += b; b = cw_rotl64(b, r) ^ a;
+#else
+#define CW_MIXF(a, b, r) a += b; b = cw_rotxor_funnel(b, a, r);
+#endif
+#define CW_MIXM(a, b, r) CW_MIXF(a, b, r)
+#define CW_MIX(a, b, r) CW_MIXF(a, b, r)
+
+// rounds 8d+0..3 and 8d+4..7 of Threefish-512 (word pairings and rotations, skein_block.c:175-216);
+#define CW_TF512_R0123(x)                                                                           \
+    CW_MIXF(x[0], x[1], 38) CW_MIXM(x[2], x[3], 30) CW_MIXM(x[4], x[5], 50) CW_MIXF(x[6], x[7], 53) \
+    CW_MIXM(x[2], x[1], 48) CW_MIXM(x[4], x[7], 20) CW_MIXF(x[6], x[5], 43) CW_MIXM(x[0], x[3], 31) \
+    CW_MIXM(x[4], x[1], 34) CW_MIXF(x[6], x[3], 14) CW_MIXM(x[0], x[5], 15) CW_MIXM(x[2], x[7], 27) \
+    CW_MIXF(x[6], x[1], 26) CW_MIXM(x[0], x[7], 12) CW_MIXM(x[2], x[5], 58) CW_MIXF(x[4], x[3], 7)
+#define CW_TF512_R4567(x)                                                                           \
+    CW_MIXM(x[0], x[1], 33) CW_MIXM(x[2], x[3], 49) CW_MIXF(x[4], x[5], 8) CW_MIXM(x[6], x[7], 42)  \
+    CW_MIXM(x[2], x[1], 39) CW_MIXF(x[4], x[7], 27) CW_MIXM(x[6], x[5], 41) CW_MIXM(x[0], x[3], 14) \
+    CW_MIXF(x[4], x[1], 29) CW_MIXM(x[6], x[3], 26) CW_MIXM(x[0], x[5], 11) CW_MIXF(x[2], x[7], 9)  \
+    CW_MIXM(x[6], x[1], 33) CW_MIXM(x[0], x[7], 51) CW_MIXF(x[2], x[5], 39) CW_MIXM(x[4], x[3], 35)
 
 // key injection number s (1..18) given ks index base u (= s mod 9 pattern) -- InjectKey, skein_block.c:29-35
 #define CW_TF512_INJECT(x, ks, ts, u, sval)         \
@@ -58,7 +90,7 @@ CW_HOSTDEV uint64_t cw_rotl64(uint64_t x, int n) { return (x << n) | (x >> (64 -
 // One UBI block: X <- Threefish512(key = X, tweak = (T0, T1), plaintext = w) ^ w.
 // UNROLL72 = true: 72 rounds straight-line; false: 3 trips of 24 rounds.
 template <bool UNROLL72>
-CW_HOSTDEV void cw_tf512_block(uint64_t (&X)[8], const uint64_t (&w)[8], uint64_t T0, uint64_t T1)
+CW_HOSTDEV void cw_tf512_block(uint64_t (&X)[8], const uint64_t (&w)[8], uint64_t T0, uint64_t T1, const uint32_t (&pw)[32])
 {
     uint64_t ks[9], ts[3], x[8];
     ks[8] = CW_SKEIN_PARITY;
@@ -115,19 +147,19 @@ CW_HOSTDEV void cw_tf512_block(uint64_t (&X)[8], const uint64_t (&w)[8], uint64_
 }
 
 // Threefish-256 rounds (skein_block.c:76-104)
-#define CW_TF256_R0123(x)                                                                        \
-    CW_MIX(x[0], x[1], 5) CW_MIX(x[2], x[3], 56) CW_MIX(x[0], x[3], 36) CW_MIX(x[2], x[1], 28)   \
-    CW_MIX(x[0], x[1], 13) CW_MIX(x[2], x[3], 46) CW_MIX(x[0], x[3], 58) CW_MIX(x[2], x[1], 44)
-#define CW_TF256_R4567(x)                                                                        \
-    CW_MIX(x[0], x[1], 26) CW_MIX(x[2], x[3], 20) CW_MIX(x[0], x[3], 53) CW_MIX(x[2], x[1], 35)  \
-    CW_MIX(x[0], x[1], 11) CW_MIX(x[2], x[3], 42) CW_MIX(x[0], x[3], 59) CW_MIX(x[2], x[1], 50)
+#define CW_TF256_R0123(x)                                                                            \
+    CW_MIXF(x[0], x[1], 5) CW_MIXM(x[2], x[3], 56) CW_MIXM(x[0], x[3], 36) CW_MIXF(x[2], x[1], 28)   \
+    CW_MIXM(x[0], x[1], 13) CW_MIXM(x[2], x[3], 46) CW_MIXF(x[0], x[3], 58) CW_MIXM(x[2], x[1], 44)
+#define CW_TF256_R4567(x)                                                                            \
+    CW_MIXM(x[0], x[1], 26) CW_MIXF(x[2], x[3], 20) CW_MIXM(x[0], x[3], 53) CW_MIXM(x[2], x[1], 35)  \
+    CW_MIXF(x[0], x[1], 11) CW_MIXM(x[2], x[3], 42) CW_MIXM(x[0], x[3], 59) CW_MIXF(x[2], x[1], 50)
 #define CW_TF256_INJECT(x, ks, ts, s)              \
     x[0] += ks[((s) + 0) % 5];                     \
     x[1] += ks[((s) + 1) % 5] + ts[(s) % 3];       \
     x[2] += ks[((s) + 2) % 5] + ts[((s) + 1) % 3]; \
     x[3] += ks[((s) + 3) % 5] + (uint64_t)(s);
 
-CW_HOSTDEV void cw_tf256_block(uint64_t (&X)[4], const uint64_t (&w)[4], uint64_t T0, uint64_t T1)
+CW_HOSTDEV void cw_tf256_block(uint64_t (&X)[4], const uint64_t (&w)[4], uint64_t T0, uint64_t T1, const uint32_t (&pw)[32])
 {
     uint64_t ks[5], ts[3], x[4];
     ks[4] = CW_SKEIN_PARITY;
@@ -160,6 +192,8 @@ template <int WORDS>
 CW_HOSTDEV void cw_skein_iv(uint64_t (&X)[WORDS], unsigned hash_bits)
 {
     uint64_t w[WORDS];
+    uint32_t pw[32];
+    for (int i = 0; i < 32; i++) pw[i] = 1u << i;
 #pragma unroll
     for (int i = 0; i < WORDS; i++) {
         X[i] = 0;
@@ -168,8 +202,8 @@ CW_HOSTDEV void cw_skein_iv(uint64_t (&X)[WORDS], unsigned hash_bits)
     w[0] = CW_SKEIN_SCHEMA;
     w[1] = hash_bits;
     const uint64_t T1 = CW_SKEIN_T1_FIRST | CW_SKEIN_T1_FINAL | CW_SKEIN_T1_CFG;
-    if constexpr (WORDS == 8) cw_tf512_block<true>(X, w, 32, T1);
-    else cw_tf256_block(X, w, 32, T1);
+    if constexpr (WORDS == 8) cw_tf512_block<true>(X, w, 32, T1, pw);
+    else cw_tf256_block(X, w, 32, T1, pw);
 }
 
 // message word loaders: p is 8-byte aligned on the fast path
@@ -208,7 +242,8 @@ CW_HOSTDEV void cw_skein_load(uint64_t (&w)[WORDS], const uint8_t *p, unsigned a
 // Hash one chunk of `len` bytes.  IV = cw_skein_iv(...) computed once on the host.  out receives
 // OUT_BYTES (<= 8*WORDS) digest bytes, little-endian words (Skein_Put64_LSB_First, skein_port.h:57).
 template <int WORDS, int OUT_BYTES, bool ALIGNED, bool UNROLL72>
-CW_HOSTDEV void cw_skein_chunk(const uint64_t (&IV)[WORDS], const uint8_t *p, uint32_t len, uint64_t (&X)[WORDS])
+CW_HOSTDEV void cw_skein_chunk(const uint64_t (&IV)[WORDS], const uint32_t (&pw)[32], const uint8_t *p, uint32_t len,
+                               uint64_t (&X)[WORDS])
 {
     constexpr uint32_t B = WORDS * 8;
     uint64_t w[WORDS];
@@ -220,17 +255,17 @@ CW_HOSTDEV void cw_skein_chunk(const uint64_t (&IV)[WORDS], const uint8_t *p, ui
     while (len - off > B) {
         cw_skein_load<WORDS, ALIGNED>(w, p + off, B);
         off += B;
-        if constexpr (WORDS == 8) cw_tf512_block<UNROLL72>(X, w, off, T1);
-        else cw_tf256_block(X, w, off, T1);
+        if constexpr (WORDS == 8) cw_tf512_block<UNROLL72>(X, w, off, T1, pw);
+        else cw_tf256_block(X, w, off, T1, pw);
         T1 = CW_SKEIN_T1_MSG;
     }
     // final (zero padded) block, T0 = total length (skein.c:383-387)
     cw_skein_load<WORDS, ALIGNED>(w, p + off, len - off);
-    if constexpr (WORDS == 8) cw_tf512_block<UNROLL72>(X, w, len, T1 | CW_SKEIN_T1_FINAL);
-    else cw_tf256_block(X, w, len, T1 | CW_SKEIN_T1_FINAL);
+    if constexpr (WORDS == 8) cw_tf512_block<UNROLL72>(X, w, len, T1 | CW_SKEIN_T1_FINAL, pw);
+    else cw_tf256_block(X, w, len, T1 | CW_SKEIN_T1_FINAL, pw);
     // output block: counter 0 under the final chaining value (skein.c:393-399)
 #pragma unroll
     for (int i = 0; i < WORDS; i++) w[i] = 0;
-    if constexpr (WORDS == 8) cw_tf512_block<UNROLL72>(X, w, 8, CW_SKEIN_T1_FIRST | CW_SKEIN_T1_FINAL | CW_SKEIN_T1_OUT);
-    else cw_tf256_block(X, w, 8, CW_SKEIN_T1_FIRST | CW_SKEIN_T1_FINAL | CW_SKEIN_T1_OUT);
+    if constexpr (WORDS == 8) cw_tf512_block<UNROLL72>(X, w, 8, CW_SKEIN_T1_FIRST | CW_SKEIN_T1_FINAL | CW_SKEIN_T1_OUT, pw);
+    else cw_tf256_block(X, w, 8, CW_SKEIN_T1_FIRST | CW_SKEIN_T1_FINAL | CW_SKEIN_T1_OUT, pw);
 }

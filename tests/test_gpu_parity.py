@@ -91,6 +91,15 @@ def test_hash_ragged_sizes_vs_oracle(eng, chunk):
         assert (eng.do_hashing(alg, d, chunk) == O.hash_chunks(alg, d, chunk)).all(), (alg, chunk)
 
 
+def test_hash_every_length_up_to_200(eng):
+    """every final-block length (a build that mis-hashed 43..51-byte tails was caught only by this sweep)"""
+    rng = np.random.default_rng(99)
+    for n in range(1, 201):
+        d = rng.integers(0, 256, 3 * n, dtype=np.uint8)
+        for alg in O.HASH_NAMES:
+            assert (eng.do_hashing(alg, d, n) == O.hash_chunks(alg, d, n)).all(), (alg, n)
+
+
 def test_hash_unaligned_buffers(eng):
     rng = np.random.default_rng(5)
     raw = rng.integers(0, 256, 64 * 4096 + 64, dtype=np.uint8)

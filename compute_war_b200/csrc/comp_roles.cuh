@@ -8,13 +8,39 @@
 
 __host__ __device__ constexpr uint32_t cw_lz4_chunk_pad(uint32_t chunk) { return (chunk + CW_LZ4_PAD + 15u) & ~15u; }
 
-// LZ4 parser role.  s: this warp's slot [chunk | pad | table]; q: this warp's queue (zeroed by the caller
-// before the CTA-wide barrier).
-template <int HASHLOG, bool ALIGNED>
+// LZ4 parser role.  s: this warp's slot [chunk | pad | table] (DIRECT: [table] only, the chunk is read where it
+// lies in global memory); q: this warp's queue (zeroed by the caller before the CTA-wide barrier).
+template <int HASHLOG, bool ALIGNED, bool DIRECT>
 __device__ __forceinline__ void cw_lz4_parser_role(uint8_t *s, CwLz4Queue *q, uint64_t *bar, const uint8_t *__restrict__ src,
                                                    uint32_t chunk, uint64_t n_chunks, unsigned long long *work)
 {
     const unsigned lane = threadIdx.x & 31u;
+    if (DIRECT) {
+        uint16_t *table = reinterpret_cast<uint16_t *>(s);
+        uint32_t qh = 0;
+        for (;;) {
+            unsigned long long g = 0;
+            if (lane == 0) g = atomicAdd(work, 1ull);
+            g = __shfl_sync(0xffffffffu, g, 0);
+            if (g >= n_chunks) break;
+            cw_lz4_q_drain(q, qh, lane);  // one chunk index per queue at a time
+            uint4 *t4 = reinterpret_cast<uint4 *>(table);
+#pragma unroll 8
+            for (uint32_t i = lane; i < (2u << HASHLOG) / 16u; i += 32u) t4[i] = make_uint4(0, 0, 0, 0);
+            if (lane == 0) {
+                q->chunk_lo = (uint32_t)g;
+                q->chunk_hi = (uint32_t)(g >> 32);
+            }
+            __syncwarp();
+            cw_lz4_parse_warp<HASHLOG, true>(src + g * chunk, chunk, table, q, qh);
+        }
+        cw_lz4_q_drain(q, qh, lane);
+        if (lane == 0) {
+            cw_fence_cta();
+            cw_st_vol(&q->done, 1u);
+        }
+        return;
+    }
     const uint32_t chunk_pad = cw_lz4_chunk_pad(chunk);
     uint16_t *table = reinterpret_cast<uint16_t *>(s + chunk_pad);
     if (lane == 0) cw_mbar_init(bar, 1);
@@ -45,7 +71,7 @@ __device__ __forceinline__ void cw_lz4_parser_role(uint8_t *s, CwLz4Queue *q, ui
             for (uint32_t i = lane; i < chunk; i += 32u) s[i] = gp[i];
         }
         __syncwarp();
-        cw_lz4_parse_warp<HASHLOG>(s, chunk, table, q, qh);
+        cw_lz4_parse_warp<HASHLOG, false>(s, chunk, table, q, qh);
     }
     cw_lz4_q_drain(q, qh, lane);
     if (lane == 0) {
@@ -54,10 +80,13 @@ __device__ __forceinline__ void cw_lz4_parser_role(uint8_t *s, CwLz4Queue *q, ui
     }
 }
 
-// LZ4 emitter role: serves the queues e, e + emitters, e + 2*emitters, ... until all their parsers are done
+// LZ4 emitter role: serves the queues e, e + emitters, e + 2*emitters, ... until all their parsers are done.
+// DIRECT: literals come from the input buffer `src` itself instead of the parsers' shared-memory slots.
+template <bool DIRECT>
 __device__ __forceinline__ void cw_lz4_emitter_role(unsigned e, unsigned emitters, unsigned parsers, uint8_t *smem,
-                                                    uint32_t slot_bytes, CwLz4Queue *queues, uint32_t chunk,
-                                                    uint8_t *__restrict__ dst, uint64_t stride, uint32_t *__restrict__ lens)
+                                                    uint32_t slot_bytes, CwLz4Queue *queues, const uint8_t *__restrict__ src,
+                                                    uint32_t chunk, uint8_t *__restrict__ dst, uint64_t stride,
+                                                    uint32_t *__restrict__ lens)
 {
     const unsigned lane = threadIdx.x & 31u;
     for (;;) {
@@ -68,7 +97,7 @@ __device__ __forceinline__ void cw_lz4_emitter_role(unsigned e, unsigned emitter
             uint32_t d = 0;
             if (lane == 0) d = cw_ld_vol(&q->done);  // read BEFORE the head: done is set after the last publish
             d = __shfl_sync(0xffffffffu, d, 0);
-            const uint32_t cnt = cw_lz4_emit_batch(q, smem + (size_t)p * slot_bytes, chunk, dst, stride, lens);
+            const uint32_t cnt = cw_lz4_emit_batch<DIRECT>(q, DIRECT ? src : smem + (size_t)p * slot_bytes, chunk, dst, stride, lens);
             did += cnt;
             if (!(d && cnt == 0u)) all_done = false;
         }

@@ -30,6 +30,9 @@ CW_DEV int cw_ffs(uint32_t v) { return __ffs(v); }       // 1-based, 0 if none
 CW_DEV int cw_clz(uint32_t v) { return __clz(v); }
 CW_DEV int cw_popc(uint32_t v) { return __popc(v); }
 CW_DEV uint32_t cw_funnel_r(uint32_t lo, uint32_t hi, unsigned sh) { return __funnelshift_r(lo, hi, sh); }
+// read-only global loads
+CW_DEV uint32_t cw_ldg32(const uint32_t *p) { return __ldg(p); }
+CW_DEV uint32_t cw_ldg8(const uint8_t *p) { return __ldg(p); }
 // inter-warp communication through shared memory (parser -> emitter queues)
 CW_DEV uint32_t cw_ld_vol(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
 CW_DEV void cw_st_vol(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }

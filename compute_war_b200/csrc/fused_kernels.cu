@@ -81,12 +81,12 @@ __global__ void __launch_bounds__(CW_FUSED_MAX_THREADS, 1)
         if (warp < parsers && lane < 8u) reinterpret_cast<uint32_t *>(&queues[warp])[lane] = 0u;
         __syncthreads();
         if (warp < parsers) {
-            cw_lz4_parser_role<(CALG == CW_C_LZ4 ? 13 : 12), ALIGNED>(smem + (size_t)warp * slot_bytes, &queues[warp], &bars[warp],
-                                                                      src, chunk, n_chunks, &work[0]);
+            cw_lz4_parser_role<(CALG == CW_C_LZ4 ? 13 : 12), ALIGNED, false>(smem + (size_t)warp * slot_bytes, &queues[warp],
+                                                                             &bars[warp], src, chunk, n_chunks, &work[0]);
             return;
         }
         if (warp < parsers + emitters) {
-            cw_lz4_emitter_role(warp - parsers, emitters, parsers, smem, slot_bytes, queues, chunk, dst, stride, lens);
+            cw_lz4_emitter_role<false>(warp - parsers, emitters, parsers, smem, slot_bytes, queues, src, chunk, dst, stride, lens);
             return;
         }
     } else if (warp < parsers) {
@@ -185,6 +185,13 @@ cudaError_t cw_launch_fused(const CwDeviceInfo &dev, int halg, int calg, bool fa
                             uint32_t *d_lens, unsigned long long *work, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
+    if (calg == CW_C_LZ4 && chunk > 16384u) {
+        // big chunks: the stand-alone LZ4 kernel reads the chunk in place (DIRECT) and keeps 13 chunks per SM in
+        // flight, the fused kernel would stage them and keep 2; run it and the hash kernel back to back instead
+        cudaError_t e = cw_launch_lz4(dev, fast, d_src, chunk, n, d_dst, stride, d_lens, &work[0], st);
+        if (e != cudaSuccess) return e;
+        return cw_launch_hash(halg, iv, d_src, chunk, n, d_digests, st);
+    }
     if (calg == CW_C_LZ4 && fast) calg = CW_C_LZ4_FAST;  // fast mode of LZF is the compat kernel
     const bool aligned = (chunk % 16u == 0) && ((reinterpret_cast<uintptr_t>(d_src) & 15u) == 0) &&
                          ((reinterpret_cast<uintptr_t>(d_digests) & 15u) == 0);

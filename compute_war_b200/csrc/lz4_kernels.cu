@@ -17,6 +17,7 @@
 #define CW_LZ4_MAX_PARSERS 16
 #define CW_LZ4_MAX_EMITTERS 4
 #define CW_LZ4_EMITTERS_DEFAULT 3
+#define CW_LZ4_DIRECT_ABOVE 16384u  // chunks larger than this are read from global memory instead of being staged
 
 static int lz4_emitters()
 {
@@ -30,7 +31,9 @@ static int lz4_emitters()
     return v;
 }
 
-template <int HASHLOG, bool ALIGNED>
+// DIRECT (chunks > CW_LZ4_DIRECT_ABOVE bytes, e.g. the 64 KB blocks of BASELINE configs[2]): a slot holds only the
+// table; parsers and emitters read the chunk where it lies (L2), which keeps 13 chunks per SM in flight instead of 2.
+template <int HASHLOG, bool ALIGNED, bool DIRECT>
 __global__ void __launch_bounds__((CW_LZ4_MAX_PARSERS + CW_LZ4_MAX_EMITTERS) * 32, 1)
     cw_lz4_kernel(const uint8_t *__restrict__ src, uint32_t chunk, uint64_t n_chunks, uint8_t *__restrict__ dst,
                   uint64_t stride, uint32_t *__restrict__ lens, unsigned long long *work, uint32_t slot_bytes,
@@ -43,10 +46,10 @@ __global__ void __launch_bounds__((CW_LZ4_MAX_PARSERS + CW_LZ4_MAX_EMITTERS) * 3
     if (warp < parsers && lane < 8u) reinterpret_cast<uint32_t *>(&queues[warp])[lane] = 0u;  // head, tail, chunk, op, done
     __syncthreads();
     if (warp < parsers)
-        cw_lz4_parser_role<HASHLOG, ALIGNED>(smem + (size_t)warp * slot_bytes, &queues[warp], &bars[warp], src, chunk, n_chunks,
-                                             work);
+        cw_lz4_parser_role<HASHLOG, ALIGNED, DIRECT>(smem + (size_t)warp * slot_bytes, &queues[warp], &bars[warp], src, chunk,
+                                                     n_chunks, work);
     else
-        cw_lz4_emitter_role(warp - parsers, emitters, parsers, smem, slot_bytes, queues, chunk, dst, stride, lens);
+        cw_lz4_emitter_role<DIRECT>(warp - parsers, emitters, parsers, smem, slot_bytes, queues, src, chunk, dst, stride, lens);
 }
 
 static int g_lz4_max_smem = 0;
@@ -54,20 +57,27 @@ static int g_lz4_max_smem = 0;
 cudaError_t cw_lz4_configure(const CwDeviceInfo &dev)
 {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, cw_lz4_kernel<13, true>);
+    cudaError_t e = cudaFuncGetAttributes(&fa, cw_lz4_kernel<13, true, false>);
     if (e != cudaSuccess) return e;
     g_lz4_max_smem = (int)dev.smem_optin - (int)fa.sharedSizeBytes;  // opt-in limit covers static + dynamic
     const int m = g_lz4_max_smem;
-    if ((e = cudaFuncSetAttribute(cw_lz4_kernel<13, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, m)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(cw_lz4_kernel<13, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(cw_lz4_kernel<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, m)) != cudaSuccess) return e;
-    return cudaFuncSetAttribute(cw_lz4_kernel<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m);
+#define CW_CFG(HL, AL, DI) \
+    if ((e = cudaFuncSetAttribute(cw_lz4_kernel<HL, AL, DI>, cudaFuncAttributeMaxDynamicSharedMemorySize, m)) != cudaSuccess) return e;
+    CW_CFG(13, true, false) CW_CFG(13, false, false) CW_CFG(12, true, false) CW_CFG(12, false, false)
+    CW_CFG(13, true, true) CW_CFG(12, true, true)
+#undef CW_CFG
+    return cudaSuccess;
 }
 
 cudaError_t cw_launch_lz4(const CwDeviceInfo &dev, bool fast, const uint8_t *d_src, uint32_t chunk, uint64_t n, uint8_t *d_dst,
                           uint64_t stride, uint32_t *d_lens, unsigned long long *work, cudaStream_t st)
 {
-    const uint32_t slot = cw_lz4_chunk_pad(chunk) + (2u << (fast ? 12 : 13));
+    const bool aligned = ((chunk & 15u) == 0) && ((reinterpret_cast<uintptr_t>(d_src) & 15u) == 0);
+    const bool direct = aligned && chunk > CW_LZ4_DIRECT_ABOVE;
+    // the 4096-entry table of fast mode stays within 1 % of the reference's ratio only up to 16 KB chunks
+    // (measured: +0.8 % at 16 KB, +1.4 % at 32 KB, +2.7 % at 64 KB); bigger chunks keep the reference's table
+    if (chunk > CW_LZ4_DIRECT_ABOVE) fast = false;
+    const uint32_t slot = (direct ? 0u : cw_lz4_chunk_pad(chunk)) + (2u << (fast ? 12 : 13));
     int parsers = g_lz4_max_smem / (int)(slot + sizeof(CwLz4Queue));
     if (parsers < 1) return cudaErrorInvalidValue;
     if (parsers > CW_LZ4_MAX_PARSERS) parsers = CW_LZ4_MAX_PARSERS;
@@ -75,17 +85,19 @@ cudaError_t cw_launch_lz4(const CwDeviceInfo &dev, bool fast, const uint8_t *d_s
     if (emitters > parsers) emitters = parsers;
     uint64_t ctas = (n + (uint64_t)parsers - 1) / (uint64_t)parsers;
     if (ctas > (uint64_t)dev.sm_count) ctas = (uint64_t)dev.sm_count;
-    const bool aligned = ((chunk & 15u) == 0) && ((reinterpret_cast<uintptr_t>(d_src) & 15u) == 0);
     const dim3 grid((unsigned)ctas), block((parsers + emitters) * 32);
     const size_t dyn = (size_t)parsers * (slot + sizeof(CwLz4Queue));
-#define CW_GO(HL, AL) \
-    cw_lz4_kernel<HL, AL><<<grid, block, dyn, st>>>(d_src, chunk, n, d_dst, stride, d_lens, work, slot, (uint32_t)parsers, (uint32_t)emitters)
-    if (fast) {
-        if (aligned) CW_GO(12, true);
-        else CW_GO(12, false);
+#define CW_GO(HL, AL, DI) \
+    cw_lz4_kernel<HL, AL, DI><<<grid, block, dyn, st>>>(d_src, chunk, n, d_dst, stride, d_lens, work, slot, (uint32_t)parsers, (uint32_t)emitters)
+    if (direct) {
+        if (fast) CW_GO(12, true, true);
+        else CW_GO(13, true, true);
+    } else if (fast) {
+        if (aligned) CW_GO(12, true, false);
+        else CW_GO(12, false, false);
     } else {
-        if (aligned) CW_GO(13, true);
-        else CW_GO(13, false);
+        if (aligned) CW_GO(13, true, false);
+        else CW_GO(13, false, false);
     }
 #undef CW_GO
     return cudaGetLastError();

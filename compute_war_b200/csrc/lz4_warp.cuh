@@ -54,16 +54,35 @@
                                // -4..-13 % on the mixed stream (profiles/r01_ab_static_spec.txt) -> off
 #endif
 #define CW_LZ4_LIT_SELF 16u   // literal runs up to this long are copied by the recording lane itself
-#define CW_LZ4_TAG 0x8000u    // slot tag used for twin detection (chunks <= 32768 bytes: positions < 0x8000)
+#define CW_LZ4_TAG 0xffe0u    // slot tag | lane, used for twin detection.  Tags never outlive a window (phase C rewrites
+                              // every tagged slot) and are only compared with tags, so they may overlap position values
 
 CW_DEV uint32_t cw_umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
-// unaligned little-endian 32-bit read from the staged chunk (base 4-byte aligned)
+// unaligned little-endian 32-bit read from the staged chunk (base 4-byte aligned, CW_LZ4_PAD readable bytes behind it)
 CW_DEV uint32_t cw_lz4_read32(const uint8_t *s, uint32_t pos)
 {
     const uint32_t *w = reinterpret_cast<const uint32_t *>(s);
     const uint32_t i = pos >> 2;
     return cw_funnel_r(w[i], w[i + 1], (pos & 3u) * 8u);
+}
+// Source access of the compressor.  DIRECT = false: the chunk sits in shared memory with padding behind it.
+// DIRECT = true: the chunk is read where it lies in global memory (chunks too big to keep several of them in
+// shared memory); words at or beyond nw = n/4 are not touched and read as 0 -- every use of such bytes is masked
+// by the match limit anyway.
+template <bool DIRECT>
+CW_DEV uint32_t cw_lz4_src32(const uint8_t *s, uint32_t pos, uint32_t nw)
+{
+    if (!DIRECT) return cw_lz4_read32(s, pos);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(s);
+    const uint32_t i = pos >> 2;
+    const uint32_t lo = i < nw ? cw_ldg32(w + i) : 0u, hi = i + 1u < nw ? cw_ldg32(w + i + 1u) : 0u;
+    return cw_funnel_r(lo, hi, (pos & 3u) * 8u);
+}
+template <bool DIRECT>
+CW_DEV uint32_t cw_lz4_src8(const uint8_t *s, uint32_t pos)
+{
+    return DIRECT ? cw_ldg8(s + pos) : s[pos];
 }
 template <int HASHLOG>
 CW_DEV uint32_t cw_lz4_hash(uint32_t v)
@@ -94,19 +113,21 @@ CW_DEV uint32_t cw_lz4_put_ext1(uint8_t *out, uint32_t op, uint32_t r)
 CW_DEV uint32_t cw_lz4_ext_bytes(uint32_t len) { return len >= 15u ? (len - 15u) / 255u + 1u : 0u; }
 
 // whole-warp copy of len literal bytes s[src..] -> out[dst..]; 32-bit stores on the aligned body
-CW_DEV void cw_lz4_copy_warp(uint8_t *out, uint32_t dst, const uint8_t *s, uint32_t src, uint32_t len, unsigned lane)
+template <bool DIRECT>
+CW_DEV void cw_lz4_copy_warp(uint8_t *out, uint32_t dst, const uint8_t *s, uint32_t src, uint32_t len, uint32_t nw,
+                             unsigned lane)
 {
     if (len < 64u) {
-        for (uint32_t x = lane; x < len; x += 32u) out[dst + x] = s[src + x];
+        for (uint32_t x = lane; x < len; x += 32u) out[dst + x] = cw_lz4_src8<DIRECT>(s, src + x);
         return;
     }
     const uint32_t head = (4u - (uint32_t)(reinterpret_cast<uintptr_t>(out + dst) & 3u)) & 3u;
-    if (lane < head) out[dst + lane] = s[src + lane];
+    if (lane < head) out[dst + lane] = cw_lz4_src8<DIRECT>(s, src + lane);
     const uint32_t words = (len - head) >> 2;
     uint32_t *o32 = reinterpret_cast<uint32_t *>(out + dst + head);
-    for (uint32_t w = lane; w < words; w += 32u) o32[w] = cw_lz4_read32(s, src + head + 4u * w);
+    for (uint32_t w = lane; w < words; w += 32u) o32[w] = cw_lz4_src32<DIRECT>(s, src + head + 4u * w, nw);
     const uint32_t done = head + 4u * words;
-    if (lane < len - done) out[dst + done + lane] = s[src + done + lane];
+    if (lane < len - done) out[dst + done + lane] = cw_lz4_src8<DIRECT>(s, src + done + lane);
 }
 
 #define CW_LZ4_QLEN 64u        // records per parser ring (power of two)
@@ -188,9 +209,11 @@ CW_DEV void cw_lz4_q_drain(CwLz4Queue *q, uint32_t qh, unsigned lane)
 // EMITTER: pop up to 32 records of queue q (one lane each) and write their sequences.  s / n: the parser's
 // chunk slot and chunk size; block of chunk g goes to dst_base + g * stride, its length to lens[g].
 // Returns the number of records consumed (same value in every lane).
+template <bool DIRECT>
 CW_DEV uint32_t cw_lz4_emit_batch(CwLz4Queue *q, const uint8_t *s, uint32_t n, uint8_t *dst_base, uint64_t stride,
                                   uint32_t *lens)
 {
+    const uint32_t nw = n >> 2;
     const unsigned lane = cw_lane();
     uint32_t hd = 0, tl = 0;
     if (lane == 0) {
@@ -205,6 +228,7 @@ CW_DEV uint32_t cw_lz4_emit_batch(CwLz4Queue *q, const uint8_t *s, uint32_t n, u
     const uint32_t m = cw_umin(avail, 32u);
     const uint64_t g = (uint64_t)q->chunk_lo | ((uint64_t)q->chunk_hi << 32);
     uint8_t *out = dst_base + g * stride;
+    if (DIRECT) s += g * (uint64_t)n;  // DIRECT: s is the base of the whole input buffer
     const uint32_t op0 = q->op;
     const bool mine = lane < m;
     uint32_t anchor = 0, cur = 0, cnd = 0, fwd = 0;
@@ -220,7 +244,7 @@ CW_DEV uint32_t cw_lz4_emit_batch(CwLz4Queue *q, const uint8_t *s, uint32_t n, u
     uint32_t back = 0;
     if (mine && !is_end) {
         const uint32_t maxb = cw_umin(cur - anchor, cnd);
-        while (back < maxb && s[cur - 1u - back] == s[cnd - 1u - back]) back++;
+        while (back < maxb && cw_lz4_src8<DIRECT>(s, cur - 1u - back) == cw_lz4_src8<DIRECT>(s, cnd - 1u - back)) back++;
     }
     const uint32_t lit = mine ? (is_end ? n - anchor : cur - back - anchor) : 0u;
     const uint32_t mcode = back + fwd;  // match length - 4
@@ -237,7 +261,7 @@ CW_DEV uint32_t cw_lz4_emit_batch(CwLz4Queue *q, const uint8_t *s, uint32_t n, u
         out[p++] = (uint8_t)((cw_umin(lit, 15u) << 4) | (is_end ? 0u : cw_umin(mcode, 15u)));
         if (lit >= 15u) p = cw_lz4_put_ext1(out, p, lit - 15u);
         if (lit <= CW_LZ4_LIT_SELF)
-            for (uint32_t x = 0; x < lit; x++) out[p + x] = s[anchor + x];
+            for (uint32_t x = 0; x < lit; x++) out[p + x] = cw_lz4_src8<DIRECT>(s, anchor + x);
         p += lit;
         if (!is_end) {
             const uint32_t off = cur - cnd;
@@ -251,7 +275,7 @@ CW_DEV uint32_t cw_lz4_emit_batch(CwLz4Queue *q, const uint8_t *s, uint32_t n, u
         const unsigned k = (unsigned)cw_ffs(big) - 1u;
         big &= big - 1u;
         const uint32_t l = cw_shfl(lit, k);
-        cw_lz4_copy_warp(out, cw_shfl(p0, k) + 1u + cw_lz4_ext_bytes(l), s, cw_shfl(anchor, k), l, lane);
+        cw_lz4_copy_warp<DIRECT>(out, cw_shfl(p0, k) + 1u + cw_lz4_ext_bytes(l), s, cw_shfl(anchor, k), l, nw, lane);
     }
     const uint32_t endm = cw_ballot(is_end);
     if (lane == 0) {
@@ -272,13 +296,13 @@ CW_DEV uint32_t cw_lz4_emit_batch(CwLz4Queue *q, const uint8_t *s, uint32_t n, u
 // PARSER: parse chunk s[0..n) (n <= 65536) and push its matches, then the end-of-chunk record, to q.
 // table: zeroed u16[1 << HASHLOG] in shared memory.  qh: records pushed so far on this queue (kept by the
 // caller across chunks).  The caller sets q->chunk_lo/hi before and drains the queue before reusing s.
-template <int HASHLOG>
+template <int HASHLOG, bool DIRECT>
 CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwLz4Queue *q, uint32_t &qh)
 {
+    const uint32_t nw = n >> 2;
     const unsigned lane = cw_lane();
     const uint32_t own = 1u << lane;
     const uint32_t lower = own - 1u;
-    const bool tag_ok = n <= 32768u;  // positions fit below CW_LZ4_TAG
     uint32_t anchor = 0, tailc = qh;  // the caller drained the queue: tail == qh
 
     if (n >= 13u) {
@@ -303,25 +327,19 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
                 pos = sbase + (uint32_t)cw_lz4_S(j);
                 valid = pos + cw_lz4_step(j) <= mfl1;
             }
-            const uint32_t v = cw_lz4_read32(s, valid ? pos : 0u);
+            const uint32_t v = cw_lz4_src32<DIRECT>(s, valid ? pos : 0u, nw);
             const uint32_t h = cw_lz4_hash<HASHLOG>(v);
             const uint32_t t = table[h];
             // twin detection: tag the slot, read it back; the lane whose tag survives owns the slot
             uint32_t M = own;
             bool owner = valid;
             uint32_t twins;
-            if (tag_ok) {
-                cw_syncwarp();  // every lane has read its old entry before any lane tags a slot
-                if (valid) table[h] = (uint16_t)(CW_LZ4_TAG | lane);
-                cw_syncwarp();
-                owner = valid && table[h] == (CW_LZ4_TAG | lane);
-                twins = cw_ballot(valid && !owner);
-            } else {
-                M = cw_match_any(valid ? h : 0x10000u + lane);
-                twins = cw_ballot(M != own);
-                owner = valid && !(M & ~((2u << lane) - 1u));  // highest lane of the group
-            }
-            const bool tmatch = valid && cw_lz4_read32(s, t) == v;
+            cw_syncwarp();  // every lane has read its old entry before any lane tags a slot
+            if (valid) table[h] = (uint16_t)(CW_LZ4_TAG | lane);
+            cw_syncwarp();
+            owner = valid && table[h] == (CW_LZ4_TAG | lane);
+            twins = cw_ballot(valid && !owner);
+            const bool tmatch = valid && cw_lz4_src32<DIRECT>(s, t, nw) == v;
             // speculative forward extension against the table candidate, every matching lane for itself:
             // spec = equal bytes after the 4-byte match; bit 15 = "still equal after CW_LZ4_SPEC_STEPS steps"
             const uint32_t tm_all = cw_ballot(tmatch);
@@ -334,7 +352,7 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
                 for (int k = 0; k < CW_LZ4_SPEC_STEPS; k++) {
                     if (open) {
                         const uint32_t pa = pos + 4u + fw;
-                        const uint32_t d = cw_lz4_read32(s, pa) ^ cw_lz4_read32(s, t + 4u + fw);
+                        const uint32_t d = cw_lz4_src32<DIRECT>(s, pa, nw) ^ cw_lz4_src32<DIRECT>(s, t + 4u + fw, nw);
                         uint32_t eq = d ? (uint32_t)(cw_ffs(d) - 1) >> 3 : 4u;
                         eq = cw_umin(eq, pa < matchlimit ? matchlimit - pa : 0u);
                         fw += eq;
@@ -352,7 +370,7 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
             const uint32_t vmask = inv_all ? (1u << (cw_ffs(inv_all) - 1)) - 1u : 0xffffffffu;
             uint32_t E = own, dyn_all = 0;
             if (twins) {
-                if (tag_ok) M = cw_match_any(valid ? h : 0x10000u + lane);
+                M = cw_match_any(valid ? h : 0x10000u + lane);
                 E = cw_match_any(v);
                 dyn_all = cw_ballot(valid && (M & lower) != 0u);  // lanes that may have an in-window candidate
             }
@@ -377,7 +395,7 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
                         const uint32_t cur = base + f, cnd = cw_shfl(t, f);
                         for (;;) {
                             const uint32_t pa = cur + 4u + fwd + 4u * lane, pb = cnd + 4u + fwd + 4u * lane;
-                            const uint32_t d = cw_lz4_read32(s, pa) ^ cw_lz4_read32(s, pb);
+                            const uint32_t d = cw_lz4_src32<DIRECT>(s, pa, nw) ^ cw_lz4_src32<DIRECT>(s, pb, nw);
                             uint32_t eq = d ? (uint32_t)(cw_ffs(d) - 1) >> 3 : 4u;
                             eq = cw_umin(eq, pa < matchlimit ? matchlimit - pa : 0u);
                             const uint32_t stop = cw_ballot(eq < 4u);
@@ -462,7 +480,7 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
                     const uint32_t cnd = cw_shfl(cand, f);
                     for (;;) {
                         const uint32_t pa = cur + 4u + fwd + 4u * lane, pb = cnd + 4u + fwd + 4u * lane;
-                        const uint32_t d = cw_lz4_read32(s, pa) ^ cw_lz4_read32(s, pb);
+                        const uint32_t d = cw_lz4_src32<DIRECT>(s, pa, nw) ^ cw_lz4_src32<DIRECT>(s, pb, nw);
                         uint32_t eq = d ? (uint32_t)(cw_ffs(d) - 1) >> 3 : 4u;  // equal leading bytes
                         eq = cw_umin(eq, pa < matchlimit ? matchlimit - pa : 0u);
                         const uint32_t stop = cw_ballot(eq < 4u);
@@ -500,17 +518,15 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
             // ---------------- phase C: every touched slot gets its final value ----------------
             if (twins) {
                 // slot owners first put the old entry back, then the highest inserted twin of each slot writes
-                if (tag_ok && owner) table[h] = (uint16_t)t;
+                if (owner) table[h] = (uint16_t)t;
                 cw_syncwarp();
                 if (((ins >> lane) & 1u) && !(M & ins & ~((2u << lane) - 1u))) table[h] = (uint16_t)pos;
-            } else if (tag_ok) {
-                if (valid) table[h] = (uint16_t)(((ins >> lane) & 1u) ? pos : t);
             } else {
-                if ((ins >> lane) & 1u) table[h] = (uint16_t)pos;
+                if (valid) table[h] = (uint16_t)(((ins >> lane) & 1u) ? pos : t);
             }
             cw_syncwarp();
             if (pend != CW_LZ4_NONE) {
-                if (lane == 0) table[cw_lz4_hash<HASHLOG>(cw_lz4_read32(s, pend))] = (uint16_t)pend;
+                if (lane == 0) table[cw_lz4_hash<HASHLOG>(cw_lz4_src32<DIRECT>(s, pend, nw))] = (uint16_t)pend;
                 cw_syncwarp();
             }
             if (restart) j0 = -1;                                       // lane 0 = re-test at e

@@ -1,6 +1,7 @@
 // emu_codecs.cpp -- runs the product's warp-cooperative compressors (csrc/lz4_warp.cuh, csrc/lzf_warp.cuh)
 // on the CPU warp emulator.  Test infrastructure only; exports a C entry point per codec for ctypes.
 #define CW_EMULATE 1
+#include <sys/mman.h>
 #include <vector>
 #include "warp_emu.h"
 #include "../../compute_war_b200/csrc/lz4_warp.cuh"
@@ -29,6 +30,7 @@ struct Lz4Job {
     uint8_t *out;
     uint32_t lens[1];
     int hashlog;
+    int direct;
 };
 
 static void lz4_block_body(void *a, int warp)
@@ -37,8 +39,11 @@ static void lz4_block_body(void *a, int warp)
     const unsigned lane = cw_lane();
     if (warp == 0) {
         uint32_t qh = 0;
-        if (j->hashlog == 12) cw_lz4_parse_warp<12>(j->s, j->n, j->table, j->q, qh);
-        else cw_lz4_parse_warp<13>(j->s, j->n, j->table, j->q, qh);
+        if (j->direct) {
+            if (j->hashlog == 12) cw_lz4_parse_warp<12, true>(j->s, j->n, j->table, j->q, qh);
+            else cw_lz4_parse_warp<13, true>(j->s, j->n, j->table, j->q, qh);
+        } else if (j->hashlog == 12) cw_lz4_parse_warp<12, false>(j->s, j->n, j->table, j->q, qh);
+        else cw_lz4_parse_warp<13, false>(j->s, j->n, j->table, j->q, qh);
         cw_lz4_q_drain(j->q, qh, lane);
         if (lane == 0) {
             cw_fence_cta();
@@ -49,7 +54,8 @@ static void lz4_block_body(void *a, int warp)
             uint32_t d = 0;
             if (lane == 0) d = cw_ld_vol(&j->q->done);
             d = cw_shfl(d, 0);
-            const uint32_t cnt = cw_lz4_emit_batch(j->q, j->s, j->n, j->out, 0, j->lens);
+            const uint32_t cnt = j->direct ? cw_lz4_emit_batch<true>(j->q, j->s, j->n, j->out, 0, j->lens)
+                                           : cw_lz4_emit_batch<false>(j->q, j->s, j->n, j->out, 0, j->lens);
             if (d && cnt == 0) break;
             if (!cnt) cw_spin();
         }
@@ -63,8 +69,26 @@ extern "C" uint32_t emu_lz4_compress_hl(const uint8_t *src, uint32_t n, uint8_t 
     std::vector<uint16_t> table(1u << hashlog, 0);
     CwLz4Queue q;
     memset(&q, 0, sizeof q);
-    Lz4Job j{(const uint8_t *)staged.data(), n, table.data(), &q, out, {0}, hashlog};
+    Lz4Job j{(const uint8_t *)staged.data(), n, table.data(), &q, out, {0}, hashlog, 0};
     cwemu::run_block(2, lz4_block_body, &j);
+    return j.lens[0];
+}
+
+// DIRECT mode: the chunk is read in place, nothing readable behind it (n must be a multiple of 4)
+extern "C" uint32_t emu_lz4_compress_direct(const uint8_t *src, uint32_t n, uint8_t *out, int hashlog)
+{
+    // the chunk ends exactly at a PROT_NONE guard page: any read past n faults
+    const size_t page = 4096, span = (n + page - 1) / page * page + page;
+    uint8_t *map = (uint8_t *)mmap(nullptr, span + page, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    mprotect(map + span, page, PROT_NONE);
+    uint8_t *exact = map + span - n;
+    memcpy(exact, src, n);
+    std::vector<uint16_t> table(1u << hashlog, 0);
+    CwLz4Queue q;
+    memset(&q, 0, sizeof q);
+    Lz4Job j{(const uint8_t *)exact, n, table.data(), &q, out, {0}, hashlog, 1};
+    cwemu::run_block(2, lz4_block_body, &j);
+    munmap(map, span + page);
     return j.lens[0];
 }
 extern "C" uint32_t emu_lz4_compress(const uint8_t *src, uint32_t n, uint8_t *out) { return emu_lz4_compress_hl(src, n, out, 13); }

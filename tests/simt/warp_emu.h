@@ -103,6 +103,8 @@ static inline uint32_t cw_funnel_r(uint32_t lo, uint32_t hi, unsigned sh)
     sh &= 31u;
     return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
 }
+static inline uint32_t cw_ldg32(const uint32_t *p) { return *p; }
+static inline uint32_t cw_ldg8(const uint8_t *p) { return *p; }
 // inter-warp communication through shared memory
 static inline uint32_t cw_ld_vol(const uint32_t *p) { return *(const volatile uint32_t *)p; }
 static inline void cw_st_vol(uint32_t *p, uint32_t v)

@@ -186,14 +186,15 @@ def test_fast_mode_roundtrips_and_ratio(eng, golden, alg):
     ref, blob = golden["ref"], golden["blob"]
     for ent in ref["files"]:
         d = blob[ent["offset"]: ent["offset"] + ent["size"]]
-        rec = ref["corpus"][ent["name"]]["8192"]
-        if rec["n"] == 0:
-            continue
-        blocks, lens = eng.do_compression(alg, d, 8192, cw.MODE_FAST)
-        assert O.verify_roundtrip(alg, d, 8192, blocks, lens) == 0
-        mine = sum(int(x) if x else 8192 for x in lens)
-        theirs = sum(int(x) if x else 8192 for x in rec[O.COMP_NAMES[alg] + "_lens"])
-        assert mine <= theirs * 1.01, (ent["name"], mine, theirs)
+        for chunk in (4096, 8192, 65536):
+            rec = ref["corpus"][ent["name"]][str(chunk)]
+            if rec["n"] == 0:
+                continue
+            blocks, lens = eng.do_compression(alg, d, chunk, cw.MODE_FAST)
+            assert O.verify_roundtrip(alg, d, chunk, blocks, lens) == 0
+            mine = sum(int(x) if x else chunk for x in lens)
+            theirs = sum(int(x) if x else chunk for x in rec[O.COMP_NAMES[alg] + "_lens"])
+            assert mine <= theirs * 1.01, (ent["name"], chunk, mine, theirs)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -203,11 +204,11 @@ def test_fast_mode_roundtrips_and_ratio(eng, golden, alg):
 @pytest.mark.parametrize("halg,calg", [(O.HASH_SKEIN512, O.COMP_LZ4), (O.HASH_SKEIN256_128, O.COMP_LZ4),
                                        (O.HASH_SKEIN256_128, O.COMP_LZF), (O.HASH_SHA256, O.COMP_LZ4),
                                        (O.HASH_SKEIN512, O.COMP_LZF), (O.HASH_SHA256, O.COMP_LZF)])
-@pytest.mark.parametrize("chunk", [4096, 8192])
+@pytest.mark.parametrize("chunk", [4096, 8192, 32768])
 def test_process_block_fused(eng, golden, halg, calg, chunk):
     """hc_sklz4 / hc_sklzf / hc_shlz4 ... : the fused pass equals the two separate primitives and the reference"""
     ref, blob = golden["ref"], golden["blob"]
-    d = np.concatenate([blob[: 40 * 8192], O.synth(chunk, 7, 96)])
+    d = np.concatenate([blob[: 40 * 8192], O.synth(chunk, 7, 96 if chunk <= 8192 else 24)])
     dig, blocks, lens = eng.process_block(halg, calg, d, chunk)
     assert (dig == O.hash_chunks(halg, d, chunk)).all()
     _check_blocks(calg, d, chunk, blocks, lens)

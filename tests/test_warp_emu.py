@@ -88,6 +88,34 @@ def test_lz4_warp_algorithm_byte_identical(emu, golden):
         assert r == lens[0] and (out[:r] == blocks[0, :r]).all(), n
 
 
+def test_lz4_direct_mode_and_fast_table(emu, golden):
+    """DIRECT mode (chunk read in place, guard page behind it) is byte-identical; the 4096-entry table of fast mode
+    yields a valid stream within 1 % of the reference's size at 8 KiB"""
+    emu.emu_lz4_compress_direct.restype = C.c_uint32
+    emu.emu_lz4_compress_hl.restype = C.c_uint32
+    rng = np.random.default_rng(4)
+    blob = golden["blob"]
+    cases = [blob[:65536].copy(), blob[100000:100000 + 32768].copy(), O.synth(65536, 2, 1), np.zeros(65536, np.uint8),
+             rng.integers(0, 256, 65536, dtype=np.uint8), blob[4096:4096 + 16].copy(), blob[0:64].copy()]
+    for c in cases:
+        n = len(c)
+        out = np.zeros(n + n // 255 + 64, np.uint8)
+        r = emu.emu_lz4_compress_direct(c.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p), 13)
+        blocks, lens = O.compress_chunks(O.COMP_LZ4, c, n)
+        assert r == lens[0] and (out[:r] == blocks[0, :r]).all(), n
+    tot_fast = tot_ref = 0
+    for ent in golden["ref"]["files"][:6]:
+        d = blob[ent["offset"]: ent["offset"] + ent["size"]]
+        for i in range(min(3, len(d) // 8192)):
+            c = d[i * 8192:(i + 1) * 8192].copy()
+            out = np.zeros(8192 + 64, np.uint8)
+            r = emu.emu_lz4_compress_hl(c.ctypes.data_as(C.c_void_p), 8192, out.ctypes.data_as(C.c_void_p), 12)
+            assert O.verify_roundtrip(O.COMP_LZ4, c, 8192, out[None, :], np.array([r], np.uint32)) == 0
+            tot_fast += r
+            tot_ref += int(O.compress_chunks(O.COMP_LZ4, c, 8192)[1][0])
+    assert tot_fast <= 1.01 * tot_ref
+
+
 def test_lzf_warp_algorithm_byte_identical(emu, golden):
     if not hasattr(emu, "emu_lzf_compress"):
         pytest.skip("LZF warp kernel not built yet")

@@ -5,6 +5,7 @@
 // HashAndCompress.cpp:95-98, doHashing :119-134, doCompression :111,342-355, ProcessBlock :231-261,
 // HashOffload HashOffload.h:15-64 + hashing_offload_entry_point HashAndCompress.cpp:160-183.
 #include <atomic>
+#include <cstdlib>
 #include <condition_variable>
 #include <deque>
 #include <map>
@@ -19,8 +20,8 @@
 
 namespace {
 
-constexpr int kSlots = 3;                     // H2D / kernel / D2H in flight
-constexpr size_t kSliceBytes = 32u << 20;     // input bytes per pipeline slice
+constexpr int kSlots = 4;                     // pipeline slots: H2D / kernel / D2H of different slices in flight
+constexpr size_t kSliceBytesDefault = 64u << 20;  // input bytes per pipeline slice (CW_SLICE_MB overrides); 64 MiB x 4 slots measured best
 constexpr int kWorkRing = 256;
 
 struct Slot {
@@ -214,13 +215,23 @@ int host_pass(cw_ctx *ctx, bool want_hash, bool want_comp, cw_hash_alg halg, cw_
     std::lock_guard<std::mutex> hg(ctx->host_mu);
     CW_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t D = want_hash ? cw_digest_bytes(halg) : 0;
-    size_t per = kSliceBytes / chunk;
+    static const size_t slice_bytes = [] {
+        const char *e = getenv("CW_SLICE_MB");
+        size_t mb = e ? (size_t)atoi(e) : 0;
+        return mb ? mb << 20 : kSliceBytesDefault;
+    }();
+    static const int n_slots = [] {
+        const char *e = getenv("CW_SLOTS");
+        int v = e ? atoi(e) : kSlots;
+        return v < 1 ? 1 : (v > kSlots ? kSlots : v);
+    }();
+    size_t per = slice_bytes / chunk;
     if (per < 1) per = 1;
     int rc = CW_OK;
     size_t k = 0;
     for (size_t lo = 0; lo < n && rc == CW_OK; lo += per, k++) {
         const size_t cnt = (n - lo < per) ? n - lo : per;
-        Slot &s = ctx->slots[k % kSlots];
+        Slot &s = ctx->slots[k % n_slots];
         if (s.busy) {
             CW_CUDA(ctx, cudaEventSynchronize(s.done));
             s.busy = false;

@@ -215,18 +215,18 @@ def test_process_block_fused(eng, golden, halg, calg, chunk):
 
 
 def test_large_batch_spans_pipeline_slices(eng):
-    """> 3 x 32 MiB so that every pipeline slot is reused; checked by sampling + order-independent properties"""
-    chunk, n = 8192, 16384  # 128 MiB
+    """5 slices of 64 MiB through the 4 pipeline slots, so a slot is reused; sampled + order-independent checks"""
+    chunk, n = 8192, 40960  # 320 MiB
     d = O.synth(chunk, 5000, n)
     dig, blocks, lens = eng.process_block(cw.HASH_SKEIN512, cw.COMP_LZ4, d, chunk)
-    idx = np.r_[0:64, 4090:4110, 8180:8200, n - 64:n]
+    idx = np.r_[0:64, 8180:8204, 16370:16400, 32760:32776, n - 64:n]
     sub = np.concatenate([d[i * chunk:(i + 1) * chunk] for i in idx])
     assert (dig[idx] == O.hash_chunks(O.HASH_SKEIN512, sub, chunk)).all()
     ob, ol = O.compress_chunks(O.COMP_LZ4, sub, chunk)
     assert (lens[idx] == ol).all()
     for k, i in enumerate(idx):
         assert (blocks[i, : lens[i]] == ob[k, : ol[k]]).all()
-    assert O.verify_roundtrip(O.COMP_LZ4, d, chunk, blocks, lens) == 0  # every one of the 16384 blocks decodes back
+    assert O.verify_roundtrip(O.COMP_LZ4, d, chunk, blocks, lens) == 0  # every one of the 40960 blocks decodes back
     # a second run is identical (no dependence on scheduling order)
     dig2, blocks2, lens2 = eng.process_block(cw.HASH_SKEIN512, cw.COMP_LZ4, d, chunk)
     assert (dig == dig2).all() and (lens == lens2).all()

@@ -489,6 +489,58 @@ int cw_wait(cw_ctx *ctx, cw_ticket ticket)
     return rc;
 }
 
+int cw_decompress_dev(cw_ctx *ctx, cw_comp_alg alg, const void *d_blocks, size_t stride, const uint32_t *d_lens,
+                      size_t chunk, size_t n, void *d_out, uint32_t *d_out_lens, void *stream)
+{
+    int rc = check_common(ctx, chunk, n, d_blocks);
+    if (rc != CW_OK) return rc;
+    if ((int)alg < 0 || (int)alg > 1 || (n && (!d_lens || !d_out || !d_out_lens))) return CW_ERR_ARG;
+    if (alg == CW_COMP_LZF && stride < chunk) return CW_ERR_ARG;  // raw-stored chunks need chunk bytes per slot
+    if (n == 0) return CW_OK;
+    CW_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    unsigned long long *w = next_work(ctx);
+    CW_CUDA(ctx, cudaMemsetAsync(w, 0, sizeof *w, st));
+    ProfScope ps(ctx, st);
+    CW_CUDA(ctx, cw_launch_decode(ctx->dev, (int)alg, (const uint8_t *)d_blocks, stride, d_lens, (uint32_t)chunk, n,
+                                  (uint8_t *)d_out, d_out_lens, w, st));
+    ctx->launches++;
+    return CW_OK;
+}
+
+int cw_decompress(cw_ctx *ctx, cw_comp_alg alg, const void *blocks, size_t stride, const uint32_t *lens, size_t chunk, size_t n,
+                  void *out, uint32_t *out_lens)
+{
+    int rc = check_common(ctx, chunk, n, blocks);
+    if (rc != CW_OK) return rc;
+    if ((int)alg < 0 || (int)alg > 1 || (n && (!lens || !out || !out_lens))) return CW_ERR_ARG;
+    if (n == 0) return CW_OK;
+    std::lock_guard<std::mutex> hg(ctx->host_mu);
+    CW_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint8_t *d_b = nullptr, *d_o = nullptr;
+    uint32_t *d_l = nullptr, *d_ol = nullptr;
+    cudaError_t e = cudaMalloc(&d_b, n * stride);
+    if (e == cudaSuccess) e = cudaMalloc(&d_o, n * chunk);
+    if (e == cudaSuccess) e = cudaMalloc(&d_l, n * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_ol, n * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_b, blocks, n * stride, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_l, lens, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        rc = cw_decompress_dev(ctx, alg, d_b, stride, d_l, chunk, n, d_o, d_ol, ctx->stream);
+        if (rc == CW_OK) {
+            e = cudaMemcpyAsync(out, d_o, n * chunk, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(out_lens, d_ol, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        }
+    }
+    cudaFree(d_b);
+    cudaFree(d_o);
+    cudaFree(d_l);
+    cudaFree(d_ol);
+    if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? CW_ERR_NOMEM : fail(ctx, e, "cw_decompress");
+    return rc;
+}
+
 int cw_synth_dev(cw_ctx *ctx, void *d_dst, size_t chunk, uint64_t first_chunk, size_t n, uint64_t seed, void *stream)
 {
     if (!ctx || !d_dst || chunk == 0 || (chunk & 7u) || (reinterpret_cast<uintptr_t>(d_dst) & 7u)) return CW_ERR_ARG;

@@ -208,5 +208,6 @@ cudaError_t cw_configure_kernels(const CwDeviceInfo &dev)
     cudaError_t e = cw_lz4_configure(dev);
     if (e == cudaSuccess) e = cw_lzf_configure(dev);
     if (e == cudaSuccess) e = cw_fused_configure(dev);
+    if (e == cudaSuccess) e = cw_decode_configure(dev);
     return e;
 }

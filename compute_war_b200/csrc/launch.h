@@ -38,5 +38,11 @@ cudaError_t cw_launch_fused(const CwDeviceInfo &dev, int halg, int calg, bool fa
                             uint32_t *d_lens, unsigned long long *work, cudaStream_t st);
 cudaError_t cw_fused_configure(const CwDeviceInfo &dev);
 
+// decode_kernels.cu
+cudaError_t cw_launch_decode(const CwDeviceInfo &dev, int alg, const uint8_t *d_blocks, uint64_t stride, const uint32_t *d_lens,
+                             uint32_t chunk, uint64_t n, uint8_t *d_out, uint32_t *d_out_lens, unsigned long long *work,
+                             cudaStream_t st);
+cudaError_t cw_decode_configure(const CwDeviceInfo &dev);
+
 // all per-kernel attribute set-up (opt-in shared memory sizes); called once from cw_init
 cudaError_t cw_configure_kernels(const CwDeviceInfo &dev);

@@ -65,6 +65,8 @@ def load_library():
     L.cw_hash_dev.argtypes = [vp, C.c_int, vp, sz, sz, vp, vp]
     L.cw_compress_dev.argtypes = [vp, C.c_int, C.c_int, vp, sz, sz, vp, sz, vp, vp]
     L.cw_hash_compress_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, sz, sz, vp, vp, sz, vp, vp]
+    L.cw_decompress.argtypes = [vp, C.c_int, vp, sz, vp, sz, sz, vp, vp]
+    L.cw_decompress_dev.argtypes = [vp, C.c_int, vp, sz, vp, sz, sz, vp, vp, vp]
     L.cw_sync.argtypes = [vp, vp]
     L.cw_submit.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, sz, sz, vp, vp, sz, vp, vp, vp, C.POINTER(u64)]
     L.cw_wait.argtypes = [vp, u64]
@@ -190,6 +192,22 @@ class Engine:
     def hash_compress_dev(self, hash_alg, comp_alg, mode, d_src, chunk, n, d_digests, d_dst, stride, d_lens, stream=0):
         self._check(self.L.cw_hash_compress_dev(self.h, hash_alg, comp_alg, mode, d_src, chunk, n, d_digests, d_dst, stride,
                                                 d_lens, stream or None))
+
+    def decompress_dev(self, comp_alg, d_blocks, stride, d_lens, chunk, n, d_out, d_out_lens, stream=0):
+        self._check(self.L.cw_decompress_dev(self.h, comp_alg, d_blocks, stride, d_lens, chunk, n, d_out, d_out_lens,
+                                             stream or None))
+
+    def do_decompression(self, comp_alg: int, blocks: np.ndarray, lens: np.ndarray, chunk: int):
+        """LZ4_decompress_safe / lzf_decompress per block: (out[n*chunk], out_lens[n]); out_lens[i] == 0 marks a bad block"""
+        b = np.ascontiguousarray(blocks, dtype=np.uint8)
+        l = np.ascontiguousarray(lens, dtype=np.uint32)
+        n = len(l)
+        stride = b.shape[1] if b.ndim == 2 else (b.size // max(n, 1))
+        out = np.zeros(n * chunk, np.uint8)
+        out_lens = np.zeros(n, np.uint32)
+        self._check(self.L.cw_decompress(self.h, comp_alg, b.ctypes.data, stride, l.ctypes.data, chunk, n, out.ctypes.data,
+                                         out_lens.ctypes.data))
+        return out, out_lens
 
     def synth_dev(self, d_dst, chunk, first_chunk, n, seed=0xC0FFEE, stream=0):
         self._check(self.L.cw_synth_dev(self.h, d_dst, chunk, first_chunk, n, seed, stream or None))

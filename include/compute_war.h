@@ -105,6 +105,15 @@ int cw_hash_compress_dev(cw_ctx *ctx, cw_hash_alg halg, cw_comp_alg calg, cw_mod
                          uint32_t *d_lens, void *stream);
 int cw_sync(cw_ctx *ctx, void *stream);
 
+/* ---- decompression: LZ4_decompress_safe / lzf_decompress as the reference calls them after each compression
+ * (experiment.cpp:256, :118; decls lz4.h:141-149, lzf.h:98-100), over a strided block array.
+ * out_lens[i] = decoded bytes (chunk_bytes on success), 0 for a malformed block.  An LZF block of length 0 is a chunk
+ * the caller stored raw (lzf.h:59-64): it is copied.  SURVEY.md 8(f) row 2. ---- */
+int cw_decompress(cw_ctx *ctx, cw_comp_alg alg, const void *blocks, size_t stride, const uint32_t *lens, size_t chunk_bytes,
+                  size_t n_chunks, void *out, uint32_t *out_lens);
+int cw_decompress_dev(cw_ctx *ctx, cw_comp_alg alg, const void *d_blocks, size_t stride, const uint32_t *d_lens,
+                      size_t chunk_bytes, size_t n_chunks, void *d_out, uint32_t *d_out_lens, void *stream);
+
 /* ---- asynchronous offload: HashOffload::{Reset,Enqueue,Start,Complete} (HashOffload.h:15-64) and the
  * consumer loop hashing_offload_entry_point (HashAndCompress.cpp:160-183) ----
  * cw_submit = Reset+Enqueue+Start: queues one fused batch (host buffers) and returns at once;

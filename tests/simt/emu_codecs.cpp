@@ -5,6 +5,7 @@
 #include <vector>
 #include "warp_emu.h"
 #include "../../compute_war_b200/csrc/lz4_warp.cuh"
+#include "../../compute_war_b200/csrc/decode_warp.cuh"
 #if __has_include("../../compute_war_b200/csrc/lzf_warp.cuh")
 #include "../../compute_war_b200/csrc/lzf_warp.cuh"
 #define HAVE_LZF 1
@@ -110,3 +111,24 @@ extern "C" uint32_t emu_lzf_compress(const uint8_t *src, uint32_t n, uint8_t *ou
     return j.result;
 }
 #endif
+
+// decoders (csrc/decode_warp.cuh): one warp per block
+struct DecJob {
+    const uint8_t *in;
+    uint32_t len;
+    uint8_t *out;
+    uint32_t cap, result;
+    int alg;
+};
+static void dec_body(void *a)
+{
+    DecJob *j = (DecJob *)a;
+    uint32_t r = j->alg == 0 ? cw_lz4_decode_warp(j->in, j->len, j->out, j->cap) : cw_lzf_decode_warp(j->in, j->len, j->out, j->cap);
+    if (cw_lane() == 0) j->result = r;
+}
+extern "C" uint32_t emu_decode(int alg, const uint8_t *in, uint32_t len, uint8_t *out, uint32_t cap)
+{
+    DecJob j{in, len, out, cap, 0, alg};
+    cwemu::run_warp(dec_body, &j);
+    return j.result;
+}

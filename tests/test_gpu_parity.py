@@ -283,6 +283,70 @@ def test_device_pointer_api_and_synth(eng):
     assert (lens_h[sel] == ol).all()
 
 
+# ------------------------------------------------------------------------------------------------
+# decompression: the GPU decoders restore what the reference's compressors produced
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("alg", [O.COMP_LZ4, O.COMP_LZF])
+def test_decompress_reference_streams(eng, golden, alg):
+    ref, blob = golden["ref"], golden["blob"]
+    for ent in ref["files"]:
+        d = blob[ent["offset"]: ent["offset"] + ent["size"]]
+        for chunk in (4096, 8192, 65536):
+            n = len(d) // chunk
+            if n == 0:
+                continue
+            blocks, lens = O.compress_chunks(alg, d, chunk)  # byte-identical to the reference's output (test_oracle)
+            if alg == O.COMP_LZF:  # chunks that "did not fit" are stored raw by the caller
+                for i in np.nonzero(lens == 0)[0]:
+                    blocks[i, :chunk] = d[i * chunk:(i + 1) * chunk]
+            out, out_lens = eng.do_decompression(alg, blocks, lens, chunk)
+            assert (out_lens == chunk).all(), (ent["name"], chunk)
+            assert (out == d[: n * chunk]).all(), (ent["name"], chunk)
+
+
+@pytest.mark.parametrize("alg", [O.COMP_LZ4, O.COMP_LZF])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_device_roundtrip_every_block(eng, alg, mode):
+    """compress then decompress 16384 chunks on the device; every decoded chunk must equal its input"""
+    torch = pytest.importorskip("torch")
+    chunk, n = 8192, 16384
+    dev = torch.device("cuda:0")
+    src = torch.empty(n * chunk, dtype=torch.uint8, device=dev)
+    eng.synth_dev(src.data_ptr(), chunk, 777, n)
+    stride = cw.compress_bound(alg, chunk)
+    blocks = torch.zeros(n * stride, dtype=torch.uint8, device=dev)
+    lens = torch.empty(n, dtype=torch.int32, device=dev)
+    back = torch.zeros(n * chunk, dtype=torch.uint8, device=dev)
+    out_lens = torch.empty(n, dtype=torch.int32, device=dev)
+    eng.compress_dev(alg, mode, src.data_ptr(), chunk, n, blocks.data_ptr(), stride, lens.data_ptr())
+    eng.sync()
+    if alg == O.COMP_LZF:  # store the chunks that did not fit raw, as the reference's caller would
+        raw = (lens == 0).nonzero().flatten()
+        assert len(raw) > 0
+        blocks.view(n, stride)[raw, :chunk] = src.view(n, chunk)[raw]
+    torch.cuda.synchronize()
+    eng.decompress_dev(alg, blocks.data_ptr(), stride, lens.data_ptr(), chunk, n, back.data_ptr(), out_lens.data_ptr())
+    eng.sync()
+    assert bool((out_lens == chunk).all())
+    assert torch.equal(back, src)
+
+
+def test_decompress_rejects_malformed_blocks(eng):
+    rng = np.random.default_rng(3)
+    chunk, n = 4096, 64
+    stride = cw.compress_bound(cw.COMP_LZ4, chunk)
+    junk = rng.integers(0, 256, (n, stride), dtype=np.uint8)
+    lens = rng.integers(1, stride, n).astype(np.uint32)
+    out, out_lens = eng.do_decompression(cw.COMP_LZ4, junk, lens, chunk)
+    assert (out_lens == 0).sum() >= n - 1  # random bytes are (almost) never a valid 4096-byte LZ4 block
+    good_b, good_l = O.compress_chunks(O.COMP_LZ4, np.zeros(chunk, np.uint8), chunk)
+    trunc = good_l.copy()
+    trunc[0] -= 1  # truncated stream
+    _, ol = eng.do_decompression(cw.COMP_LZ4, good_b, trunc, chunk)
+    assert ol[0] == 0
+
+
 def test_full_corpus_totals_if_staged(eng, golden):
     """whole Canterbury + Canterbury-large at 4 KiB and 8 KiB against the totals recorded from the reference"""
     import os

@@ -126,3 +126,27 @@ def test_lzf_warp_algorithm_byte_identical(emu, golden):
         blocks, lens = O.compress_chunks(O.COMP_LZF, c, n)
         assert r == lens[0], (n, r, lens[0])
         assert (out[:r] == blocks[0, :r]).all(), n
+
+
+def test_warp_decoders_restore_reference_streams(emu, golden):
+    """csrc/decode_warp.cuh on the emulator: decodes what the oracle (== reference) compressors produced; junk never crashes"""
+    emu.emu_decode.restype = C.c_uint32
+    rng = np.random.default_rng(1)
+    blob = golden["blob"]
+    cases = [blob[i * 8192:(i + 1) * 8192].copy() for i in range(0, 70, 5)] + [
+        np.zeros(8192, np.uint8), rng.integers(0, 256, 8192, dtype=np.uint8), O.synth(8192, 4, 1), blob[:65536].copy(),
+        np.tile(rng.integers(0, 256, 3, dtype=np.uint8), 3000)[:8192], blob[:100].copy()]
+    for c in cases:
+        n = len(c)
+        for alg in (O.COMP_LZ4, O.COMP_LZF):
+            blocks, lens = O.compress_chunks(alg, c, n)
+            if lens[0] == 0:
+                continue
+            out = np.zeros(n, np.uint8)
+            r = emu.emu_decode(alg, blocks[0].ctypes.data_as(C.c_void_p), int(lens[0]), out.ctypes.data_as(C.c_void_p), n)
+            assert r == n and (out == c).all(), (alg, n)
+    for alg in (0, 1):
+        for _ in range(100):
+            junk = rng.integers(0, 256, int(rng.integers(1, 300)), dtype=np.uint8)
+            out = np.zeros(512, np.uint8)
+            emu.emu_decode(alg, junk.ctypes.data_as(C.c_void_p), len(junk), out.ctypes.data_as(C.c_void_p), 512)

@@ -88,9 +88,17 @@ CW_DEV uint32_t cw_lzf_compress_warp(const uint8_t *s, uint32_t n, CwLzfScratch 
         }
         const bool tmatch = valid && q != CW_LZF_NONE && q > 0u && (pos - q - 1u) < CW_LZF_MAX_OFF && hq == hv;
         const uint32_t own = 1u << lane;
-        const uint32_t M13 = cw_match_any(valid ? b : 0x10000u + lane);
-        uint32_t M16 = own, E = own;
-        if (cw_ballot(M13 != own)) {
+        // lanes that share a bucket inside the window ("twins") are detected by tagging the bucket head and reading
+        // it back (MATCH.ANY costs several hundred cycles on sm_100); the chain walk above is done by then, and
+        // phase C rewrites every tagged head
+        cw_syncwarp();
+        if (valid) scr->head[b] = (uint16_t)(0xffe0u | lane);
+        cw_syncwarp();
+        const bool owner = valid && scr->head[b] == (0xffe0u | lane);
+        uint32_t M13 = own, M16 = own, E = own;
+        const uint32_t twins = cw_ballot(valid && !owner);
+        if (twins) {
+            M13 = cw_match_any(valid ? b : 0x10000u + lane);
             M16 = cw_match_any(valid ? slot : 0x10000u + lane);
             E = cw_match_any(valid ? hv : 0x1000000u + lane);
         }
@@ -182,6 +190,10 @@ CW_DEV uint32_t cw_lzf_compress_warp(const uint8_t *s, uint32_t n, CwLzfScratch 
         }
         if (ended_by_match) break;
         // ---------------- phase C: link the inserted positions into their bucket chains ----------------
+        // every bucket touched by a valid lane carries a tag: its owner first puts the old head back, then the
+        // inserted lanes link themselves in (highest inserted lane of a bucket becomes the new head)
+        if (owner) scr->head[b] = (uint16_t)head_old;
+        cw_syncwarp();
         if (valid && ((ins >> lane) & 1u)) {
             const uint32_t grp = M13 & ins;
             const uint32_t lo = grp & lower;

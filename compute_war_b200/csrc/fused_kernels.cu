@@ -55,7 +55,7 @@ static int fused_emitters(bool fast)
         v = e ? atoi(e) : 0;
         if (v > 3) v = 3;
     }
-    return v > 0 ? v : (fast ? 2 : CW_FUSED_EMITTERS_DEFAULT);
+    return v > 0 ? v : 2;
 }
 
 template <int CALG>

@@ -49,10 +49,6 @@
 #ifndef CW_LZ4_SPEC_STEPS
 #define CW_LZ4_SPEC_STEPS 3     // per-lane speculative forward extension in phase A: 4 bytes per step
 #endif
-#ifndef CW_LZ4_STATIC_PATH
-#define CW_LZ4_STATIC_PATH 0   // replay of twin-free unit windows without per-match bookkeeping: +6 % on text,
-                               // -4..-13 % on the mixed stream (profiles/r01_ab_static_spec.txt) -> off
-#endif
 #define CW_LZ4_LIT_SELF 16u   // literal runs up to this long are copied by the recording lane itself
 #define CW_LZ4_TAG 0xffe0u    // slot tag | lane, used for twin detection.  Tags never outlive a window (phase C rewrites
                               // every tagged slot) and are only compared with tags, so they may overlap position values
@@ -167,24 +163,6 @@ CW_DEV void cw_lz4_q_push(CwLz4Queue *q, uint32_t &qh, uint32_t &tailc, uint32_t
         q->rec[qh & (CW_LZ4_QLEN - 1u)][1] = b;
     }
     qh++;
-}
-// parser side: make room for `need` (<= 32) records that the lanes are about to write themselves
-CW_DEV void cw_lz4_q_reserve(CwLz4Queue *q, uint32_t qh, uint32_t &tailc, uint32_t need, unsigned lane)
-{
-    if (qh + need - tailc > CW_LZ4_QLEN) {
-        cw_syncwarp();
-        if (lane == 0) {
-            cw_fence_cta();
-            cw_st_vol(&q->head, qh);
-        }
-        for (;;) {
-            uint32_t t = 0;
-            if (lane == 0) t = cw_ld_vol(&q->tail);
-            tailc = cw_shfl(t, 0);
-            if (qh + need - tailc <= CW_LZ4_QLEN) break;
-            cw_spin();
-        }
-    }
 }
 CW_DEV void cw_lz4_q_publish(CwLz4Queue *q, uint32_t qh, unsigned lane)
 {
@@ -378,78 +356,6 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
             uint32_t ins = 0, i0 = 0, pend = CW_LZ4_NONE;
             const uint32_t qh0 = qh;
             bool restart = false;
-            if (CW_LZ4_STATIC_PATH && unit && !dyn_all) {
-                // Static window (the common case): every hitting lane's candidate is its table entry, so the
-                // replay only has to walk "first hit at or after the previous match's end".  The loop carries
-                // nothing but that; records, the inserted-lanes mask and the anchors are derived afterwards by
-                // all selected lanes in parallel.
-                const uint32_t dlim = cw_umin(32u, mfl1 - base);  // a match ending here or later leaves the window / the input
-                uint32_t S = 0, last_de = 0;                      // selected lanes; end (lane index) of the last match
-                for (;;) {
-                    const uint32_t hm = tm_all & ~((1u << i0) - 1u);
-                    if (!hm) break;
-                    const unsigned f = (unsigned)cw_ffs(hm) - 1u;
-                    const uint32_t sp = cw_shfl(spec, f);
-                    uint32_t fwd = sp & 0x7fffffffu;
-                    if (sp & 0x80000000u) {  // long match: the whole warp extends it, 32 lanes x 4 bytes per step
-                        const uint32_t cur = base + f, cnd = cw_shfl(t, f);
-                        for (;;) {
-                            const uint32_t pa = cur + 4u + fwd + 4u * lane, pb = cnd + 4u + fwd + 4u * lane;
-                            const uint32_t d = cw_lz4_src32<DIRECT>(s, pa, nw) ^ cw_lz4_src32<DIRECT>(s, pb, nw);
-                            uint32_t eq = d ? (uint32_t)(cw_ffs(d) - 1) >> 3 : 4u;
-                            eq = cw_umin(eq, pa < matchlimit ? matchlimit - pa : 0u);
-                            const uint32_t stop = cw_ballot(eq < 4u);
-                            if (stop) {
-                                const unsigned L = (unsigned)cw_ffs(stop) - 1u;
-                                fwd += 4u * L + cw_shfl(eq, L);
-                                break;
-                            }
-                            fwd += 128u;
-                        }
-                        if (lane == f) spec = fwd;
-                    }
-                    S |= 1u << f;
-                    spec_on = fwd < 28u;
-                    last_de = f + 4u + fwd;
-                    if (last_de >= dlim) break;
-                    i0 = last_de;
-                }
-                if (S) {
-                    const bool sel = (S >> lane) & 1u;
-                    const uint32_t myfw = spec & 0x7fffffffu;
-                    const uint32_t my_de = lane + 4u + myfw;  // lane index one past my match
-                    const uint32_t below = S & lower;
-                    const uint32_t prev_de = cw_shfl(my_de, below ? (unsigned)(31 - cw_clz(below)) : lane);
-                    const uint32_t my_anchor = below ? base + prev_de : anchor;
-                    const uint32_t nsel = (uint32_t)cw_popc(S);
-                    cw_lz4_q_reserve(q, qh, tailc, nsel, lane);
-                    if (sel) {
-                        const uint32_t idx = (qh + (uint32_t)cw_popc(below)) & (CW_LZ4_QLEN - 1u);
-                        q->rec[idx][0] = my_anchor | (pos << 16);
-                        q->rec[idx][1] = t | (myfw << 16);
-                    }
-                    qh += nsel;
-                    // lanes inside a match were never probed -- except the parser's insert of position e-2
-                    uint32_t cov = 0;
-                    if (sel) {
-                        const uint32_t hi = cw_umin(my_de, 32u);
-                        cov = (hi >= 32u ? 0xffffffffu : (1u << hi) - 1u) & ~((2u << lane) - 1u);
-                        if (my_de < 34u) cov &= ~(1u << (my_de - 2u));
-                    }
-                    ins = vmask & ~cw_reduce_or(cov);
-                    anchor = base + last_de;
-                    sbase = anchor + 1u;
-                    if (last_de >= mfl1 - base) done = true;  // "if (ip > mflimit) break" -> last literals
-                    else if (last_de >= 32u) {
-                        restart = true;
-                        if (last_de >= 34u) pend = anchor - 2u;
-                    } else
-                        done = vmask != 0xffffffffu;  // window exhausted; an invalid lane is the end-of-input rule
-                } else {
-                    ins = vmask;
-                    done = vmask != 0xffffffffu;
-                }
-            } else
             for (;;) {
                 const uint32_t range = ~((1u << i0) - 1u);
                 uint32_t hitm = tm_all & range;

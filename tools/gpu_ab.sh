@@ -1,5 +1,4 @@
-for v in "" _static _nospec; do for mode in 0 1; do
+for v in "" _static; do for mode in 0 1; do
   export CW_LIB=$PWD/compute_war_b200/libcomputewar$v.so CW_MODE=$mode
-  python tools/prof_classes.py lz4 8192 2>&1 | grep "synthetic\|bible\|kennedy" | sed "s/^/v=[$v] mode=$mode /"
-  python tools/prof_classes.py fused 8192 2>&1 | grep "synthetic mixed\|bible" | sed "s/^/v=[$v] mode=$mode /"
+  python tools/prof_classes.py fused 8192 2>&1 | grep "synthetic\|bible\|kennedy" | sed "s/^/v=[$v] mode=$mode /"
 done; done

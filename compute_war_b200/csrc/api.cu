@@ -57,6 +57,8 @@ struct cw_ctx {
     std::atomic<uint64_t> launches{0};
     unsigned long long *d_work = nullptr;
     int work_next = 0;
+    unsigned long long *d_pack = nullptr;  // scratch of cw_pack_dev (tile totals)
+    size_t pack_cap = 0;
     std::mutex mu;       // guards work ring, profiling lists, last_error
     std::mutex host_mu;  // one host-buffer pipeline at a time per context
     std::string last_error;
@@ -376,6 +378,7 @@ void cw_shutdown(cw_ctx *ctx)
     }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->d_work) cudaFree(ctx->d_work);
+    if (ctx->d_pack) cudaFree(ctx->d_pack);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -539,6 +542,32 @@ int cw_decompress(cw_ctx *ctx, cw_comp_alg alg, const void *blocks, size_t strid
     cudaFree(d_ol);
     if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? CW_ERR_NOMEM : fail(ctx, e, "cw_decompress");
     return rc;
+}
+
+int cw_pack_dev(cw_ctx *ctx, const void *d_blocks, size_t stride, const uint32_t *d_lens, const void *d_src, size_t chunk,
+                size_t n, void *d_packed, size_t packed_cap, uint64_t *d_offsets, void *stream)
+{
+    int rc = check_common(ctx, chunk, n, d_blocks);
+    if (rc != CW_OK) return rc;
+    if (n && (!d_lens || !d_offsets || (!d_packed && packed_cap))) return CW_ERR_ARG;
+    if (n == 0) return CW_OK;
+    CW_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    const size_t need = ((n + 1023) / 1024 + 1) * sizeof(unsigned long long);
+    {
+        std::lock_guard<std::mutex> g(ctx->mu);
+        if (ctx->pack_cap < need) {
+            if (ctx->d_pack) cudaFree(ctx->d_pack);
+            ctx->d_pack = nullptr;
+            ctx->pack_cap = 0;
+            if (cudaMalloc(&ctx->d_pack, need) != cudaSuccess) return CW_ERR_NOMEM;
+            ctx->pack_cap = need;
+        }
+    }
+    CW_CUDA(ctx, cw_launch_pack((const uint8_t *)d_blocks, stride, d_lens, (const uint8_t *)d_src, (uint32_t)chunk, n,
+                                (uint8_t *)d_packed, packed_cap, (unsigned long long *)d_offsets, ctx->d_pack, st));
+    ctx->launches += 3;
+    return CW_OK;
 }
 
 int cw_synth_dev(cw_ctx *ctx, void *d_dst, size_t chunk, uint64_t first_chunk, size_t n, uint64_t seed, void *stream)

@@ -44,5 +44,10 @@ cudaError_t cw_launch_decode(const CwDeviceInfo &dev, int alg, const uint8_t *d_
                              cudaStream_t st);
 cudaError_t cw_decode_configure(const CwDeviceInfo &dev);
 
+// pack_kernels.cu -- d_offsets: u64[n + 1]; d_scratch: u64[ceil(n / 1024) + 1]
+cudaError_t cw_launch_pack(const uint8_t *d_blocks, uint64_t stride, const uint32_t *d_lens, const uint8_t *d_src, uint32_t chunk,
+                           uint64_t n, uint8_t *d_packed, uint64_t packed_cap, unsigned long long *d_offsets,
+                           unsigned long long *d_scratch, cudaStream_t st);
+
 // all per-kernel attribute set-up (opt-in shared memory sizes); called once from cw_init
 cudaError_t cw_configure_kernels(const CwDeviceInfo &dev);

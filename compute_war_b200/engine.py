@@ -67,6 +67,7 @@ def load_library():
     L.cw_hash_compress_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, sz, sz, vp, vp, sz, vp, vp]
     L.cw_decompress.argtypes = [vp, C.c_int, vp, sz, vp, sz, sz, vp, vp]
     L.cw_decompress_dev.argtypes = [vp, C.c_int, vp, sz, vp, sz, sz, vp, vp, vp]
+    L.cw_pack_dev.argtypes = [vp, vp, sz, vp, vp, sz, sz, vp, sz, vp, vp]
     L.cw_sync.argtypes = [vp, vp]
     L.cw_submit.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, sz, sz, vp, vp, sz, vp, vp, vp, C.POINTER(u64)]
     L.cw_wait.argtypes = [vp, u64]
@@ -208,6 +209,11 @@ class Engine:
         self._check(self.L.cw_decompress(self.h, comp_alg, b.ctypes.data, stride, l.ctypes.data, chunk, n, out.ctypes.data,
                                          out_lens.ctypes.data))
         return out, out_lens
+
+    def pack_dev(self, d_blocks, stride, d_lens, d_src, chunk, n, d_packed, packed_cap, d_offsets, stream=0):
+        """strided blocks -> contiguous stream + u64 offsets[n + 1] (blocks of length 0 are stored raw from d_src)"""
+        self._check(self.L.cw_pack_dev(self.h, d_blocks, stride, d_lens, d_src or None, chunk, n, d_packed, packed_cap,
+                                       d_offsets, stream or None))
 
     def synth_dev(self, d_dst, chunk, first_chunk, n, seed=0xC0FFEE, stream=0):
         self._check(self.L.cw_synth_dev(self.h, d_dst, chunk, first_chunk, n, seed, stream or None))

@@ -114,6 +114,15 @@ int cw_decompress(cw_ctx *ctx, cw_comp_alg alg, const void *blocks, size_t strid
 int cw_decompress_dev(cw_ctx *ctx, cw_comp_alg alg, const void *d_blocks, size_t stride, const uint32_t *d_lens,
                       size_t chunk_bytes, size_t n_chunks, void *d_out, uint32_t *d_out_lens, void *stream);
 
+/* ---- packed output (device buffers): compacts a strided block array into one contiguous stream.
+ * offsets[i] (u64, n_chunks + 1 entries) = start of block i in `packed`; offsets[n_chunks] = total bytes.
+ * A block of length 0 (lzf_compress "did not fit", lzf.h:59-64) is stored raw: chunk_bytes copied from d_src (required
+ * then).  If packed_cap is too small the offsets are still produced (so the caller learns the size) and blocks that
+ * do not fit are skipped.  The reference discards its blocks (HashAndCompress.cpp:259-260); SURVEY.md 8(f) row 2.
+ * The single-stream use of one context is assumed (the scratch buffer belongs to the context). ---- */
+int cw_pack_dev(cw_ctx *ctx, const void *d_blocks, size_t stride, const uint32_t *d_lens, const void *d_src,
+                size_t chunk_bytes, size_t n_chunks, void *d_packed, size_t packed_cap, uint64_t *d_offsets, void *stream);
+
 /* ---- asynchronous offload: HashOffload::{Reset,Enqueue,Start,Complete} (HashOffload.h:15-64) and the
  * consumer loop hashing_offload_entry_point (HashAndCompress.cpp:160-183) ----
  * cw_submit = Reset+Enqueue+Start: queues one fused batch (host buffers) and returns at once;

@@ -332,6 +332,37 @@ def test_device_roundtrip_every_block(eng, alg, mode):
     assert torch.equal(back, src)
 
 
+@pytest.mark.parametrize("alg", [O.COMP_LZ4, O.COMP_LZF])
+def test_packed_output(eng, alg):
+    """cw_pack_dev: offsets = exclusive scan of stored sizes (raw size where LZF returned 0), bytes back to back"""
+    torch = pytest.importorskip("torch")
+    from compute_war_b200.sharding import packed_offsets
+    chunk, n = 8192, 5000  # not a multiple of the 1024-chunk scan tile
+    dev = torch.device("cuda:0")
+    src = torch.empty(n * chunk, dtype=torch.uint8, device=dev)
+    eng.synth_dev(src.data_ptr(), chunk, 31, n)
+    stride = cw.compress_bound(alg, chunk)
+    blocks = torch.zeros(n * stride, dtype=torch.uint8, device=dev)
+    lens = torch.empty(n, dtype=torch.int32, device=dev)
+    eng.compress_dev(alg, cw.MODE_COMPAT, src.data_ptr(), chunk, n, blocks.data_ptr(), stride, lens.data_ptr())
+    eng.sync()
+    lens_h = lens.cpu().numpy().astype(np.uint32)
+    want = packed_offsets(lens_h, chunk)
+    packed = torch.zeros(int(want[-1]) + 64, dtype=torch.uint8, device=dev)
+    offsets = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    eng.pack_dev(blocks.data_ptr(), stride, lens.data_ptr(), src.data_ptr(), chunk, n, packed.data_ptr(), int(want[-1]),
+                 offsets.data_ptr())
+    eng.sync()
+    assert (offsets.cpu().numpy() == want).all()
+    p = packed.cpu().numpy()
+    b = blocks.cpu().numpy().reshape(n, stride)
+    s_h = src.cpu().numpy().reshape(n, chunk)
+    for i in list(range(0, 40)) + list(range(1020, 1030)) + list(range(n - 40, n)):
+        seg = p[want[i]: want[i + 1]]
+        assert (seg == (b[i, : lens_h[i]] if lens_h[i] else s_h[i])).all(), i
+    assert (p[want[-1]:] == 0).all()  # nothing written past the end
+
+
 def test_decompress_rejects_malformed_blocks(eng):
     rng = np.random.default_rng(3)
     chunk, n = 4096, 64

@@ -5,6 +5,7 @@
 // HashAndCompress.cpp:95-98, doHashing :119-134, doCompression :111,342-355, ProcessBlock :231-261,
 // HashOffload HashOffload.h:15-64 + hashing_offload_entry_point HashAndCompress.cpp:160-183.
 #include <atomic>
+#include <cmath>
 #include <cstdlib>
 #include <condition_variable>
 #include <deque>
@@ -59,6 +60,8 @@ struct cw_ctx {
     int work_next = 0;
     unsigned long long *d_pack = nullptr;  // scratch of cw_pack_dev (tile totals)
     size_t pack_cap = 0;
+    uint32_t *d_dedup = nullptr;  // slot table of cw_dedup_dev
+    size_t dedup_slots = 0;
     std::mutex mu;       // guards work ring, profiling lists, last_error
     std::mutex host_mu;  // one host-buffer pipeline at a time per context
     std::string last_error;
@@ -379,6 +382,7 @@ void cw_shutdown(cw_ctx *ctx)
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->d_work) cudaFree(ctx->d_work);
     if (ctx->d_pack) cudaFree(ctx->d_pack);
+    if (ctx->d_dedup) cudaFree(ctx->d_dedup);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -558,6 +562,7 @@ int cw_pack_dev(cw_ctx *ctx, const void *d_blocks, size_t stride, const uint32_t
         std::lock_guard<std::mutex> g(ctx->mu);
         if (ctx->pack_cap < need) {
             if (ctx->d_pack) cudaFree(ctx->d_pack);
+    if (ctx->d_dedup) cudaFree(ctx->d_dedup);
             ctx->d_pack = nullptr;
             ctx->pack_cap = 0;
             if (cudaMalloc(&ctx->d_pack, need) != cudaSuccess) return CW_ERR_NOMEM;
@@ -567,6 +572,87 @@ int cw_pack_dev(cw_ctx *ctx, const void *d_blocks, size_t stride, const uint32_t
     CW_CUDA(ctx, cw_launch_pack((const uint8_t *)d_blocks, stride, d_lens, (const uint8_t *)d_src, (uint32_t)chunk, n,
                                 (uint8_t *)d_packed, packed_cap, (unsigned long long *)d_offsets, ctx->d_pack, st));
     ctx->launches += 3;
+    return CW_OK;
+}
+
+int cw_digest_hist_dev(cw_ctx *ctx, const void *d_digests, size_t D, size_t n, uint64_t *d_hist, void *stream)
+{
+    if (!ctx || D == 0 || D > 1024 || !d_hist || (n && !d_digests)) return CW_ERR_ARG;
+    CW_CUDA(ctx, cudaSetDevice(ctx->device));
+    CW_CUDA(ctx, cw_launch_digest_hist(ctx->dev, (const uint8_t *)d_digests, (uint32_t)D, n, (unsigned long long *)d_hist,
+                                       stream ? (cudaStream_t)stream : ctx->stream));
+    if (n) ctx->launches++;
+    return CW_OK;
+}
+
+int cw_digest_byte_stats(const uint64_t *hist, size_t n_bytes, double *avg, double *stddev, double *avg_stddev)
+{
+    if (!hist || n_bytes == 0) return CW_ERR_ARG;
+    double sum_sd = 0;
+    for (size_t b = 0; b < n_bytes; b++) {
+        const uint64_t *h = hist + b * 256;
+        // the reference's map holds the values 0..254 from the start and 255 only once it has been seen
+        const int present = h[255] ? 256 : 255;
+        uint64_t total = 0;
+        for (int v = 0; v < present; v++) total += h[v];
+        const double a = (double)total / 255.0;
+        double sd = 0;
+        for (int v = 0; v < present; v++) {
+            const double d = (double)h[v] - a;
+            sd += d * d;
+        }
+        sd = std::sqrt(sd / 254.0);
+        if (avg) avg[b] = a;
+        if (stddev) stddev[b] = sd;
+        sum_sd += sd;
+    }
+    if (avg_stddev) *avg_stddev = sum_sd / (double)n_bytes;
+    return CW_OK;
+}
+
+int cw_digest_stats(cw_ctx *ctx, const void *digests, size_t D, size_t n, size_t n_bytes, double *avg, double *stddev,
+                    double *avg_stddev)
+{
+    if (!ctx || D == 0 || D > 1024 || n_bytes == 0 || n_bytes > D || (n && !digests)) return CW_ERR_ARG;
+    CW_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> hg(ctx->host_mu);
+    uint8_t *d_dig = nullptr;
+    unsigned long long *d_hist = nullptr;
+    std::vector<uint64_t> hist(D * 256);
+    cudaError_t e = cudaMalloc(&d_hist, hist.size() * sizeof(uint64_t));
+    if (e == cudaSuccess && n) e = cudaMalloc(&d_dig, n * D);
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(d_dig, digests, n * D, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cw_launch_digest_hist(ctx->dev, d_dig, (uint32_t)D, n, d_hist, ctx->stream);
+    if (e == cudaSuccess && n) ctx->launches++;
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(hist.data(), d_hist, hist.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_dig);
+    cudaFree(d_hist);
+    if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? CW_ERR_NOMEM : fail(ctx, e, "cw_digest_stats");
+    return cw_digest_byte_stats(hist.data(), n_bytes, avg, stddev, avg_stddev);
+}
+
+int cw_dedup_dev(cw_ctx *ctx, const void *d_digests, size_t D, size_t n, uint32_t *d_first, uint64_t *d_n_unique, void *stream)
+{
+    if (!ctx || D == 0 || (D & 3u) || D > 1024 || !d_n_unique || (n && (!d_digests || !d_first))) return CW_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_digests) & 3u) || n >= (1ull << 31)) return CW_ERR_ARG;
+    CW_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t slots = 1024;
+    while (slots < 2 * n) slots <<= 1;
+    {
+        std::lock_guard<std::mutex> g(ctx->mu);
+        if (ctx->dedup_slots < slots) {
+            if (ctx->d_dedup) cudaFree(ctx->d_dedup);
+            ctx->d_dedup = nullptr;
+            ctx->dedup_slots = 0;
+            if (cudaMalloc(&ctx->d_dedup, slots * sizeof(uint32_t)) != cudaSuccess) return CW_ERR_NOMEM;
+            ctx->dedup_slots = slots;
+        }
+    }
+    CW_CUDA(ctx, cw_launch_dedup((const uint8_t *)d_digests, (uint32_t)D, n, ctx->d_dedup, (uint32_t)slots, d_first,
+                                 (unsigned long long *)d_n_unique, stream ? (cudaStream_t)stream : ctx->stream));
+    if (n) ctx->launches += 2;
     return CW_OK;
 }
 

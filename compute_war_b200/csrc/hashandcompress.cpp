@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <iostream>
 #include <string>
 #include <vector>
 
@@ -39,14 +40,16 @@ static void usage(const char *argv0, const char *msg = nullptr)
             "  -k, --chunk BYTES     chunk size (default 4096)\n"
             "  -m, --mode M          compat | fast (default compat)\n"
             "  -d, --device N        CUDA device (default 0)\n"
-            "  -i, --iters N         repeat the timed pass N times (default 1)\n",
+            "  -i, --iters N         repeat the timed pass N times (default 1)\n"
+            "  -R, --randomness      also print the digest byte distribution lines of the reference's hashing_randomness\n"
+            "                        tool (byte|alg|avg|stddev|, then \"Average std dev\") for the first 16 digest bytes\n",
             argv0);
     exit(msg ? 2 : 0);
 }
 
 int main(int argc, char **argv)
 {
-    int threads = 8, offload = 0, device = 0, iters = 1;
+    int threads = 8, offload = 0, device = 0, iters = 1, randomness = 0;
     size_t chunk = 4096;
     std::string comp = "lz4", hash = "skein", mode = "compat";
     static const option opts[] = {{"help", no_argument, 0, 'h'},          {"c-threads", required_argument, 0, 'c'},
@@ -54,9 +57,10 @@ int main(int argc, char **argv)
                                   {"hash-blocks", required_argument, 0, 'G'}, {"comp-alg", required_argument, 0, 'C'},
                                   {"hash-alg", required_argument, 0, 'H'},    {"chunk", required_argument, 0, 'k'},
                                   {"mode", required_argument, 0, 'm'},        {"device", required_argument, 0, 'd'},
-                                  {"iters", required_argument, 0, 'i'},       {0, 0, 0, 0}};
+                                  {"iters", required_argument, 0, 'i'},       {"randomness", no_argument, 0, 'R'},
+                                  {0, 0, 0, 0}};
     int o;
-    while ((o = getopt_long(argc, argv, "hc:g:r:G:C:H:k:m:d:i:", opts, nullptr)) != -1) {
+    while ((o = getopt_long(argc, argv, "hc:g:r:G:C:H:k:m:d:i:R", opts, nullptr)) != -1) {
         switch (o) {
         case 'h': usage(argv[0]); break;
         case 'c': threads = atoi(optarg); break;
@@ -69,6 +73,7 @@ int main(int argc, char **argv)
         case 'm': mode = optarg; break;
         case 'd': device = atoi(optarg); break;
         case 'i': iters = atoi(optarg); break;
+        case 'R': randomness = 1; break;
         default: usage(argv[0], "bad option");
         }
     }
@@ -151,6 +156,18 @@ int main(int argc, char **argv)
     printf("%s|%s|%llu|%llu\n", hash.c_str(), comp.c_str(), (unsigned long long)(ms + 0.5), (unsigned long long)mbps);
     // ... plus what it throws away
     fprintf(stderr, "chunks=%zu chunk=%zu ms=%.3f MBps=%.1f ratio=%.4f\n", n, chunk, ms, mbps, (double)csum / (double)(n * chunk));
+    if (randomness) {
+        // Hasher::LogResultsInternal / LogByteResults, src/hashing_randomness/hash.cpp:30-101
+        const size_t nb = 16;
+        double avg[16], sd[16], tot = 0;
+        rc = cw_digest_stats(ctx, digests.data(), D, n, nb, avg, sd, &tot);
+        if (rc != CW_OK) {
+            fprintf(stderr, "engine: %s (%s)\n", cw_status_string(rc), cw_last_error(ctx));
+            return 1;
+        }
+        for (size_t b = 0; b < nb; b++) std::cout << b << "|" << hash << "|" << avg[b] << "|" << sd[b] << "|" << std::endl;
+        std::cout << "Average std dev: " << tot << std::endl;
+    }
     cw_shutdown(ctx);
     return 0;
 }

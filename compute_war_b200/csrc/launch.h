@@ -49,5 +49,12 @@ cudaError_t cw_launch_pack(const uint8_t *d_blocks, uint64_t stride, const uint3
                            uint64_t n, uint8_t *d_packed, uint64_t packed_cap, unsigned long long *d_offsets,
                            unsigned long long *d_scratch, cudaStream_t st);
 
+// digest_kernels.cu -- d_hist: u64[D * 256] (zeroed by the launch); d_table: u32[table_slots], table_slots a power of
+// two >= 2 * n; D % 4 == 0 for the dedup kernels
+cudaError_t cw_launch_digest_hist(const CwDeviceInfo &dev, const uint8_t *d_digests, uint32_t D, uint64_t n,
+                                  unsigned long long *d_hist, cudaStream_t st);
+cudaError_t cw_launch_dedup(const uint8_t *d_digests, uint32_t D, uint64_t n, uint32_t *d_table, uint32_t table_slots,
+                            uint32_t *d_first, unsigned long long *d_n_unique, cudaStream_t st);
+
 // all per-kernel attribute set-up (opt-in shared memory sizes); called once from cw_init
 cudaError_t cw_configure_kernels(const CwDeviceInfo &dev);

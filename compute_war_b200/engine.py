@@ -68,6 +68,10 @@ def load_library():
     L.cw_decompress.argtypes = [vp, C.c_int, vp, sz, vp, sz, sz, vp, vp]
     L.cw_decompress_dev.argtypes = [vp, C.c_int, vp, sz, vp, sz, sz, vp, vp, vp]
     L.cw_pack_dev.argtypes = [vp, vp, sz, vp, vp, sz, sz, vp, sz, vp, vp]
+    L.cw_digest_hist_dev.argtypes = [vp, vp, sz, sz, vp, vp]
+    L.cw_digest_byte_stats.argtypes = [vp, sz, vp, vp, C.POINTER(C.c_double)]
+    L.cw_digest_stats.argtypes = [vp, vp, sz, sz, sz, vp, vp, C.POINTER(C.c_double)]
+    L.cw_dedup_dev.argtypes = [vp, vp, sz, sz, vp, vp, vp]
     L.cw_sync.argtypes = [vp, vp]
     L.cw_submit.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, sz, sz, vp, vp, sz, vp, vp, vp, C.POINTER(u64)]
     L.cw_wait.argtypes = [vp, u64]
@@ -214,6 +218,26 @@ class Engine:
         """strided blocks -> contiguous stream + u64 offsets[n + 1] (blocks of length 0 are stored raw from d_src)"""
         self._check(self.L.cw_pack_dev(self.h, d_blocks, stride, d_lens, d_src or None, chunk, n, d_packed, packed_cap,
                                        d_offsets, stream or None))
+
+    # ---- digest post-processing (src/hashing_randomness/hash.cpp:30-101; dedup map) ----
+    def digest_hist_dev(self, d_digests, digest_bytes, n, d_hist, stream=0):
+        """d_hist: u64[digest_bytes * 256]; hist[b*256 + v] = digests whose byte b equals v"""
+        self._check(self.L.cw_digest_hist_dev(self.h, d_digests, digest_bytes, n, d_hist, stream or None))
+
+    def digest_stats(self, digests: np.ndarray, n_bytes: int = 16):
+        """Hasher::LogResults figures: (avg[n_bytes], stddev[n_bytes], average std dev)"""
+        d = np.ascontiguousarray(digests, dtype=np.uint8)
+        n, D = d.shape
+        avg = np.zeros(n_bytes, np.float64)
+        sd = np.zeros(n_bytes, np.float64)
+        tot = C.c_double()
+        self._check(self.L.cw_digest_stats(self.h, d.ctypes.data, D, n, n_bytes, avg.ctypes.data, sd.ctypes.data,
+                                           C.byref(tot)))
+        return avg, sd, tot.value
+
+    def dedup_dev(self, d_digests, digest_bytes, n, d_first, d_n_unique, stream=0):
+        """d_first: u32[n], first[i] = smallest j with an equal digest; d_n_unique: u64"""
+        self._check(self.L.cw_dedup_dev(self.h, d_digests, digest_bytes, n, d_first, d_n_unique, stream or None))
 
     def synth_dev(self, d_dst, chunk, first_chunk, n, seed=0xC0FFEE, stream=0):
         self._check(self.L.cw_synth_dev(self.h, d_dst, chunk, first_chunk, n, seed, stream or None))

@@ -123,6 +123,23 @@ int cw_decompress_dev(cw_ctx *ctx, cw_comp_alg alg, const void *d_blocks, size_t
 int cw_pack_dev(cw_ctx *ctx, const void *d_blocks, size_t stride, const uint32_t *d_lens, const void *d_src,
                 size_t chunk_bytes, size_t n_chunks, void *d_packed, size_t packed_cap, uint64_t *d_offsets, void *stream);
 
+/* ---- digest post-processing: what the digests are computed for ----
+ * cw_digest_hist_dev: hist[b*256 + v] (u64, digest_bytes*256 entries) = number of digests whose byte b has value v --
+ *   the table Hasher::LogResultsInternal accumulates (src/hashing_randomness/hash.cpp:30-58).
+ * cw_digest_byte_stats: the per-byte figures the reference prints from that table (hash.cpp:60-101), for the first
+ *   n_bytes digest bytes (the reference uses 16): avg[b] = total/255, stddev[b] = sqrt(sum (count-avg)^2 / 254) over the
+ *   values 0..254 plus 255 only when it occurred (its map is pre-filled with `bucket < UINT8_MAX`), *avg_stddev = their
+ *   mean ("Average std dev").  Pure arithmetic on 256*n_bytes numbers; runs on the host.
+ * cw_digest_stats: both steps for digests in host memory.
+ * cw_dedup_dev: first[i] = smallest j with digest j == digest i (first[i] == i <=> a deduplicating store keeps chunk
+ *   i), *n_unique = number of distinct digests.  digest_bytes % 4 == 0, n < 2^31. */
+int cw_digest_hist_dev(cw_ctx *ctx, const void *d_digests, size_t digest_bytes, size_t n, uint64_t *d_hist, void *stream);
+int cw_digest_byte_stats(const uint64_t *hist, size_t n_bytes, double *avg, double *stddev, double *avg_stddev);
+int cw_digest_stats(cw_ctx *ctx, const void *digests, size_t digest_bytes, size_t n, size_t n_bytes, double *avg,
+                    double *stddev, double *avg_stddev);
+int cw_dedup_dev(cw_ctx *ctx, const void *d_digests, size_t digest_bytes, size_t n, uint32_t *d_first, uint64_t *d_n_unique,
+                 void *stream);
+
 /* ---- asynchronous offload: HashOffload::{Reset,Enqueue,Start,Complete} (HashOffload.h:15-64) and the
  * consumer loop hashing_offload_entry_point (HashAndCompress.cpp:160-183) ----
  * cw_submit = Reset+Enqueue+Start: queues one fused batch (host buffers) and returns at once;

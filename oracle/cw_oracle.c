@@ -19,6 +19,7 @@
 #include "cw_oracle.h"
 #include "../include/cw_synth.h"
 
+#include <math.h>
 #include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
@@ -614,3 +615,64 @@ void cwo_synth_fill(uint8_t *dst, size_t chunk, uint64_t first_chunk, size_t n, 
 }
 
 unsigned cwo_synth_class(uint64_t seed, uint64_t idx) { return cw_synth_class(seed, idx); }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Digest randomness study: src/hashing_randomness/hash.cpp:30-101.
+ * LogResultsInternal (:30-72) keeps, per digest byte, a map value -> count that is pre-filled with the keys
+ * 0..254 (`bucket < UINT8_MAX`, :38) and gains the key 255 only through operator[] when such a byte is seen (:55).
+ * LogByteResults (:74-101): total = sum of the counts, avg = total / UINT8_MAX (255), stdDev = sqrt(sum over the
+ * map's entries of (count - avg)^2 / (UINT8_MAX - 1)).  The summation order is the map's (ascending value).
+ * ------------------------------------------------------------------------------------------------------------------ */
+double cwo_digest_byte_stats(const uint8_t *digests, size_t D, size_t n, size_t n_bytes, double *avg, double *stddev)
+{
+    double total_sd = 0;
+    for (size_t b = 0; b < n_bytes; b++) {
+        size_t count[256];
+        int have255 = 0;
+        memset(count, 0, sizeof count);
+        for (size_t i = 0; i < n; i++) {
+            const uint8_t v = digests[i * D + b];
+            if (v == 255) have255 = 1;
+            count[v]++;
+        }
+        const int entries = have255 ? 256 : 255;
+        size_t total = 0;
+        for (int v = 0; v < entries; v++) total += count[v];
+        const double a = (double)total / 255;
+        double sd = 0;
+        for (int v = 0; v < entries; v++) sd += pow((double)count[v] - a, 2);
+        sd /= 254;
+        sd = sqrt(sd);
+        if (avg) avg[b] = a;
+        if (stddev) stddev[b] = sd;
+        total_sd += sd;
+    }
+    return total_sd / (double)n_bytes;
+}
+
+/* dedup map by definition: sort (digest, index) pairs, the first of every run of equal digests is the keeper */
+static size_t g_dedup_D;
+static const uint8_t *g_dedup_base;
+static int dedup_cmp(const void *pa, const void *pb)
+{
+    const uint32_t a = *(const uint32_t *)pa, b = *(const uint32_t *)pb;
+    const int c = memcmp(g_dedup_base + (size_t)a * g_dedup_D, g_dedup_base + (size_t)b * g_dedup_D, g_dedup_D);
+    return c ? c : (a < b ? -1 : (a > b));
+}
+size_t cwo_dedup_first(const uint8_t *digests, size_t D, size_t n, uint32_t *first)
+{
+    uint32_t *idx = (uint32_t *)malloc((n ? n : 1) * sizeof(uint32_t));
+    size_t uniq = 0;
+    for (size_t i = 0; i < n; i++) idx[i] = (uint32_t)i;
+    g_dedup_D = D;
+    g_dedup_base = digests;
+    qsort(idx, n, sizeof(uint32_t), dedup_cmp);
+    for (size_t i = 0; i < n;) {
+        size_t j = i;
+        while (j < n && memcmp(digests + (size_t)idx[j] * D, digests + (size_t)idx[i] * D, D) == 0) first[idx[j++]] = idx[i];
+        uniq++;
+        i = j;
+    }
+    free(idx);
+    return uniq;
+}

@@ -76,6 +76,14 @@ double cwo_hash_compress_mt(int hash_alg, int comp_alg, const uint8_t *src, size
 unsigned cwo_synth_class(uint64_t seed, uint64_t idx);
 void cwo_synth_fill(uint8_t *dst, size_t chunk, uint64_t first_chunk, size_t n, uint64_t seed);
 
+/* The digest randomness study, Hasher::LogResultsInternal + LogByteResults (src/hashing_randomness/hash.cpp:30-101),
+ * over the first n_bytes bytes of n digests of D bytes: avg[b], stddev[b] = the two numbers of the reference's log line
+ * for byte b; returns "Average std dev". */
+double cwo_digest_byte_stats(const uint8_t *digests, size_t D, size_t n, size_t n_bytes, double *avg, double *stddev);
+/* first[i] = smallest j with digest j == digest i (definition of the dedup map; the reference has no counterpart);
+ * returns the number of distinct digests */
+size_t cwo_dedup_first(const uint8_t *digests, size_t D, size_t n, uint32_t *first);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,10 @@ def lib():
                                            C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
         L.cwo_hash_compress_mt.restype = C.c_double
         L.cwo_synth_fill.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_size_t, C.c_uint64]
+        L.cwo_digest_byte_stats.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.cwo_digest_byte_stats.restype = C.c_double
+        L.cwo_dedup_first.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+        L.cwo_dedup_first.restype = C.c_size_t
         _lib = L
     return _lib
 
@@ -138,6 +142,24 @@ def synth(chunk: int, first_chunk: int, n: int, seed: int = 0xC0FFEE) -> np.ndar
     out = np.zeros(n * chunk, np.uint8)
     lib().cwo_synth_fill(_ptr(out), chunk, first_chunk, n, seed)
     return out
+
+
+def digest_byte_stats(digests: np.ndarray, n_bytes: int = 16):
+    """(avg[n_bytes], stddev[n_bytes], average std dev) as src/hashing_randomness/hash.cpp:30-101 logs them"""
+    d = np.ascontiguousarray(digests, dtype=np.uint8)
+    n, D = d.shape
+    avg = np.zeros(n_bytes, dtype=np.float64)
+    sd = np.zeros(n_bytes, dtype=np.float64)
+    tot = lib().cwo_digest_byte_stats(_ptr(d), D, n, n_bytes, _ptr(avg), _ptr(sd))
+    return avg, sd, float(tot)
+
+
+def dedup_first(digests: np.ndarray):
+    d = np.ascontiguousarray(digests, dtype=np.uint8)
+    n, D = d.shape
+    first = np.zeros(max(n, 1), dtype=np.uint32)
+    uniq = lib().cwo_dedup_first(_ptr(d), D, n, _ptr(first))
+    return first[:n], int(uniq)
 
 
 def hash_compress_mt(halg: int, calg: int, data: np.ndarray, chunk: int, threads: int):

@@ -363,6 +363,84 @@ def test_packed_output(eng, alg):
     assert (p[want[-1]:] == 0).all()  # nothing written past the end
 
 
+# ------------------------------------------------------------------------------------------------
+# digest post-processing
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("halg", [O.HASH_SKEIN256_128, O.HASH_SKEIN512, O.HASH_SHA256])
+def test_digest_byte_distribution_matches_reference_statistic(eng, halg):
+    """cw_digest_hist_dev + cw_digest_byte_stats == Hasher::LogResults' numbers (hashing_randomness/hash.cpp:30-101)"""
+    torch = pytest.importorskip("torch")
+    chunk, n = 4096, 20000
+    D = cw.digest_bytes(halg)
+    dev = torch.device("cuda:0")
+    src = torch.empty(n * chunk, dtype=torch.uint8, device=dev)
+    eng.synth_dev(src.data_ptr(), chunk, 5, n)
+    dig = torch.empty(n * D, dtype=torch.uint8, device=dev)
+    eng.hash_dev(halg, src.data_ptr(), chunk, n, dig.data_ptr())
+    hist = torch.full((D * 256,), -1, dtype=torch.int64, device=dev)
+    eng.digest_hist_dev(dig.data_ptr(), D, n, hist.data_ptr())
+    eng.sync()
+    dig_h = dig.cpu().numpy().reshape(n, D)
+    want = np.stack([np.bincount(dig_h[:, b], minlength=256) for b in range(D)]).reshape(-1)
+    assert (hist.cpu().numpy() == want).all()
+    avg, sd, tot = eng.digest_stats(dig_h, 16)
+    o_avg, o_sd, o_tot = O.digest_byte_stats(dig_h, 16)
+    assert np.allclose(avg, o_avg, rtol=0, atol=0) and np.allclose(sd, o_sd, rtol=1e-12) and abs(tot - o_tot) <= 1e-12 * o_tot
+    # unaligned base, odd width (byte path of the kernel)
+    odd = dig[3: 3 + (n - 1) * D]
+    hist2 = torch.zeros(7 * 256, dtype=torch.int64, device=dev)
+    eng.digest_hist_dev(odd.data_ptr(), 7, (n - 1) * D // 7, hist2.data_ptr())
+    eng.sync()
+    o = odd.cpu().numpy()[: ((n - 1) * D // 7) * 7].reshape(-1, 7)
+    want2 = np.stack([np.bincount(o[:, b], minlength=256) for b in range(7)]).reshape(-1)
+    assert (hist2.cpu().numpy() == want2).all()
+
+
+def test_digest_stats_value_255_quirk(eng):
+    """the reference's map has no key 255 until one is seen (hash.cpp:38,55): both branches, tiny inputs"""
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 255, size=(300, 16), dtype=np.uint8)  # never 255
+    b = a.copy()
+    b[::7, 3] = 255
+    for d in (a, b, a[:1], np.zeros((0, 16), np.uint8)):
+        avg, sd, tot = eng.digest_stats(d, 16)
+        o_avg, o_sd, o_tot = O.digest_byte_stats(d, 16)
+        assert (avg == o_avg).all() and np.allclose(sd, o_sd, rtol=1e-12, atol=0) and abs(tot - o_tot) <= 1e-12 * max(o_tot, 1)
+
+
+@pytest.mark.parametrize("halg", [O.HASH_SKEIN256_128, O.HASH_SKEIN512])
+def test_dedup_map(eng, halg):
+    """first[i] = first chunk with the same digest; duplicates planted by repeating chunks"""
+    torch = pytest.importorskip("torch")
+    chunk, n = 4096, 30000
+    D = cw.digest_bytes(halg)
+    dev = torch.device("cuda:0")
+    base = torch.empty(n * chunk, dtype=torch.uint8, device=dev)
+    eng.synth_dev(base.data_ptr(), chunk, 77, n)
+    rng = np.random.default_rng(11)
+    pick = np.arange(n)
+    dup = rng.random(n) < 0.4
+    pick[dup] = rng.integers(0, 500, size=int(dup.sum()))  # 40 % of the chunks repeat one of 500 chunks
+    src = base.view(n, chunk)[torch.from_numpy(pick).to(dev)].contiguous()
+    dig = torch.empty(n * D, dtype=torch.uint8, device=dev)
+    eng.hash_dev(halg, src.data_ptr(), chunk, n, dig.data_ptr())
+    first = torch.full((n,), -1, dtype=torch.int32, device=dev)
+    uniq = torch.zeros(1, dtype=torch.int64, device=dev)
+    eng.dedup_dev(dig.data_ptr(), D, n, first.data_ptr(), uniq.data_ptr())
+    eng.sync()
+    want, want_u = O.dedup_first(dig.cpu().numpy().reshape(n, D))
+    assert (first.cpu().numpy().astype(np.uint32) == want).all()
+    assert int(uniq.item()) == want_u and want_u < n
+    # structured "digests" (all equal / two values) still resolve
+    z = torch.zeros(1000 * 16, dtype=torch.uint8, device=dev)
+    z[16 * 500:] = 9
+    f2 = torch.empty(1000, dtype=torch.int32, device=dev)
+    eng.dedup_dev(z.data_ptr(), 16, 1000, f2.data_ptr(), uniq.data_ptr())
+    eng.sync()
+    f2h = f2.cpu().numpy()
+    assert (f2h[:500] == 0).all() and (f2h[500:] == 500).all() and int(uniq.item()) == 2
+
+
 def test_decompress_rejects_malformed_blocks(eng):
     rng = np.random.default_rng(3)
     chunk, n = 4096, 64

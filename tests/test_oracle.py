@@ -151,3 +151,32 @@ def test_oracle_vs_reference_artifacts_full_corpus(golden):
             assert hashlib.sha256(dig.tobytes()).hexdigest()[:32] == tot[name + "_sha256"]
         assert sk.skein512(d[:8192].tobytes()) == O.skein(512, 512, d[:8192].tobytes())
         assert sk.skein256(d[:4096].tobytes()) == O.skein(256, 128, d[:4096].tobytes())
+
+
+def test_digest_statistic_restatement():
+    """cwo_digest_byte_stats follows hashing_randomness/hash.cpp:30-101, including its map that lacks the key 255
+    until one is seen: checked against the same formula written with a dict, as the reference does it"""
+    import math
+    rng = np.random.default_rng(5)
+    for with255 in (False, True):
+        d = rng.integers(0, 255, size=(777, 16), dtype=np.uint8)
+        if with255:
+            d[::5, 2] = 255
+        avg, sd, tot = O.digest_byte_stats(d, 16)
+        acc = 0.0
+        for b in range(16):
+            m = {v: 0 for v in range(255)}
+            for v in d[:, b]:
+                m[int(v)] = m.get(int(v), 0) + 1
+            total = sum(m.values())
+            a = total / 255
+            s2 = math.sqrt(sum((c - a) ** 2 for _, c in sorted(m.items())) / 254)
+            assert avg[b] == a and math.isclose(sd[b], s2, rel_tol=1e-13)
+            acc += s2
+        assert math.isclose(tot, acc / 16, rel_tol=1e-13)
+
+
+def test_dedup_definition():
+    d = np.array([[1, 2], [3, 4], [1, 2], [0, 0], [3, 4], [1, 2]], dtype=np.uint8)
+    first, uniq = O.dedup_first(d)
+    assert first.tolist() == [0, 1, 0, 3, 1, 0] and uniq == 3

@@ -106,11 +106,10 @@ __device__ __forceinline__ void cw_lz4_emitter_role(unsigned e, unsigned emitter
     }
 }
 
-// LZF role: one warp does the whole chunk (lzf_warp.cuh); slot = [chunk | 16 B pad | CwLzfScratch]
+// LZF parser role; slot = [chunk | 16 B pad | CwLzfScratch], one queue per parser as for LZ4
 template <bool ALIGNED>
-__device__ __forceinline__ void cw_lzf_role(uint8_t *s, uint64_t *bar, const uint8_t *__restrict__ src, uint32_t chunk,
-                                            uint64_t n_chunks, uint8_t *__restrict__ dst, uint64_t stride,
-                                            uint32_t *__restrict__ lens, unsigned long long *work)
+__device__ __forceinline__ void cw_lzf_parser_role(uint8_t *s, CwLz4Queue *q, uint64_t *bar, const uint8_t *__restrict__ src,
+                                                   uint32_t chunk, uint64_t n_chunks, unsigned long long *work)
 {
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t chunk_pad = (chunk + 16u + 15u) & ~15u;
@@ -118,14 +117,58 @@ __device__ __forceinline__ void cw_lzf_role(uint8_t *s, uint64_t *bar, const uin
     if (lane == 0) cw_mbar_init(bar, 1);
     for (uint32_t i = chunk + lane; i < chunk_pad; i += 32u) s[i] = 0;
     __syncwarp();
-    uint32_t phase = 0;
+    uint32_t phase = 0, qh = 0;
     for (;;) {
         unsigned long long g = 0;
         if (lane == 0) g = atomicAdd(work, 1ull);
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= n_chunks) break;
-        cw_stage_chunk(s, src + g * chunk, chunk, ALIGNED, bar, phase);
-        const uint32_t len = cw_lzf_compress_warp(s, chunk, scr, dst + g * stride, chunk - 1u);
-        if (lane == 0) lens[g] = len;
+        cw_lz4_q_drain(q, qh, lane);  // the emitter still reads literals of the previous chunk from this slot
+        if (lane == 0) {
+            q->chunk_lo = (uint32_t)g;
+            q->chunk_hi = (uint32_t)(g >> 32);
+        }
+        const bool tagged = chunk <= CW_LZF_BUCKETS;
+        if (ALIGNED && lane == 0) cw_bulk_load(s, src + g * chunk, chunk, bar);
+        if (tagged) cw_lzf_table_init<true>(scr);
+        else cw_lzf_table_init<false>(scr);
+        if (ALIGNED) {
+            cw_mbar_wait(bar, phase);
+            phase ^= 1u;
+        } else {
+            const uint8_t *gp = src + g * chunk;
+            for (uint32_t i = lane; i < chunk; i += 32u) s[i] = gp[i];
+        }
+        __syncwarp();
+        if (tagged) cw_lzf_parse_warp<true>(s, chunk, scr, q, qh);
+        else cw_lzf_parse_warp<false>(s, chunk, scr, q, qh);
+    }
+    cw_lz4_q_drain(q, qh, lane);
+    if (lane == 0) {
+        cw_fence_cta();
+        cw_st_vol(&q->done, 1u);
+    }
+}
+
+// LZF emitter role: same protocol as cw_lz4_emitter_role
+__device__ __forceinline__ void cw_lzf_emitter_role(unsigned e, unsigned emitters, unsigned parsers, uint8_t *smem,
+                                                    uint32_t slot_bytes, CwLz4Queue *queues, uint32_t chunk,
+                                                    uint8_t *__restrict__ dst, uint64_t stride, uint32_t *__restrict__ lens)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    for (;;) {
+        bool all_done = true;
+        uint32_t did = 0;
+        for (unsigned p = e; p < parsers; p += emitters) {
+            CwLz4Queue *q = &queues[p];
+            uint32_t d = 0;
+            if (lane == 0) d = cw_ld_vol(&q->done);  // read BEFORE the head: done is set after the last publish
+            d = __shfl_sync(0xffffffffu, d, 0);
+            const uint32_t cnt = cw_lzf_emit_batch(q, smem + (size_t)p * slot_bytes, chunk, chunk - 1u, dst, stride, lens);
+            did += cnt;
+            if (!(d && cnt == 0u)) all_done = false;
+        }
+        if (all_done) break;
+        if (!did) cw_spin();
     }
 }

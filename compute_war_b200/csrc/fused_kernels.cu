@@ -2,9 +2,9 @@
 // in ONE pass over the input.
 //
 // One persistent CTA per SM, warp-specialised:
-//   * compress warps (as many as the SM's shared memory holds: 9 for LZ4 / 5 for LZF at 8 KB chunks) each
+//   * parser warps (as many as the SM's shared memory holds: 9 for LZ4 / 5 for LZF at 8 KB chunks) each
 //     own a shared-memory slot, pull chunk indices from a global counter, stage the chunk with a bulk
-//     async copy and run the warp compressor of lz4_warp.cuh / lzf_warp.cuh;
+//     async copy and run the parser of lz4_warp.cuh / lzf_warp.cuh; 2-3 emitter warps write the streams;
 //   * hash warps (1 per CTA by default, no shared memory) take groups of 32 consecutive chunks, one chunk per lane,
 //     and run the register-resident Skein / SHA-256 chain of skein.cuh / sha256.cuh straight from global
 //     memory.
@@ -46,7 +46,7 @@ static int fused_hash_warps(bool fast)
 
 enum { CW_C_LZ4 = 0, CW_C_LZF = 1, CW_C_LZ4_FAST = 2 };  // LZ4 with the reference's 13-bit table / LZF / LZ4 with a 12-bit table
 
-#define CW_FUSED_EMITTERS_DEFAULT 3  // emitter warps per CTA (LZ4 only)
+#define CW_FUSED_EMITTERS_DEFAULT 3  // emitter warps per CTA
 static int fused_emitters(bool fast)
 {
     static int v = -1;
@@ -61,11 +61,12 @@ static int fused_emitters(bool fast)
 template <int CALG>
 __host__ __device__ constexpr uint32_t cw_slot_bytes(uint32_t chunk)
 {
-    return CALG == CW_C_LZF ? ((chunk + 16u + 15u) & ~15u) + (uint32_t)sizeof(CwLzfScratch)
-                            : cw_lz4_chunk_pad(chunk) + (2u << (CALG == CW_C_LZ4 ? 13 : 12)) + (uint32_t)sizeof(CwLz4Queue);
+    return (CALG == CW_C_LZF ? ((chunk + 16u + 15u) & ~15u) + (uint32_t)sizeof(CwLzfScratch)
+                             : cw_lz4_chunk_pad(chunk) + (2u << (CALG == CW_C_LZ4 ? 13 : 12))) +
+           (uint32_t)sizeof(CwLz4Queue);
 }
 
-// warps [0, parsers): compress; [parsers, parsers + emitters): LZ4 emitters; the rest: hash
+// warps [0, parsers): parsers; [parsers, parsers + emitters): emitters; the rest: hash
 template <int HALG, int CALG, bool ALIGNED>
 __global__ void __launch_bounds__(CW_FUSED_MAX_THREADS, 1)
     cw_fused_kernel(const __grid_constant__ CwSkeinIV iv, const uint8_t *__restrict__ src, uint32_t chunk, uint64_t n_chunks,
@@ -75,23 +76,28 @@ __global__ void __launch_bounds__(CW_FUSED_MAX_THREADS, 1)
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bars[32];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    if (CALG != CW_C_LZF) {
-        // slot_bytes here excludes the queue: queues sit behind the slots
+    {
+        // slot_bytes excludes the queue: queues sit behind the slots
         CwLz4Queue *queues = reinterpret_cast<CwLz4Queue *>(smem + (size_t)parsers * slot_bytes);
         if (warp < parsers && lane < 8u) reinterpret_cast<uint32_t *>(&queues[warp])[lane] = 0u;
         __syncthreads();
         if (warp < parsers) {
-            cw_lz4_parser_role<(CALG == CW_C_LZ4 ? 13 : 12), ALIGNED, false>(smem + (size_t)warp * slot_bytes, &queues[warp],
-                                                                             &bars[warp], src, chunk, n_chunks, &work[0]);
+            if (CALG == CW_C_LZF)
+                cw_lzf_parser_role<ALIGNED>(smem + (size_t)warp * slot_bytes, &queues[warp], &bars[warp], src, chunk, n_chunks,
+                                            &work[0]);
+            else
+                cw_lz4_parser_role<(CALG == CW_C_LZ4 ? 13 : 12), ALIGNED, false>(smem + (size_t)warp * slot_bytes, &queues[warp],
+                                                                                 &bars[warp], src, chunk, n_chunks, &work[0]);
             return;
         }
         if (warp < parsers + emitters) {
-            cw_lz4_emitter_role<false>(warp - parsers, emitters, parsers, smem, slot_bytes, queues, src, chunk, dst, stride, lens);
+            if (CALG == CW_C_LZF)
+                cw_lzf_emitter_role(warp - parsers, emitters, parsers, smem, slot_bytes, queues, chunk, dst, stride, lens);
+            else
+                cw_lz4_emitter_role<false>(warp - parsers, emitters, parsers, smem, slot_bytes, queues, src, chunk, dst, stride,
+                                           lens);
             return;
         }
-    } else if (warp < parsers) {
-        cw_lzf_role<ALIGNED>(smem + (size_t)warp * slot_bytes, &bars[warp], src, chunk, n_chunks, dst, stride, lens, &work[0]);
-        return;
     }
     // ------------------------------ hash role ------------------------------
     constexpr int D = cw_digest_len<HALG>();
@@ -118,12 +124,12 @@ static cudaError_t launch_one(const CwDeviceInfo &dev, int max_dyn_smem, const C
                               uint32_t *d_lens, unsigned long long *work, cudaStream_t st)
 {
     auto kern = cw_fused_kernel<HALG, CALG, ALIGNED>;
-    const uint32_t per = cw_slot_bytes<CALG>(chunk);  // slot (+ queue for LZ4)
-    const uint32_t slot = CALG == CW_C_LZF ? per : per - (uint32_t)sizeof(CwLz4Queue);
+    const uint32_t per = cw_slot_bytes<CALG>(chunk);  // slot + queue
+    const uint32_t slot = per - (uint32_t)sizeof(CwLz4Queue);
     int parsers = max_dyn_smem / (int)per;
     if (parsers < 1) return cudaErrorInvalidValue;
     if (parsers > CW_FUSED_MAX_COMP_WARPS) parsers = CW_FUSED_MAX_COMP_WARPS;
-    int emitters = CALG == CW_C_LZF ? 0 : fused_emitters(CALG == CW_C_LZ4_FAST);
+    int emitters = fused_emitters(CALG == CW_C_LZ4_FAST);
     if (emitters > parsers) emitters = parsers;
     uint64_t ctas = (n + (uint64_t)parsers - 1) / (uint64_t)parsers;
     if (ctas > (uint64_t)dev.sm_count) ctas = (uint64_t)dev.sm_count;

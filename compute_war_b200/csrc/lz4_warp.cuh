@@ -17,8 +17,8 @@
 // of the parser at once ("window"):
 //   phase A (all lanes, independent): read32, hash, table look-up, candidate compare; lanes that share a
 //            table slot inside the window ("twins") are detected by writing a lane tag into the slot and
-//            reading it back -- MATCH.ANY, which costs several hundred cycles on sm_100, is only issued
-//            for windows that really contain twins.
+//            reading it back; the groups are then resolved with two ballots per group of equal values
+//            (MATCH.ANY costs several hundred cycles on sm_100 and is kept for windows with many groups).
 //   phase B (uniform, registers only): replay the parser's control flow over the window.  `ins` is the
 //            set of window lanes whose position the sequential parser has inserted so far; a lane's true
 //            candidate is the highest inserted twin below it, else the table entry read in phase A.  The
@@ -348,8 +348,23 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
             const uint32_t vmask = inv_all ? (1u << (cw_ffs(inv_all) - 1)) - 1u : 0xffffffffu;
             uint32_t E = own, dyn_all = 0;
             if (twins) {
-                M = cw_match_any(valid ? h : 0x10000u + lane);
-                E = cw_match_any(v);
+                // every slot shared by several lanes has at least one lane that lost the tag race: walk those, one
+                // group of equal 4-byte values per step (two ballots; MATCH.ANY costs ~365 cycles on sm_100)
+                uint32_t rem = twins;
+                if (cw_popc(twins) > 6) {  // many groups: the fixed cost of two MATCH.ANY is lower
+                    M = cw_match_any(valid ? h : 0x10000u + lane);
+                    E = cw_match_any(v);
+                    rem = 0;
+                }
+                while (rem) {
+                    const unsigned L = (unsigned)cw_ffs(rem) - 1u;
+                    const uint32_t hL = cw_shfl(h, L), vL = cw_shfl(v, L);
+                    const bool sh = valid && h == hL, sv = valid && v == vL;
+                    const uint32_t mh = cw_ballot(sh), mv = cw_ballot(sv);
+                    if (sh) M = mh;
+                    if (sv) E = mv;
+                    rem &= ~mv;
+                }
                 dyn_all = cw_ballot(valid && (M & lower) != 0u);  // lanes that may have an in-window candidate
             }
             // ---------------- phase B ----------------

@@ -95,20 +95,65 @@ extern "C" uint32_t emu_lz4_compress_direct(const uint8_t *src, uint32_t n, uint
 extern "C" uint32_t emu_lz4_compress(const uint8_t *src, uint32_t n, uint8_t *out) { return emu_lz4_compress_hl(src, n, out, 13); }
 
 #ifdef HAVE_LZF
-static void lzf_body(void *a)
+// LZF: a two-warp CTA -- warp 0 parses, warp 1 emits (csrc/lzf_warp.cuh)
+struct LzfJob {
+    const uint8_t *s;
+    uint32_t n;
+    CwLzfScratch *scr;
+    CwLz4Queue *q;
+    uint8_t *out;
+    uint32_t out_cap;
+    uint32_t lens[1];
+    int tagged;
+};
+static void lzf_block_body(void *a, int warp)
 {
-    Job *j = (Job *)a;
-    uint32_t r = cw_lzf_compress_warp(j->s, j->n, (CwLzfScratch *)j->aux, j->out, j->out_cap);
-    if (cw_lane() == 0) j->result = r;
+    LzfJob *j = (LzfJob *)a;
+    const unsigned lane = cw_lane();
+    if (warp == 0) {
+        uint32_t qh = 0;
+        if (j->tagged) {
+            cw_lzf_table_init<true>(j->scr);
+            cw_syncwarp();
+            cw_lzf_parse_warp<true>(j->s, j->n, j->scr, j->q, qh);
+        } else {
+            cw_lzf_table_init<false>(j->scr);
+            cw_syncwarp();
+            cw_lzf_parse_warp<false>(j->s, j->n, j->scr, j->q, qh);
+        }
+        cw_lz4_q_drain(j->q, qh, lane);
+        if (lane == 0) {
+            cw_fence_cta();
+            cw_st_vol(&j->q->done, 1u);
+        }
+    } else {
+        for (;;) {
+            uint32_t d = 0;
+            if (lane == 0) d = cw_ld_vol(&j->q->done);
+            d = cw_shfl(d, 0);
+            const uint32_t cnt = cw_lzf_emit_batch(j->q, j->s, j->n, j->out_cap, j->out, 0, j->lens);
+            if (d && cnt == 0) break;
+            if (!cnt) cw_spin();
+        }
+    }
+}
+// tagged: 1 = the <= 8192-byte table format, 0 = the general one, -1 = what the kernels pick
+extern "C" uint32_t emu_lzf_compress_mode(const uint8_t *src, uint32_t n, uint8_t *out, uint32_t out_cap, int tagged)
+{
+    if (n == 0) return 0;
+    std::vector<uint32_t> staged((n + CW_LZ4_PAD + 3) / 4 + 4, 0);
+    memcpy(staged.data(), src, n);
+    std::vector<uint8_t> scratch(sizeof(CwLzfScratch), 0xA5);  // contents irrelevant on entry
+    CwLz4Queue q;
+    memset(&q, 0, sizeof q);
+    if (tagged < 0) tagged = n <= CW_LZF_BUCKETS;
+    LzfJob j{(const uint8_t *)staged.data(), n, (CwLzfScratch *)scratch.data(), &q, out, out_cap, {0}, tagged};
+    cwemu::run_block(2, lzf_block_body, &j);
+    return j.lens[0];
 }
 extern "C" uint32_t emu_lzf_compress(const uint8_t *src, uint32_t n, uint8_t *out, uint32_t out_cap)
 {
-    std::vector<uint32_t> staged((n + CW_LZ4_PAD + 3) / 4 + 4, 0);
-    memcpy(staged.data(), src, n);
-    std::vector<uint8_t> scratch(sizeof(CwLzfScratch), 0);
-    Job j{(const uint8_t *)staged.data(), n, nullptr, scratch.data(), out, out_cap, 0, 0};
-    cwemu::run_warp(lzf_body, &j);
-    return j.result;
+    return emu_lzf_compress_mode(src, n, out, out_cap, -1);
 }
 #endif
 

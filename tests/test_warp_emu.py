@@ -37,6 +37,7 @@ def emu():
     L.emu_lz4_compress.restype = C.c_uint32
     if hasattr(L, "emu_lzf_compress"):
         L.emu_lzf_compress.restype = C.c_uint32
+        L.emu_lzf_compress_mode.restype = C.c_uint32
     return L
 
 
@@ -74,6 +75,8 @@ def _cases(golden, small):
     for i in range(12):
         cases.append(O.synth(8192, i, 1))
     cases += [O.synth(65536, 1, 1), rng.integers(0, 256, 65536, dtype=np.uint8), np.zeros(65536, np.uint8)]
+    big = [e for e in golden["ref"]["files"] if e["size"] >= 65536][:3]  # 64 KB of real text: matches that run to the end
+    cases += [blob[e["offset"]: e["offset"] + 65536].copy() for e in big]
     if small:
         cases += [np.zeros(n, np.uint8) for n in (1, 2, 5, 12)]
     return cases
@@ -119,13 +122,16 @@ def test_lz4_direct_mode_and_fast_table(emu, golden):
 def test_lzf_warp_algorithm_byte_identical(emu, golden):
     if not hasattr(emu, "emu_lzf_compress"):
         pytest.skip("LZF warp kernel not built yet")
-    for c in _cases(golden, small=False):
+    for c in _cases(golden, small=True):
         n = len(c)
         out = np.zeros(n + 64, np.uint8)
-        r = emu.emu_lzf_compress(c.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p), n - 1)
         blocks, lens = O.compress_chunks(O.COMP_LZF, c, n)
-        assert r == lens[0], (n, r, lens[0])
-        assert (out[:r] == blocks[0, :r]).all(), n
+        # both table formats: tagged entries (chunks <= 8192 bytes) and the general one
+        for tagged in ([1, 0] if n <= 8192 else [0]):
+            out[:] = 0
+            r = emu.emu_lzf_compress_mode(c.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p), n - 1, tagged)
+            assert r == lens[0], (n, tagged, r, lens[0])
+            assert (out[:r] == blocks[0, :r]).all(), (n, tagged)
 
 
 def test_warp_decoders_restore_reference_streams(emu, golden):

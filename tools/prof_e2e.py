@@ -22,7 +22,7 @@ step(); step()
 t0 = time.perf_counter()
 for _ in range(5): step()
 dt = (time.perf_counter() - t0) / 5
-print(f"slice_mb={os.environ.get('CW_SLICE_MB','32')} slots={os.environ.get('CW_SLOTS','3')} mode={mode}: {dt*1e3:.1f} ms/pass = {n*chunk/dt/1e9:.1f} GB/s e2e")
+print(f"slice_mb={os.environ.get("CW_SLICE_MB","64")} slots={os.environ.get("CW_SLOTS","4")} mode={mode}: {dt*1e3:.1f} ms/pass = {n*chunk/dt/1e9:.1f} GB/s e2e")
 # plain copies for reference
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); src.copy_(h_src, non_blocking=True); e1.record(); torch.cuda.synchronize()

@@ -153,6 +153,35 @@ class ClockSampler:
 # our arm
 # ------------------------------------------------------------------------------------------------
 
+def _parse_cpulist(text: str):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(props):
+    """Multi-GPU runs: keep this rank's threads (and so, by first touch, its pinned host buffers) on the NUMA node its
+    GPU hangs off, so that the host<->device copies of the end-to-end leg do not cross the socket interconnect.
+    CW_BENCH_NUMA=0 turns it off.  Returns what was done, for the JSON line."""
+    if os.environ.get("CW_BENCH_NUMA", "1") == "0":
+        return {"bound": False, "why": "CW_BENCH_NUMA=0"}
+    try:
+        dev = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        base = "/sys/bus/pci/devices/" + dev
+        node = int(open(base + "/numa_node").read())
+        cpus = _parse_cpulist(open(base + "/local_cpulist").read()) & os.sched_getaffinity(0)
+        if node < 0 or not cpus:
+            return {"bound": False, "why": "no NUMA information for " + dev}
+        os.sched_setaffinity(0, cpus)
+        return {"bound": True, "node": node, "cpus": len(cpus)}
+    except Exception as e:  # sysfs not readable in this container: run unbound
+        return {"bound": False, "why": type(e).__name__}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -182,6 +211,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(torch.cuda.get_device_properties(local)) if world > 1 else None
     dist = None
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner out of stdout: one JSON line only
@@ -393,7 +423,7 @@ def main():
                        "l2": "inputs larger than L2 (2 GiB per pass vs 126 MB)", "compression_ratio": ratio_all,
                        "parity": "first/last 128 chunks of every shard bit-exact vs oracle before timing; "
                                  "all blocks of the shard decoded back on the device == input",
-                       "roundtrip_all_blocks": roundtrip_compat},
+                       "roundtrip_all_blocks": roundtrip_compat, "host_numa_binding_rank0": numa},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "fast_mode": fast,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,

@@ -11,8 +11,11 @@
 //   * --hash-alg also accepts skein512 and sha256 (= what sha256mb intended, :136-158);
 //   * the whole batch is one cw_hash_compress call (or --c-threads concurrent cw_submit batches when
 //     --gpu-offload 1), instead of one call per 4 KB block;
-//   * --verify checks nothing on the CPU: it re-runs the batch and compares the two GPU results (the
-//     oracle lives in tests/, not in the product).
+//   * --devices N shards the chunks over N GPUs by contiguous range (one context + host thread per GPU);
+//   * --randomness appends the per-byte digest distribution lines of the reference's hashing_randomness tool
+//     (src/hashing_randomness/hash.cpp:74-101);
+//   * --dump PREFIX writes PREFIX.digests / PREFIX.lens (u32 LE) / PREFIX.blocks (blocks back to back) so a
+//     run can be compared with another one byte for byte (the tests do; the oracle lives in tests/, not here).
 #include <getopt.h>
 
 #include <chrono>
@@ -22,6 +25,7 @@
 #include <fstream>
 #include <iostream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/compute_war.h"
@@ -39,8 +43,11 @@ static void usage(const char *argv0, const char *msg = nullptr)
             "  -H, --hash-alg A      skein (= skein256-128) | skein512 | sha256mb | sha256 (default skein)\n"
             "  -k, --chunk BYTES     chunk size (default 4096)\n"
             "  -m, --mode M          compat | fast (default compat)\n"
-            "  -d, --device N        CUDA device (default 0)\n"
+            "  -d, --device N        first CUDA device (default 0)\n"
+            "  -D, --devices N       shard the chunks over N GPUs starting at --device: contiguous chunk ranges, one\n"
+            "                        context and host thread per GPU, no exchange between them (default 1)\n"
             "  -i, --iters N         repeat the timed pass N times (default 1)\n"
+            "  -o, --dump PREFIX     write PREFIX.digests, PREFIX.lens, PREFIX.blocks\n"
             "  -R, --randomness      also print the digest byte distribution lines of the reference's hashing_randomness\n"
             "                        tool (byte|alg|avg|stddev|, then \"Average std dev\") for the first 16 digest bytes\n",
             argv0);
@@ -49,7 +56,8 @@ static void usage(const char *argv0, const char *msg = nullptr)
 
 int main(int argc, char **argv)
 {
-    int threads = 8, offload = 0, device = 0, iters = 1, randomness = 0;
+    int threads = 8, offload = 0, device = 0, iters = 1, randomness = 0, devices = 1;
+    std::string dump;
     size_t chunk = 4096;
     std::string comp = "lz4", hash = "skein", mode = "compat";
     static const option opts[] = {{"help", no_argument, 0, 'h'},          {"c-threads", required_argument, 0, 'c'},
@@ -57,10 +65,11 @@ int main(int argc, char **argv)
                                   {"hash-blocks", required_argument, 0, 'G'}, {"comp-alg", required_argument, 0, 'C'},
                                   {"hash-alg", required_argument, 0, 'H'},    {"chunk", required_argument, 0, 'k'},
                                   {"mode", required_argument, 0, 'm'},        {"device", required_argument, 0, 'd'},
-                                  {"iters", required_argument, 0, 'i'},       {"randomness", no_argument, 0, 'R'},
+                                  {"iters", required_argument, 0, 'i'},       {"randomness", no_argument, 0, 'R'},       {"devices", required_argument, 0, 'D'},
+                                  {"dump", required_argument, 0, 'o'},
                                   {0, 0, 0, 0}};
     int o;
-    while ((o = getopt_long(argc, argv, "hc:g:r:G:C:H:k:m:d:i:R", opts, nullptr)) != -1) {
+    while ((o = getopt_long(argc, argv, "hc:g:r:G:C:H:k:m:d:i:RD:o:", opts, nullptr)) != -1) {
         switch (o) {
         case 'h': usage(argv[0]); break;
         case 'c': threads = atoi(optarg); break;
@@ -74,6 +83,8 @@ int main(int argc, char **argv)
         case 'd': device = atoi(optarg); break;
         case 'i': iters = atoi(optarg); break;
         case 'R': randomness = 1; break;
+        case 'D': devices = atoi(optarg); break;
+        case 'o': dump = optarg; break;
         default: usage(argv[0], "bad option");
         }
     }
@@ -108,32 +119,59 @@ int main(int argc, char **argv)
         return 1;
     }
 
-    cw_ctx *ctx = nullptr;
-    int rc = cw_init(&ctx, device);
-    if (rc != CW_OK) {
-        fprintf(stderr, "cw_init: %s\n", cw_status_string(rc));
-        return 1;
+    // one context per GPU; GPU g of G owns chunks [g*n/G, (g+1)*n/G) -- the reference shards its blocks over worker
+    // threads through a queue (HashAndCompress.cpp:263-272), here the ranges are fixed and the outputs land in place
+    if (devices < 1) devices = 1;
+    if ((size_t)devices > n) devices = (int)n;
+    std::vector<cw_ctx *> ctxs(devices, nullptr);
+    int rc = CW_OK;
+    for (int g = 0; g < devices; g++) {
+        rc = cw_init(&ctxs[g], device + g);
+        if (rc != CW_OK) {
+            fprintf(stderr, "cw_init(device %d): %s %s\n", device + g, cw_status_string(rc), cw_last_error(nullptr));
+            return 1;
+        }
     }
+    cw_ctx *ctx = ctxs[0];
     const size_t D = cw_digest_bytes(halg), stride = cw_compress_bound(calg, chunk);
     std::vector<uint8_t> digests(n * D), blocks(n * stride);
     std::vector<uint32_t> lens(n);
 
-    auto pass = [&]() -> int {
-        if (!offload) return cw_hash_compress(ctx, halg, calg, cmode, data.data(), chunk, n, digests.data(), blocks.data(), stride, lens.data());
+    auto pass_range = [&](cw_ctx *c, size_t first, size_t cnt) -> int {
+        const uint8_t *src = data.data() + first * chunk;
+        uint8_t *dg = digests.data() + first * D, *bl = blocks.data() + first * stride;
+        uint32_t *ln = lens.data() + first;
+        if (!offload) return cw_hash_compress(c, halg, calg, cmode, src, chunk, cnt, dg, bl, stride, ln);
         // HashOffload-style: `threads` batches in flight (Reset/Enqueue/Start ... Complete)
         std::vector<cw_ticket> tk(threads);
         int bad = CW_OK;
         for (int t = 0; t < threads; t++) {
-            size_t lo = n * t / threads, hi = n * (t + 1) / threads;
-            int r = cw_submit(ctx, halg, calg, cmode, data.data() + lo * chunk, chunk, hi - lo, digests.data() + lo * D,
-                              blocks.data() + lo * stride, stride, lens.data() + lo, nullptr, nullptr, &tk[t]);
+            size_t lo = cnt * t / threads, hi = cnt * (t + 1) / threads;
+            int r = cw_submit(c, halg, calg, cmode, src + lo * chunk, chunk, hi - lo, dg + lo * D, bl + lo * stride, stride,
+                              ln + lo, nullptr, nullptr, &tk[t]);
             if (r != CW_OK) bad = r;
         }
         for (int t = 0; t < threads; t++) {
-            int r = cw_wait(ctx, tk[t]);
+            int r = cw_wait(c, tk[t]);
             if (r != CW_OK) bad = r;
         }
         return bad;
+    };
+    auto pass = [&]() -> int {
+        if (devices == 1) return pass_range(ctx, 0, n);
+        std::vector<int> rcs(devices, CW_OK);
+        std::vector<std::thread> th;
+        for (int g = 0; g < devices; g++) {
+            const size_t lo = n * g / devices, hi = n * (g + 1) / devices;
+            th.emplace_back([&, g, lo, hi] { rcs[g] = pass_range(ctxs[g], lo, hi - lo); });
+        }
+        for (auto &t : th) t.join();
+        for (int g = 0; g < devices; g++)
+            if (rcs[g] != CW_OK) {
+                ctx = ctxs[g];  // report this context's error text
+                return rcs[g];
+            }
+        return CW_OK;
     };
 
     rc = pass();  // warm-up: context, module load, pipeline buffers
@@ -155,7 +193,14 @@ int main(int argc, char **argv)
     // the reference's line (HashAndCompress.cpp:409-412) ...
     printf("%s|%s|%llu|%llu\n", hash.c_str(), comp.c_str(), (unsigned long long)(ms + 0.5), (unsigned long long)mbps);
     // ... plus what it throws away
-    fprintf(stderr, "chunks=%zu chunk=%zu ms=%.3f MBps=%.1f ratio=%.4f\n", n, chunk, ms, mbps, (double)csum / (double)(n * chunk));
+    fprintf(stderr, "chunks=%zu chunk=%zu gpus=%d ms=%.3f MBps=%.1f ratio=%.4f\n", n, chunk, devices, ms, mbps, (double)csum / (double)(n * chunk));
+    if (!dump.empty()) {
+        std::ofstream(dump + ".digests", std::ios::binary).write((const char *)digests.data(), (std::streamsize)digests.size());
+        std::ofstream(dump + ".lens", std::ios::binary).write((const char *)lens.data(), (std::streamsize)(n * sizeof(uint32_t)));
+        std::ofstream bo(dump + ".blocks", std::ios::binary);
+        for (size_t i = 0; i < n; i++)
+            bo.write((const char *)(lens[i] ? blocks.data() + i * stride : data.data() + i * chunk), lens[i] ? lens[i] : chunk);
+    }
     if (randomness) {
         // Hasher::LogResultsInternal / LogByteResults, src/hashing_randomness/hash.cpp:30-101
         const size_t nb = 16;
@@ -168,6 +213,6 @@ int main(int argc, char **argv)
         for (size_t b = 0; b < nb; b++) std::cout << b << "|" << hash << "|" << avg[b] << "|" << sd[b] << "|" << std::endl;
         std::cout << "Average std dev: " << tot << std::endl;
     }
-    cw_shutdown(ctx);
+    for (cw_ctx *c : ctxs) cw_shutdown(c);
     return 0;
 }

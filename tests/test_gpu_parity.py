@@ -441,6 +441,47 @@ def test_dedup_map(eng, halg):
     assert (f2h[:500] == 0).all() and (f2h[500:] == 500).all() and int(uniq.item()) == 2
 
 
+def test_host_tool_end_to_end(eng, tmp_path):
+    """the C++ host tool (reference CLI, C ABI underneath): result line, dumped outputs == oracle, randomness lines,
+    --gpu-offload batches, and -- when the box has them -- two GPUs give the same bytes as one"""
+    import os
+    import re
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "compute_war_b200", "hashandcompress")
+    if not os.path.exists(exe):
+        pytest.skip("host tool not built")
+    chunk, n = 4096, 3000
+    d = O.synth(chunk, 900, n)
+    f = tmp_path / "in.bin"
+    f.write_bytes(d.tobytes() + b"tail that is dropped")
+    want_dig = O.hash_chunks(O.HASH_SKEIN256_128, d, chunk)
+    ob, ol = O.compress_chunks(O.COMP_LZF, d, chunk)
+    want_blocks = b"".join(bytes(ob[i, : ol[i]]) if ol[i] else bytes(d[i * chunk:(i + 1) * chunk]) for i in range(n))
+
+    def run(*extra):
+        pre = str(tmp_path / ("o" + "_".join(extra).replace("-", "")))
+        r = subprocess.run([exe, "-H", "skein", "-C", "lzf", "-k", str(chunk), "--dump", pre, *extra, str(f)],
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        assert re.match(r"^skein\|lzf\|\d+\|\d+$", r.stdout.splitlines()[0]), r.stdout
+        assert np.fromfile(pre + ".digests", np.uint8).tobytes() == want_dig.tobytes()
+        assert (np.fromfile(pre + ".lens", np.uint32) == ol).all()
+        assert open(pre + ".blocks", "rb").read() == want_blocks
+        return r.stdout
+
+    out = run("--randomness")
+    lines = out.splitlines()[1:]
+    o_avg, o_sd, o_tot = O.digest_byte_stats(want_dig, 16)
+    for b in range(16):
+        k, alg, avg, sd = lines[b].split("|")[:4]
+        assert int(k) == b and alg == "skein" and abs(float(avg) - o_avg[b]) < 1e-3 * o_avg[b] and abs(float(sd) - o_sd[b]) < 1e-3 * o_sd[b]
+    assert lines[16].startswith("Average std dev: ") and abs(float(lines[16].split(": ")[1]) - o_tot) < 1e-3 * o_tot
+    run("--gpu-offload", "1", "--c-threads", "5")
+    torch = pytest.importorskip("torch")
+    if torch.cuda.device_count() >= 2:
+        run("--devices", "2")
+
+
 def test_decompress_rejects_malformed_blocks(eng):
     rng = np.random.default_rng(3)
     chunk, n = 4096, 64

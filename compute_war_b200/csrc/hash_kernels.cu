@@ -8,7 +8,6 @@ void cw_make_skein_iv(CwSkeinIV *iv)
     // skein.c:226-266 and :31-71)
     cw_skein_iv<8>(iv->iv512, 512);
     cw_skein_iv<4>(iv->iv256, 128);
-    for (int i = 0; i < 32; i++) iv->pw[i] = 1u << i;
 }
 
 template <int ALG>

@@ -15,7 +15,6 @@
 struct CwSkeinIV {
     uint64_t iv512[8];  // Skein-512, 512-bit output
     uint64_t iv256[4];  // Skein-256, 128-bit output
-    uint32_t pw[32];    // pw[r] = 2^r: multipliers of the rotate-by-IMAD.WIDE MIX form (skein.cuh)
 };
 
 enum { CW_K_SKEIN512 = 0, CW_K_SKEIN256_128 = 1, CW_K_SHA256 = 2 };
@@ -31,7 +30,7 @@ __device__ __forceinline__ void cw_hash_one(const CwSkeinIV &iv, const uint8_t *
 {
     if constexpr (ALG == CW_K_SKEIN512) {
         uint64_t X[8];
-        cw_skein_chunk<8, 64, ALIGNED, CW_SKEIN_UNROLL72>(iv.iv512, iv.pw, p, len, X);
+        cw_skein_chunk<8, 64, ALIGNED, CW_SKEIN_UNROLL72>(iv.iv512, p, len, X);
         if (OUT_ALIGNED) {
             uint4 *o = reinterpret_cast<uint4 *>(out);
 #pragma unroll
@@ -44,7 +43,7 @@ __device__ __forceinline__ void cw_hash_one(const CwSkeinIV &iv, const uint8_t *
         }
     } else if constexpr (ALG == CW_K_SKEIN256_128) {
         uint64_t X[4];
-        cw_skein_chunk<4, 16, ALIGNED, true>(iv.iv256, iv.pw, p, len, X);
+        cw_skein_chunk<4, 16, ALIGNED, true>(iv.iv256, p, len, X);
         if (OUT_ALIGNED) {
             *reinterpret_cast<uint4 *>(out) =
                 make_uint4((uint32_t)X[0], (uint32_t)(X[0] >> 32), (uint32_t)X[1], (uint32_t)(X[1] >> 32));

@@ -90,7 +90,7 @@ CW_HOSTDEV uint64_t cw_rotxor_funnel(uint64_t b, uint64_t a, int r)
 // One UBI block: X <- Threefish512(key = X, tweak = (T0, T1), plaintext = w) ^ w.
 // UNROLL72 = true: 72 rounds straight-line; false: 3 trips of 24 rounds.
 template <bool UNROLL72>
-CW_HOSTDEV void cw_tf512_block(uint64_t (&X)[8], const uint64_t (&w)[8], uint64_t T0, uint64_t T1, const uint32_t (&pw)[32])
+CW_HOSTDEV void cw_tf512_block(uint64_t (&X)[8], const uint64_t (&w)[8], uint64_t T0, uint64_t T1)
 {
     uint64_t ks[9], ts[3], x[8];
     ks[8] = CW_SKEIN_PARITY;
@@ -159,7 +159,7 @@ CW_HOSTDEV void cw_tf512_block(uint64_t (&X)[8], const uint64_t (&w)[8], uint64_
     x[2] += ks[((s) + 2) % 5] + ts[((s) + 1) % 3]; \
     x[3] += ks[((s) + 3) % 5] + (uint64_t)(s);
 
-CW_HOSTDEV void cw_tf256_block(uint64_t (&X)[4], const uint64_t (&w)[4], uint64_t T0, uint64_t T1, const uint32_t (&pw)[32])
+CW_HOSTDEV void cw_tf256_block(uint64_t (&X)[4], const uint64_t (&w)[4], uint64_t T0, uint64_t T1)
 {
     uint64_t ks[5], ts[3], x[4];
     ks[4] = CW_SKEIN_PARITY;
@@ -192,8 +192,6 @@ template <int WORDS>
 CW_HOSTDEV void cw_skein_iv(uint64_t (&X)[WORDS], unsigned hash_bits)
 {
     uint64_t w[WORDS];
-    uint32_t pw[32];
-    for (int i = 0; i < 32; i++) pw[i] = 1u << i;
 #pragma unroll
     for (int i = 0; i < WORDS; i++) {
         X[i] = 0;
@@ -202,8 +200,8 @@ CW_HOSTDEV void cw_skein_iv(uint64_t (&X)[WORDS], unsigned hash_bits)
     w[0] = CW_SKEIN_SCHEMA;
     w[1] = hash_bits;
     const uint64_t T1 = CW_SKEIN_T1_FIRST | CW_SKEIN_T1_FINAL | CW_SKEIN_T1_CFG;
-    if constexpr (WORDS == 8) cw_tf512_block<true>(X, w, 32, T1, pw);
-    else cw_tf256_block(X, w, 32, T1, pw);
+    if constexpr (WORDS == 8) cw_tf512_block<true>(X, w, 32, T1);
+    else cw_tf256_block(X, w, 32, T1);
 }
 
 // message word loaders: p is 8-byte aligned on the fast path
@@ -242,7 +240,7 @@ CW_HOSTDEV void cw_skein_load(uint64_t (&w)[WORDS], const uint8_t *p, unsigned a
 // Hash one chunk of `len` bytes.  IV = cw_skein_iv(...) computed once on the host.  out receives
 // OUT_BYTES (<= 8*WORDS) digest bytes, little-endian words (Skein_Put64_LSB_First, skein_port.h:57).
 template <int WORDS, int OUT_BYTES, bool ALIGNED, bool UNROLL72>
-CW_HOSTDEV void cw_skein_chunk(const uint64_t (&IV)[WORDS], const uint32_t (&pw)[32], const uint8_t *p, uint32_t len,
+CW_HOSTDEV void cw_skein_chunk(const uint64_t (&IV)[WORDS], const uint8_t *p, uint32_t len,
                                uint64_t (&X)[WORDS])
 {
     constexpr uint32_t B = WORDS * 8;
@@ -255,17 +253,17 @@ CW_HOSTDEV void cw_skein_chunk(const uint64_t (&IV)[WORDS], const uint32_t (&pw)
     while (len - off > B) {
         cw_skein_load<WORDS, ALIGNED>(w, p + off, B);
         off += B;
-        if constexpr (WORDS == 8) cw_tf512_block<UNROLL72>(X, w, off, T1, pw);
-        else cw_tf256_block(X, w, off, T1, pw);
+        if constexpr (WORDS == 8) cw_tf512_block<UNROLL72>(X, w, off, T1);
+        else cw_tf256_block(X, w, off, T1);
         T1 = CW_SKEIN_T1_MSG;
     }
     // final (zero padded) block, T0 = total length (skein.c:383-387)
     cw_skein_load<WORDS, ALIGNED>(w, p + off, len - off);
-    if constexpr (WORDS == 8) cw_tf512_block<UNROLL72>(X, w, len, T1 | CW_SKEIN_T1_FINAL, pw);
-    else cw_tf256_block(X, w, len, T1 | CW_SKEIN_T1_FINAL, pw);
+    if constexpr (WORDS == 8) cw_tf512_block<UNROLL72>(X, w, len, T1 | CW_SKEIN_T1_FINAL);
+    else cw_tf256_block(X, w, len, T1 | CW_SKEIN_T1_FINAL);
     // output block: counter 0 under the final chaining value (skein.c:393-399)
 #pragma unroll
     for (int i = 0; i < WORDS; i++) w[i] = 0;
-    if constexpr (WORDS == 8) cw_tf512_block<UNROLL72>(X, w, 8, CW_SKEIN_T1_FIRST | CW_SKEIN_T1_FINAL | CW_SKEIN_T1_OUT, pw);
-    else cw_tf256_block(X, w, 8, CW_SKEIN_T1_FIRST | CW_SKEIN_T1_FINAL | CW_SKEIN_T1_OUT, pw);
+    if constexpr (WORDS == 8) cw_tf512_block<UNROLL72>(X, w, 8, CW_SKEIN_T1_FIRST | CW_SKEIN_T1_FINAL | CW_SKEIN_T1_OUT);
+    else cw_tf256_block(X, w, 8, CW_SKEIN_T1_FIRST | CW_SKEIN_T1_FINAL | CW_SKEIN_T1_OUT);
 }

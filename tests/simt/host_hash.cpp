@@ -8,20 +8,16 @@
 extern "C" void host_skein512(const uint8_t *p, uint32_t len, uint8_t *out, int unroll72)
 {
     uint64_t IV[8], X[8];
-    uint32_t pw[32];
-    for (int i = 0; i < 32; i++) pw[i] = 1u << i;
     cw_skein_iv<8>(IV, 512);
-    if (unroll72) cw_skein_chunk<8, 64, false, true>(IV, pw, p, len, X);
-    else cw_skein_chunk<8, 64, false, false>(IV, pw, p, len, X);
+    if (unroll72) cw_skein_chunk<8, 64, false, true>(IV, p, len, X);
+    else cw_skein_chunk<8, 64, false, false>(IV, p, len, X);
     memcpy(out, X, 64);
 }
 extern "C" void host_skein256_128(const uint8_t *p, uint32_t len, uint8_t *out)
 {
     uint64_t IV[4], X[4];
-    uint32_t pw[32];
-    for (int i = 0; i < 32; i++) pw[i] = 1u << i;
     cw_skein_iv<4>(IV, 128);
-    cw_skein_chunk<4, 16, false, true>(IV, pw, p, len, X);
+    cw_skein_chunk<4, 16, false, true>(IV, p, len, X);
     memcpy(out, X, 16);
 }
 extern "C" void host_sha256(const uint8_t *p, uint32_t len, uint8_t *out)

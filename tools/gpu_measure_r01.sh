@@ -8,9 +8,6 @@ python tools/prof_kernels.py all 262144 4096 >> gpurun_out/kernels_r01.txt 2>&1
 python tools/prof_kernels.py lz4,lzf,fused 16384 65536 >> gpurun_out/kernels_r01.txt 2>&1; tail -9 gpurun_out/kernels_r01.txt
 for mode in 0 1; do CW_MODE=$mode python tools/prof_classes.py fused 8192 2>&1 | sed "s/^/mode=$mode /"; done > gpurun_out/classes_fused_r01.txt
 CW_MODE=0 python tools/prof_classes.py lzf 8192 > gpurun_out/classes_lzf_r01.txt 2>&1
+CW_MODE=0 python tools/prof_classes.py lz4 8192 > gpurun_out/classes_lz4_r01.txt 2>&1
 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/plain_bench.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r01.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; tail -2 gpurun_out/ncu_bench.log
-python tools/prof_kernels.py fused 262144 8192 1 > gpurun_out/plainF.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:cw_fused_kernel -s 1 -c 1 -f -o gpurun_out/prof_r01_fused python tools/prof_kernels.py fused 262144 8192 1 > gpurun_out/ncu_F.log 2>&1; tail -2 gpurun_out/ncu_F.log
-python tools/prof_kernels.py skein512,sha256 262144 8192 1 > gpurun_out/plainH.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:cw_hash_kernel -s 1 -c 1 -f -o gpurun_out/prof_r01_skein512 python tools/prof_kernels.py skein512 262144 8192 1 > gpurun_out/ncu_H.log 2>&1; tail -2 gpurun_out/ncu_H.log

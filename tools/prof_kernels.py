@@ -32,6 +32,10 @@ runs = {
     "sha256": lambda: eng.hash_dev(cw.HASH_SHA256, src.data_ptr(), chunk, n, dig.data_ptr(), s),
     "fused": lambda: eng.hash_compress_dev(cw.HASH_SKEIN512, cw.COMP_LZ4, 0, src.data_ptr(), chunk, n, dig.data_ptr(),
                                            blocks.data_ptr(), stride, lens.data_ptr(), s),
+    "fusedlzf": lambda: eng.hash_compress_dev(cw.HASH_SKEIN512, cw.COMP_LZF, 0, src.data_ptr(), chunk, n, dig.data_ptr(),
+                                              blocks.data_ptr(), stride, lens.data_ptr(), s),
+    "fusedsha": lambda: eng.hash_compress_dev(cw.HASH_SHA256, cw.COMP_LZ4, 0, src.data_ptr(), chunk, n, dig.data_ptr(),
+                                              blocks.data_ptr(), stride, lens.data_ptr(), s),
 }
 names = list(runs) if what == "all" else what.split(",")
 for name in names:

@@ -253,6 +253,35 @@ def test_async_offload_tickets(eng):
         _check_blocks(O.COMP_LZ4, src, chunk, blocks, lens)
 
 
+def test_concurrent_callers_threads_and_contexts(eng):
+    """doHashing / doCompression are called from --c-threads worker threads in the reference (HashAndCompress.cpp:398-403):
+    several host threads on ONE context, and a second context on the same GPU, all at once"""
+    import threading
+    chunk, n = 4096, 1500
+    eng2 = cw.Engine(0)
+    jobs = []
+    for t in range(6):
+        d = O.synth(chunk, 10000 + 3000 * t, n)
+        jobs.append({"eng": eng if t % 3 else eng2, "alg": O.COMP_LZ4 if t % 2 else O.COMP_LZF, "d": d})
+
+    def work(j):
+        for _ in range(3):
+            j["out"] = j["eng"].process_block(cw.HASH_SKEIN256_128, j["alg"], j["d"], chunk)
+
+    th = [threading.Thread(target=work, args=(j,)) for j in jobs]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    eng2.close()
+    for j in jobs:
+        dig, blocks, lens = j["out"]
+        assert (dig == O.hash_chunks(O.HASH_SKEIN256_128, j["d"], chunk)).all()
+        ob, ol = O.compress_chunks(j["alg"], j["d"], chunk)
+        assert (lens == ol).all()
+        assert all((blocks[i, : ol[i]] == ob[i, : ol[i]]).all() for i in range(0, n, 7))
+
+
 def test_device_pointer_api_and_synth(eng):
     torch = pytest.importorskip("torch")
     chunk, n = 8192, 4096

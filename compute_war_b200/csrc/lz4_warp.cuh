@@ -127,6 +127,9 @@ CW_DEV void cw_lz4_copy_warp(uint8_t *out, uint32_t dst, const uint8_t *s, uint3
 }
 
 #define CW_LZ4_QLEN 64u        // records per parser ring (power of two)
+#ifndef CW_LZ4_PUB_BATCH
+#define CW_LZ4_PUB_BATCH 16u // the parser makes its records visible to the emitter in batches of this many
+#endif
 #define CW_LZ4_REC_END 0xffffu  // cur field of the record that closes a chunk (final literals from anchor)
 
 // parser -> emitter ring, one per parser warp, in shared memory
@@ -282,6 +285,7 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
     const uint32_t own = 1u << lane;
     const uint32_t lower = own - 1u;
     uint32_t anchor = 0, tailc = qh;  // the caller drained the queue: tail == qh
+    uint32_t pub = qh;                // records published so far
 
     if (n >= 13u) {
         const uint32_t mfl1 = n - 11u;       // mflimit + 1: a probe happens only if the NEXT probe position is <= this
@@ -369,7 +373,6 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
             }
             // ---------------- phase B ----------------
             uint32_t ins = 0, i0 = 0, pend = CW_LZ4_NONE;
-            const uint32_t qh0 = qh;
             bool restart = false;
             for (;;) {
                 const uint32_t range = ~((1u << i0) - 1u);
@@ -434,7 +437,10 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
                 restart = true;
                 break;
             }
-            if (qh != qh0) cw_lz4_q_publish(q, qh, lane);
+            if (qh - pub >= CW_LZ4_PUB_BATCH) {  // publishing costs a fence: not after every window
+                cw_lz4_q_publish(q, qh, lane);
+                pub = qh;
+            }
             if (done) break;
             // ---------------- phase C: every touched slot gets its final value ----------------
             if (twins) {

@@ -78,12 +78,12 @@ CW_DEV void cw_lzf_parse_warp(const uint8_t *s, uint32_t n, CwLzfScratch *scr, C
     const unsigned lane = cw_lane();
     const uint32_t lower = (1u << lane) - 1u;
     uint32_t tailc = qh;  // the caller drained the queue
+    uint32_t pub = qh;    // records published so far
     uint32_t anchor = 0;                          // first literal of the current stretch
     const uint32_t limit = n > 2u ? n - 2u : 0u;  // positions < limit are probed
     uint32_t base = 0;
     bool ended_by_match = false;
     while (base < limit) {
-        const uint32_t qh0 = qh;
         // ---------------- phase A ----------------
         const uint32_t pos = base + lane;
         const bool valid = pos < limit;
@@ -238,7 +238,10 @@ CW_DEV void cw_lzf_parse_warp(const uint8_t *s, uint32_t n, CwLzfScratch *scr, C
             }
             cw_syncwarp();
         }
-        if (qh != qh0) cw_lz4_q_publish(q, qh, lane);
+        if (qh - pub >= CW_LZ4_PUB_BATCH) {
+            cw_lz4_q_publish(q, qh, lane);
+            pub = qh;
+        }
         base = restart ? e : base + 32u;
     }
     // liblzf's length rule can carry the last match to the very end of the input (anchor == n, 17 bits for a 64 KB

@@ -400,6 +400,22 @@ size_t cw_compress_bound(cw_comp_alg alg, size_t chunk)
     return chunk;
 }
 
+int cw_host_register(cw_ctx *ctx, void *ptr, size_t bytes)
+{
+    if (!ctx || !ptr || bytes == 0) return CW_ERR_ARG;
+    CW_CUDA(ctx, cudaSetDevice(ctx->device));
+    CW_CUDA(ctx, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return CW_OK;
+}
+
+int cw_host_unregister(cw_ctx *ctx, void *ptr)
+{
+    if (!ctx || !ptr) return CW_ERR_ARG;
+    CW_CUDA(ctx, cudaSetDevice(ctx->device));
+    CW_CUDA(ctx, cudaHostUnregister(ptr));
+    return CW_OK;
+}
+
 int cw_hash_dev(cw_ctx *ctx, cw_hash_alg alg, const void *d_src, size_t chunk, size_t n, void *d_digests, void *stream)
 {
     int rc = check_common(ctx, chunk, n, d_src);

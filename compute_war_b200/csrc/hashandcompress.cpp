@@ -47,6 +47,8 @@ static void usage(const char *argv0, const char *msg = nullptr)
             "  -D, --devices N       shard the chunks over N GPUs starting at --device: contiguous chunk ranges, one\n"
             "                        context and host thread per GPU, no exchange between them (default 1)\n"
             "  -i, --iters N         repeat the timed pass N times (default 1)\n"
+            "  -P, --no-pin          leave the host buffers pageable, as the reference's malloc'd buffers are (default: page-lock\n"
+            "                        them once before the timed passes, cw_host_register)\n"
             "  -o, --dump PREFIX     write PREFIX.digests, PREFIX.lens, PREFIX.blocks\n"
             "  -R, --randomness      also print the digest byte distribution lines of the reference's hashing_randomness\n"
             "                        tool (byte|alg|avg|stddev|, then \"Average std dev\") for the first 16 digest bytes\n",
@@ -58,6 +60,7 @@ int main(int argc, char **argv)
 {
     int threads = 8, offload = 0, device = 0, iters = 1, randomness = 0, devices = 1;
     std::string dump;
+    int pin = 1;
     size_t chunk = 4096;
     std::string comp = "lz4", hash = "skein", mode = "compat";
     static const option opts[] = {{"help", no_argument, 0, 'h'},          {"c-threads", required_argument, 0, 'c'},
@@ -66,10 +69,10 @@ int main(int argc, char **argv)
                                   {"hash-alg", required_argument, 0, 'H'},    {"chunk", required_argument, 0, 'k'},
                                   {"mode", required_argument, 0, 'm'},        {"device", required_argument, 0, 'd'},
                                   {"iters", required_argument, 0, 'i'},       {"randomness", no_argument, 0, 'R'},       {"devices", required_argument, 0, 'D'},
-                                  {"dump", required_argument, 0, 'o'},
+                                  {"dump", required_argument, 0, 'o'},       {"no-pin", no_argument, 0, 'P'},
                                   {0, 0, 0, 0}};
     int o;
-    while ((o = getopt_long(argc, argv, "hc:g:r:G:C:H:k:m:d:i:RD:o:", opts, nullptr)) != -1) {
+    while ((o = getopt_long(argc, argv, "hc:g:r:G:C:H:k:m:d:i:RD:o:P", opts, nullptr)) != -1) {
         switch (o) {
         case 'h': usage(argv[0]); break;
         case 'c': threads = atoi(optarg); break;
@@ -85,6 +88,7 @@ int main(int argc, char **argv)
         case 'R': randomness = 1; break;
         case 'D': devices = atoi(optarg); break;
         case 'o': dump = optarg; break;
+        case 'P': pin = 0; break;
         default: usage(argv[0], "bad option");
         }
     }
@@ -137,6 +141,12 @@ int main(int argc, char **argv)
     std::vector<uint8_t> digests(n * D), blocks(n * stride);
     std::vector<uint32_t> lens(n);
 
+    if (pin) {  // untimed, like the reference's ReadAllFiles: the timed passes then copy at full PCIe rate
+        int r1 = cw_host_register(ctx, data.data(), data.size()), r2 = cw_host_register(ctx, blocks.data(), blocks.size());
+        int r3 = cw_host_register(ctx, digests.data(), digests.size()), r4 = cw_host_register(ctx, lens.data(), n * sizeof(uint32_t));
+        if (r1 != CW_OK || r2 != CW_OK || r3 != CW_OK || r4 != CW_OK)
+            fprintf(stderr, "warning: could not page-lock the host buffers (%s); continuing with pageable memory\n", cw_last_error(ctx));
+    }
     auto pass_range = [&](cw_ctx *c, size_t first, size_t cnt) -> int {
         const uint8_t *src = data.data() + first * chunk;
         uint8_t *dg = digests.data() + first * D, *bl = blocks.data() + first * stride;
@@ -212,6 +222,12 @@ int main(int argc, char **argv)
         }
         for (size_t b = 0; b < nb; b++) std::cout << b << "|" << hash << "|" << avg[b] << "|" << sd[b] << "|" << std::endl;
         std::cout << "Average std dev: " << tot << std::endl;
+    }
+    if (pin) {
+        cw_host_unregister(ctxs[0], data.data());
+        cw_host_unregister(ctxs[0], blocks.data());
+        cw_host_unregister(ctxs[0], digests.data());
+        cw_host_unregister(ctxs[0], lens.data());
     }
     for (cw_ctx *c : ctxs) cw_shutdown(c);
     return 0;

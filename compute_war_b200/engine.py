@@ -72,6 +72,8 @@ def load_library():
     L.cw_digest_byte_stats.argtypes = [vp, sz, vp, vp, C.POINTER(C.c_double)]
     L.cw_digest_stats.argtypes = [vp, vp, sz, sz, sz, vp, vp, C.POINTER(C.c_double)]
     L.cw_dedup_dev.argtypes = [vp, vp, sz, sz, vp, vp, vp]
+    L.cw_host_register.argtypes = [vp, vp, sz]
+    L.cw_host_unregister.argtypes = [vp, vp]
     L.cw_sync.argtypes = [vp, vp]
     L.cw_submit.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, sz, sz, vp, vp, sz, vp, vp, vp, C.POINTER(u64)]
     L.cw_wait.argtypes = [vp, u64]
@@ -238,6 +240,13 @@ class Engine:
     def dedup_dev(self, d_digests, digest_bytes, n, d_first, d_n_unique, stream=0):
         """d_first: u32[n], first[i] = smallest j with an equal digest; d_n_unique: u64"""
         self._check(self.L.cw_dedup_dev(self.h, d_digests, digest_bytes, n, d_first, d_n_unique, stream or None))
+
+    def host_register(self, arr: np.ndarray):
+        """page-lock a numpy buffer the caller keeps reusing (cw_host_register)"""
+        self._check(self.L.cw_host_register(self.h, arr.ctypes.data, arr.nbytes))
+
+    def host_unregister(self, arr: np.ndarray):
+        self._check(self.L.cw_host_unregister(self.h, arr.ctypes.data))
 
     def synth_dev(self, d_dst, chunk, first_chunk, n, seed=0xC0FFEE, stream=0):
         self._check(self.L.cw_synth_dev(self.h, d_dst, chunk, first_chunk, n, seed, stream or None))

@@ -77,6 +77,13 @@ size_t cw_compress_bound(cw_comp_alg alg, size_t chunk_bytes);
  * Blocking.  Buffers are the caller's (the library never frees or keeps them); pinned host memory makes
  * the internal H2D/D2H copies asynchronous and overlapped with the kernels, pageable memory also works. */
 
+/* Page-locks (and later releases) a caller-owned buffer so that the copies of the host-buffer calls run asynchronously at
+ * full PCIe rate; the reference allocates its buffers with malloc / std::string (HashAndCompress.cpp:233-239), which
+ * works here too but is staged through the driver's bounce buffers.  Registration is slow (about a second per GiB):
+ * do it once for buffers that are reused.  No counterpart in the reference. */
+int cw_host_register(cw_ctx *ctx, void *ptr, size_t bytes);
+int cw_host_unregister(cw_ctx *ctx, void *ptr);
+
 /* doHashing(const char* src, char* dst, int count): HashAndCompress.cpp:119, doSkeinHashing :121-134,
  * HashBlockSkein256 / HashBlockSHA256 (src/hashing_perf/hash.cpp:5-46) */
 int cw_hash(cw_ctx *ctx, cw_hash_alg alg, const void *src, size_t chunk_bytes, size_t n_chunks, void *digests);

@@ -66,16 +66,68 @@ __host__ __device__ constexpr uint32_t cw_slot_bytes(uint32_t chunk)
            (uint32_t)sizeof(CwLz4Queue);
 }
 
-// warps [0, parsers): parsers; [parsers, parsers + emitters): emitters; the rest: hash
+// Which role a physical warp plays.  Warp w issues from scheduler w % 4.  A hash warp is the one role that wants issue
+// slots all the time, the emitters mostly wait, the parsers are what the pass waits for: hash warps are therefore put
+// on schedulers of their own as far as possible, with the emitters for company, and the parsers share the others
+// (compat: scheduler 3 = {hash, emitter, emitter}, 3 parsers on each of the other three).
+struct CwRoleMap {
+    uint8_t logical[32];  // logical index: [0, parsers) parser, [parsers, parsers + emitters) emitter, then hash
+};
+
+// hs / es: scheduler of every hash warp / emitter warp (nullptr: roles in warp order)
+static CwRoleMap make_role_map(int parsers, int emitters, int hash_warps, const int *hs, const int *es)
+{
+    CwRoleMap m;
+    const int W = parsers + emitters + hash_warps;
+    int role[32];
+    for (int i = 0; i < 32; i++) role[i] = -1;
+    auto pick_any = [&](int s) {  // highest free physical warp of scheduler s, else of the next scheduler down
+        for (int k = 0; k < 4; k++)
+            for (int p = W - 1; p >= 0; p--)
+                if (p % 4 == (s + 4 - k) % 4 && role[p] < 0) return p;
+        return -1;
+    };
+    if (hs && es) {
+        for (int i = 0; i < hash_warps; i++) role[pick_any(hs[i])] = parsers + emitters + i;
+        for (int i = 0; i < emitters; i++) role[pick_any(es[i])] = parsers + i;
+    }
+    int next = 0;
+    for (int p = 0; p < W; p++) {
+        if (!(hs && es)) role[p] = p;
+        else if (role[p] < 0) role[p] = next++;
+    }
+    for (int i = 0; i < 32; i++) m.logical[i] = (uint8_t)(i < W ? role[i] : 0);
+    return m;
+}
+
+// "3;3,3" -> hash warp on scheduler 3, two emitters on scheduler 3 (tuning knob CW_ROLE_MAP; "0" = warp order)
+static bool parse_role_env(int *hs, int *es)
+{
+    const char *e = getenv("CW_ROLE_MAP");
+    if (!e) return false;
+    int *dst = hs, k = 0;
+    for (int i = 0; i < 4; i++) hs[i] = es[i] = 3;
+    for (; *e; e++) {
+        if (*e == ';') {
+            dst = es;
+            k = 0;
+        } else if (*e >= '0' && *e <= '3' && k < 4)
+            dst[k++] = *e - '0';
+    }
+    return true;
+}
+
+// logical warps [0, parsers): parsers; [parsers, parsers + emitters): emitters; the rest: hash
 template <int HALG, int CALG, bool ALIGNED>
 __global__ void __launch_bounds__(CW_FUSED_MAX_THREADS, 1)
     cw_fused_kernel(const __grid_constant__ CwSkeinIV iv, const uint8_t *__restrict__ src, uint32_t chunk, uint64_t n_chunks,
                     uint8_t *__restrict__ digests, uint8_t *__restrict__ dst, uint64_t stride, uint32_t *__restrict__ lens,
-                    unsigned long long *work, uint32_t slot_bytes, uint32_t parsers, uint32_t emitters)
+                    unsigned long long *work, uint32_t slot_bytes, uint32_t parsers, uint32_t emitters,
+                    const __grid_constant__ CwRoleMap roles)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bars[32];
-    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const unsigned warp = roles.logical[threadIdx.x >> 5], lane = threadIdx.x & 31u;
     {
         // slot_bytes excludes the queue: queues sit behind the slots
         CwLz4Queue *queues = reinterpret_cast<CwLz4Queue *>(smem + (size_t)parsers * slot_bytes);
@@ -118,6 +170,22 @@ __global__ void __launch_bounds__(CW_FUSED_MAX_THREADS, 1)
     }
 }
 
+static CwRoleMap fused_role_map(int calg, int parsers, int emitters, int hw)
+{
+    static int ehs[4], ees[4];
+    static const bool have_env = parse_role_env(ehs, ees);
+    if (have_env) {
+        const char *e = getenv("CW_ROLE_MAP");
+        if (e[0] == '0' && e[1] == 0) return make_role_map(parsers, emitters, hw, nullptr, nullptr);
+        return make_role_map(parsers, emitters, hw, ehs, ees);
+    }
+    // measured (profiles/r01_tune_emitters_hashwarps.txt): with 9 parsers the hash warp gets scheduler 3 to itself, the
+    // emitters for company, and every other scheduler runs 3 parsers; the 13-parser fast kernel keeps the warp order
+    static const int hs3[4] = {3, 3, 3, 3}, es3[4] = {3, 3, 3, 3};
+    if (calg == CW_C_LZ4 && hw == 1 && (parsers + emitters + hw) % 4 == 0) return make_role_map(parsers, emitters, hw, hs3, es3);
+    return make_role_map(parsers, emitters, hw, nullptr, nullptr);
+}
+
 template <int HALG, int CALG, bool ALIGNED>
 static cudaError_t launch_one(const CwDeviceInfo &dev, int max_dyn_smem, const CwSkeinIV &iv, const uint8_t *d_src,
                               uint32_t chunk, uint64_t n, uint8_t *d_digests, uint8_t *d_dst, uint64_t stride,
@@ -133,8 +201,10 @@ static cudaError_t launch_one(const CwDeviceInfo &dev, int max_dyn_smem, const C
     if (emitters > parsers) emitters = parsers;
     uint64_t ctas = (n + (uint64_t)parsers - 1) / (uint64_t)parsers;
     if (ctas > (uint64_t)dev.sm_count) ctas = (uint64_t)dev.sm_count;
-    kern<<<(unsigned)ctas, (parsers + emitters + fused_hash_warps(CALG == CW_C_LZ4_FAST)) * 32, (size_t)parsers * per, st>>>(
-        iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, slot, (uint32_t)parsers, (uint32_t)emitters);
+    const int hw = fused_hash_warps(CALG == CW_C_LZ4_FAST);
+    kern<<<(unsigned)ctas, (parsers + emitters + hw) * 32, (size_t)parsers * per, st>>>(
+        iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, slot, (uint32_t)parsers, (uint32_t)emitters,
+        fused_role_map(CALG, parsers, emitters, hw));
     return cudaGetLastError();
 }
 

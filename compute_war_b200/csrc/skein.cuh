@@ -239,7 +239,10 @@ CW_HOSTDEV void cw_skein_load(uint64_t (&w)[WORDS], const uint8_t *p, unsigned a
 
 // Hash one chunk of `len` bytes.  IV = cw_skein_iv(...) computed once on the host.  out receives
 // OUT_BYTES (<= 8*WORDS) digest bytes, little-endian words (Skein_Put64_LSB_First, skein_port.h:57).
-template <int WORDS, int OUT_BYTES, bool ALIGNED, bool UNROLL72>
+// PREFETCH: the next block's words are loaded before the current block is processed.  The lone hash warp of the fused
+// kernel needs this -- its loads come from L2 and nothing else on its scheduler hides them (+18 % when hashing is the
+// limit); with thousands of threads per SM it is still worth 2.5 % (stand-alone kernel: 675 -> 692 GB/s).
+template <int WORDS, int OUT_BYTES, bool ALIGNED, bool UNROLL72, bool PREFETCH = false>
 CW_HOSTDEV void cw_skein_chunk(const uint64_t (&IV)[WORDS], const uint8_t *p, uint32_t len,
                                uint64_t (&X)[WORDS])
 {
@@ -250,15 +253,31 @@ CW_HOSTDEV void cw_skein_chunk(const uint64_t (&IV)[WORDS], const uint8_t *p, ui
     uint64_t T1 = CW_SKEIN_T1_FIRST | CW_SKEIN_T1_MSG;
     uint32_t off = 0;
     // all blocks but the last are full (Skein_512_Update keeps the last 1..B bytes for Final, skein.c:354-370)
-    while (len - off > B) {
-        cw_skein_load<WORDS, ALIGNED>(w, p + off, B);
-        off += B;
-        if constexpr (WORDS == 8) cw_tf512_block<UNROLL72>(X, w, off, T1);
-        else cw_tf256_block(X, w, off, T1);
-        T1 = CW_SKEIN_T1_MSG;
+    if constexpr (PREFETCH) {
+        uint64_t wn[WORDS];
+        cw_skein_load<WORDS, ALIGNED>(w, p, len > B ? B : len);
+        while (len - off > B) {
+            const uint32_t rest = len - off - B;  // bytes behind this block: 1..B of them form the next one
+            cw_skein_load<WORDS, ALIGNED>(wn, p + off + B, rest > B ? B : rest);
+            off += B;
+            if constexpr (WORDS == 8) cw_tf512_block<UNROLL72>(X, w, off, T1);
+            else cw_tf256_block(X, w, off, T1);
+            T1 = CW_SKEIN_T1_MSG;
+#pragma unroll
+            for (int i = 0; i < WORDS; i++) w[i] = wn[i];
+        }
+    } else {
+        while (len - off > B) {
+            cw_skein_load<WORDS, ALIGNED>(w, p + off, B);
+            off += B;
+            if constexpr (WORDS == 8) cw_tf512_block<UNROLL72>(X, w, off, T1);
+            else cw_tf256_block(X, w, off, T1);
+            T1 = CW_SKEIN_T1_MSG;
+        }
+        // final (zero padded) block
+        cw_skein_load<WORDS, ALIGNED>(w, p + off, len - off);
     }
-    // final (zero padded) block, T0 = total length (skein.c:383-387)
-    cw_skein_load<WORDS, ALIGNED>(w, p + off, len - off);
+    // final block, T0 = total length (skein.c:383-387)
     if constexpr (WORDS == 8) cw_tf512_block<UNROLL72>(X, w, len, T1 | CW_SKEIN_T1_FINAL);
     else cw_tf256_block(X, w, len, T1 | CW_SKEIN_T1_FINAL);
     // output block: counter 0 under the final chaining value (skein.c:393-399)

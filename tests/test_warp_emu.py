@@ -46,13 +46,14 @@ def test_device_hash_source_on_host(hosthash):
     for n in [0, 1, 7, 8, 31, 32, 33, 55, 56, 63, 64, 65, 127, 128, 129, 200, 1000, 4096, 8192, 65536]:
         b = rng.integers(0, 256, n + 1, dtype=np.uint8)
         bb = b[:n].tobytes()
-        for unroll in (0, 1):
+        for unroll in (0, 1, 2, 3):  # both round-loop shapes, without and with the next-block prefetch loop
             out = np.zeros(64, np.uint8)
             hosthash.host_skein512(b.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p), unroll)
             assert out.tobytes() == O.skein(512, 512, bb), (n, unroll)
-        out = np.zeros(16, np.uint8)
-        hosthash.host_skein256_128(b.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p))
-        assert out.tobytes() == O.skein(256, 128, bb), n
+        for prefetch in (0, 1):
+            out = np.zeros(16, np.uint8)
+            hosthash.host_skein256_128(b.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p), prefetch)
+            assert out.tobytes() == O.skein(256, 128, bb), (n, prefetch)
         out = np.zeros(32, np.uint8)
         hosthash.host_sha256(b.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p))
         assert out.tobytes() == O.sha256(bb), n

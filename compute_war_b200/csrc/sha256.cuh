@@ -111,9 +111,18 @@ CW_SHAFN void cw_sha256_chunk(const uint8_t *p, uint32_t len, uint32_t (&H)[8])
     H[0] = 0x6a09e667u; H[1] = 0xbb67ae85u; H[2] = 0x3c6ef372u; H[3] = 0xa54ff53au;
     H[4] = 0x510e527fu; H[5] = 0x9b05688cu; H[6] = 0x1f83d9abu; H[7] = 0x5be0cd19u;
     uint32_t off = 0;
-    for (; off + 64 <= len; off += 64) {
-        cw_sha256_load<ALIGNED>(w, p + off);
+    // full blocks, the next one loaded before the current one is compressed (as in cw_skein_chunk)
+    if (len >= 64u) {
+        uint32_t wn[16];
+        cw_sha256_load<ALIGNED>(w, p);
+        for (; off + 128 <= len; off += 64) {
+            cw_sha256_load<ALIGNED>(wn, p + off + 64);
+            cw_sha256_compress(H, w);
+#pragma unroll
+            for (int i = 0; i < 16; i++) w[i] = wn[i];
+        }
         cw_sha256_compress(H, w);
+        off += 64;
     }
     // padding: 0x80, zeros, 64-bit big-endian bit length
     const uint32_t rem = len - off;

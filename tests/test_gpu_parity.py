@@ -181,6 +181,26 @@ def test_compress_edge_cases(eng, alg):
 
 
 @pytest.mark.parametrize("alg", [O.COMP_LZ4, O.COMP_LZF])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_compress_ragged_chunk_sizes_and_strides(eng, golden, alg, mode):
+    """chunk sizes around every internal switch (staged / in-place reads at 16 KiB, tagged LZF entries at 8 KiB, 16-byte
+    alignment of the bulk copy), real data, several chunks per call, odd output strides"""
+    blob = golden["blob"]
+    for chunk in (3, 13, 100, 1000, 4104, 5000, 8191, 8192, 8193, 8200, 16383, 16384, 16400, 20001, 32768, 50000, 65535, 65536):
+        n = min(9, len(blob) // chunk)
+        d = blob[7: 7 + n * chunk].copy()  # source offset 7 inside the blob: content differs from the other tests
+        stride = cw.compress_bound(alg, chunk) + (5 if chunk % 2 else 0)
+        blocks, lens = eng.do_compression(alg, d, chunk, mode, stride=stride)
+        if mode == 0:
+            _check_blocks(alg, d, chunk, blocks, lens)
+        else:
+            assert O.verify_roundtrip(alg, d, chunk, blocks, lens) == 0, chunk
+            ol = O.compress_chunks(alg, d, chunk)[1]
+            tot = sum(int(x) if x else chunk for x in lens)
+            assert tot <= 1.02 * sum(int(x) if x else chunk for x in ol) + 16 * n, chunk
+
+
+@pytest.mark.parametrize("alg", [O.COMP_LZ4, O.COMP_LZF])
 def test_fast_mode_roundtrips_and_ratio(eng, golden, alg):
     """fast mode: every block must decode back exactly; total size within 1 % of the reference's"""
     ref, blob = golden["ref"], golden["blob"]

@@ -81,6 +81,10 @@ cudaError_t cw_launch_lz4(const CwDeviceInfo &dev, bool fast, const uint8_t *d_s
     int parsers = g_lz4_max_smem / (int)(slot + sizeof(CwLz4Queue));
     if (parsers < 1) return cudaErrorInvalidValue;
     if (parsers > CW_LZ4_MAX_PARSERS) parsers = CW_LZ4_MAX_PARSERS;
+    if (const char *e = getenv("CW_LZ4_PARSERS")) {  // tuning knob for the profiling scripts
+        const int v = atoi(e);
+        if (v > 0 && v < parsers) parsers = v;
+    }
     int emitters = lz4_emitters();
     if (emitters > parsers) emitters = parsers;
     uint64_t ctas = (n + (uint64_t)parsers - 1) / (uint64_t)parsers;

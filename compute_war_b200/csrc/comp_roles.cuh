@@ -106,14 +106,15 @@ __device__ __forceinline__ void cw_lz4_emitter_role(unsigned e, unsigned emitter
     }
 }
 
-// LZF parser role; slot = [chunk | 16 B pad | CwLzfScratch], one queue per parser as for LZ4
+// LZF parser role; slot = [chunk | 16 B pad | table of cw_lzf_table_bytes(format)], one queue per parser as for LZ4
 template <bool ALIGNED>
 __device__ __forceinline__ void cw_lzf_parser_role(uint8_t *s, CwLz4Queue *q, uint64_t *bar, const uint8_t *__restrict__ src,
                                                    uint32_t chunk, uint64_t n_chunks, unsigned long long *work)
 {
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t chunk_pad = (chunk + 16u + 15u) & ~15u;
-    CwLzfScratch *scr = reinterpret_cast<CwLzfScratch *>(s + chunk_pad);
+    uint16_t *tab = reinterpret_cast<uint16_t *>(s + chunk_pad);
+    const int bb = cw_lzf_table_format(chunk);
     if (lane == 0) cw_mbar_init(bar, 1);
     for (uint32_t i = chunk + lane; i < chunk_pad; i += 32u) s[i] = 0;
     __syncwarp();
@@ -128,10 +129,10 @@ __device__ __forceinline__ void cw_lzf_parser_role(uint8_t *s, CwLz4Queue *q, ui
             q->chunk_lo = (uint32_t)g;
             q->chunk_hi = (uint32_t)(g >> 32);
         }
-        const bool tagged = chunk <= CW_LZF_BUCKETS;
         if (ALIGNED && lane == 0) cw_bulk_load(s, src + g * chunk, chunk, bar);
-        if (tagged) cw_lzf_table_init<true>(scr);
-        else cw_lzf_table_init<false>(scr);
+        if (bb == 12) cw_lzf_table_init<12>(tab);
+        else if (bb == 13) cw_lzf_table_init<13>(tab);
+        else cw_lzf_table_init<0>(tab);
         if (ALIGNED) {
             cw_mbar_wait(bar, phase);
             phase ^= 1u;
@@ -140,8 +141,9 @@ __device__ __forceinline__ void cw_lzf_parser_role(uint8_t *s, CwLz4Queue *q, ui
             for (uint32_t i = lane; i < chunk; i += 32u) s[i] = gp[i];
         }
         __syncwarp();
-        if (tagged) cw_lzf_parse_warp<true>(s, chunk, scr, q, qh);
-        else cw_lzf_parse_warp<false>(s, chunk, scr, q, qh);
+        if (bb == 12) cw_lzf_parse_warp<12>(s, chunk, tab, q, qh);
+        else if (bb == 13) cw_lzf_parse_warp<13>(s, chunk, tab, q, qh);
+        else cw_lzf_parse_warp<0>(s, chunk, tab, q, qh);
     }
     cw_lz4_q_drain(q, qh, lane);
     if (lane == 0) {

@@ -61,7 +61,7 @@ static int fused_emitters(bool fast)
 template <int CALG>
 __host__ __device__ constexpr uint32_t cw_slot_bytes(uint32_t chunk)
 {
-    return (CALG == CW_C_LZF ? ((chunk + 16u + 15u) & ~15u) + (uint32_t)sizeof(CwLzfScratch)
+    return (CALG == CW_C_LZF ? ((chunk + 16u + 15u) & ~15u) + cw_lzf_table_bytes(cw_lzf_table_format(chunk))
                              : cw_lz4_chunk_pad(chunk) + (2u << (CALG == CW_C_LZ4 ? 13 : 12))) +
            (uint32_t)sizeof(CwLz4Queue);
 }

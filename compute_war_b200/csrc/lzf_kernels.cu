@@ -6,7 +6,8 @@
 // it raw, lzf.h:59-64).
 //
 // Same structure as lz4_kernels.cu: one CTA per SM; parser warps each own a shared-memory slot
-// [chunk + 16 B pad][head u16[8192]][next u16[8192]] = 40 KB at 8 KB chunks (5 per SM) plus a record queue, and pull
+// [chunk + 16 B pad][head u16[NB]][next u16[NB]] (NB = 8192: 40 KB at 8 KB chunks, 5 per SM; NB = 4096 for chunks of
+// up to 4 KB: 20 KB, 11 per SM) plus a record queue, and pull
 // chunk indices from a global counter; emitter warps (no slot) write the streams (lzf_warp.cuh).
 #include "comp_roles.cuh"
 #include "launch.h"
@@ -28,7 +29,10 @@ static int lzf_emitters()
 }
 
 // bytes of one parser's slot, without its queue
-static inline uint32_t lzf_slot_bytes(uint32_t chunk) { return ((chunk + 16u + 15u) & ~15u) + (uint32_t)sizeof(CwLzfScratch); }
+static inline uint32_t lzf_slot_bytes(uint32_t chunk)
+{
+    return ((chunk + 16u + 15u) & ~15u) + cw_lzf_table_bytes(cw_lzf_table_format(chunk));
+}
 
 template <bool ALIGNED>
 __global__ void __launch_bounds__((CW_LZF_MAX_WARPS + 3) * 32, 1)

@@ -19,8 +19,9 @@
 // a lane walks the chain until it meets a position whose own slot (recomputed from its bytes) equals the
 // query slot.  32 KB per chunk instead of 128 KB.  Positions older than 8192 bytes can never match
 // (MAX_OFF), so the next[] ring never needs more than 8192 entries whatever the chunk size.
-// For chunks of up to 8192 bytes (TAGGED) a table entry is  (slot >> 13) << 13 | position : the three slot bits the
-// bucket index does not cover ride along with the 13-bit position, so a chain walk is one shared-memory load per step
+// For chunks of up to 8192 bytes (BB = 13) a table entry is  (slot >> 13) << 13 | position : the three slot bits the
+// bucket index does not cover ride along with the 13-bit position (chunks of up to 4096 bytes, BB = 12: 4096 buckets,
+// four tag bits, a 4096-entry ring -- 16 KB of table instead of 32, so almost twice the chunks per SM), so a chain walk is one shared-memory load per step
 // and no trigram has to be re-read and re-hashed.  Position 0 terminates a chain: it is the oldest position and can
 // never be a match source (the reference requires ref > in_data), exactly like an empty slot of its zeroed table.
 // As in lz4_warp.cuh the parser warp evaluates 32 consecutive probe positions at once and then replays the
@@ -41,6 +42,10 @@ struct CwLzfScratch {
     uint16_t head[CW_LZF_BUCKETS];  // newest inserted position per bucket (slot & 8191), NONE if empty
     uint16_t next[CW_LZF_BUCKETS];  // ring: previous position in the same bucket, indexed by pos & 8191
 };
+// Table formats.  BB = 0: plain positions, 8192 buckets + 8192-entry ring (any chunk size).  BB = 13 / 12: tagged
+// entries, 2^BB buckets + 2^BB-entry ring, for chunks of up to 2^BB bytes.  Layout: u16 head[NB], then u16 next[NB].
+CW_HOSTDEV int cw_lzf_table_format(uint32_t chunk) { return chunk <= 4096u ? 12 : (chunk <= CW_LZF_BUCKETS ? 13 : 0); }
+CW_HOSTDEV uint32_t cw_lzf_table_bytes(int bb) { return 4u << (bb ? bb : 13); }
 
 // 24-bit big-endian trigram at p (liblzf's hval) and its 16-bit table slot (IDX with VERY_FAST, HLOG 16)
 CW_DEV uint32_t cw_lzf_hv(const uint8_t *s, uint32_t p)
@@ -59,22 +64,27 @@ CW_DEV void cw_lzf_put_literals(uint8_t *out, uint32_t op, const uint8_t *s, uin
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// PARSER.  s[0..n): the chunk (shared memory, >= 8 readable bytes behind it); scr: table scratch prepared by
-// cw_lzf_table_init; q / qh as in cw_lz4_parse_warp.  Records: {anchor | cur << 16, ref | len << 16}; the closing record is
+// PARSER.  s[0..n): the chunk (shared memory, >= 8 readable bytes behind it); tab: table prepared by
+// cw_lzf_table_init<BB>; q / qh as in cw_lz4_parse_warp.  Records: {anchor | cur << 16, ref | len << 16}; the closing record is
 // {CW_LZ4_REC_END << 16, anchor | "the last match ran into the end of the input" << 31}.
 // ---------------------------------------------------------------------------------------------------------------
 // empty table (the caller runs this while the chunk's bulk copy is in flight, then syncs the warp)
-template <bool TAGGED>
-CW_DEV void cw_lzf_table_init(CwLzfScratch *scr)
+template <int BB>
+CW_DEV void cw_lzf_table_init(uint16_t *tab)
 {
-    uint32_t *h = reinterpret_cast<uint32_t *>(scr->head);
-    const uint32_t f = TAGGED ? 0u : 0xffffffffu;
-    for (uint32_t i = cw_lane(); i < CW_LZF_BUCKETS / 2u; i += 32u) h[i] = f;
+    uint32_t *h = reinterpret_cast<uint32_t *>(tab);
+    const uint32_t f = BB ? 0u : 0xffffffffu;
+    for (uint32_t i = cw_lane(); i < (1u << (BB ? BB : 13)) / 2u; i += 32u) h[i] = f;
 }
 
-template <bool TAGGED>
-CW_DEV void cw_lzf_parse_warp(const uint8_t *s, uint32_t n, CwLzfScratch *scr, CwLz4Queue *q, uint32_t &qh)
+template <int BB>
+CW_DEV void cw_lzf_parse_warp(const uint8_t *s, uint32_t n, uint16_t *tab, CwLz4Queue *q, uint32_t &qh)
 {
+    constexpr bool TAGGED = BB != 0;
+    constexpr uint32_t NB = 1u << (TAGGED ? BB : 13);  // buckets = ring entries
+    constexpr uint32_t PM = NB - 1u;                   // position / bucket mask
+    constexpr uint32_t TM = 0xffffu & ~PM;             // tag bits of an entry = the slot bits above the bucket index
+    uint16_t *const head = tab, *const next = tab + NB;
     const unsigned lane = cw_lane();
     const uint32_t lower = (1u << lane) - 1u;
     uint32_t tailc = qh;  // the caller drained the queue
@@ -89,16 +99,16 @@ CW_DEV void cw_lzf_parse_warp(const uint8_t *s, uint32_t n, CwLzfScratch *scr, C
         const bool valid = pos < limit;
         const uint32_t hv = cw_lzf_hv(s, valid ? pos : 0u);
         const uint32_t slot = cw_lzf_slot(hv);
-        const uint32_t b = slot & (CW_LZF_BUCKETS - 1u);
-        const uint32_t head_old = scr->head[b];
+        const uint32_t b = slot & PM;
+        const uint32_t head_old = head[b];
         uint32_t cq;  // most recent inserted position with this 16-bit slot, CW_LZF_NONE if there is none
         bool tmatch;
         if (TAGGED) {
             uint32_t e = valid ? head_old : 0u;
             for (;;) {
-                cq = e & (CW_LZF_BUCKETS - 1u);
-                if (cq == 0u || (e >> 13) == (slot >> 13)) break;
-                e = scr->next[cq];
+                cq = e & PM;
+                if (cq == 0u || (e & TM) == (slot & TM)) break;
+                e = next[cq];
             }
             tmatch = cq != 0u && cw_lzf_hv(s, cq) == hv;
             if (cq == 0u) cq = CW_LZF_NONE;
@@ -112,7 +122,7 @@ CW_DEV void cw_lzf_parse_warp(const uint8_t *s, uint32_t n, CwLzfScratch *scr, C
                 }
                 hq = cw_lzf_hv(s, cq);
                 if (cw_lzf_slot(hq) == slot) break;
-                cq = scr->next[cq & (CW_LZF_BUCKETS - 1u)];
+                cq = next[cq & PM];
             }
             tmatch = valid && cq != CW_LZF_NONE && cq > 0u && (pos - cq - 1u) < CW_LZF_MAX_OFF && hq == hv;
         }
@@ -120,9 +130,9 @@ CW_DEV void cw_lzf_parse_warp(const uint8_t *s, uint32_t n, CwLzfScratch *scr, C
         // lanes that share a bucket inside the window ("twins") are detected by tagging the bucket head and reading
         // it back; the chain walk above is done by then, and phase C rewrites every tagged head
         cw_syncwarp();
-        if (valid) scr->head[b] = (uint16_t)(0xffe0u | lane);
+        if (valid) head[b] = (uint16_t)(0xffe0u | lane);
         cw_syncwarp();
-        const bool owner = valid && scr->head[b] == (0xffe0u | lane);
+        const bool owner = valid && head[b] == (0xffe0u | lane);
         uint32_t M13 = own, M16 = own, E = own;
         const uint32_t twins = cw_ballot(valid && !owner);
         if (cw_popc(twins) > 8) {  // many groups (e.g. tables of small integers): MATCH.ANY's fixed ~365 cycles each win
@@ -136,7 +146,7 @@ CW_DEV void cw_lzf_parse_warp(const uint8_t *s, uint32_t n, CwLzfScratch *scr, C
             while (rem) {
                 const uint32_t hvL = cw_shfl(hv, (unsigned)cw_ffs(rem) - 1u);
                 const uint32_t slotL = cw_lzf_slot(hvL);
-                const bool s13 = valid && b == (slotL & (CW_LZF_BUCKETS - 1u)), s16 = valid && slot == slotL, se = valid && hv == hvL;
+                const bool s13 = valid && b == (slotL & PM), s16 = valid && slot == slotL, se = valid && hv == hvL;
                 const uint32_t m13 = cw_ballot(s13), m16 = cw_ballot(s16), me = cw_ballot(se);
                 if (s13) M13 = m13;
                 if (s16) M16 = m16;
@@ -213,16 +223,16 @@ CW_DEV void cw_lzf_parse_warp(const uint8_t *s, uint32_t n, CwLzfScratch *scr, C
         // ---------------- phase C: link the inserted positions into their bucket chains ----------------
         // every bucket touched by a valid lane carries a tag: its owner first puts the old head back, then the
         // inserted lanes link themselves in (highest inserted lane of a bucket becomes the new head)
-        if (owner) scr->head[b] = (uint16_t)head_old;
+        if (owner) head[b] = (uint16_t)head_old;
         const uint32_t grp = M13 & ins;
         const uint32_t lo = grp & lower;
         const int jprev = lo ? 31 - cw_clz(lo) : (int)lane;  // nearest inserted lane below this one in the same bucket
-        const uint32_t tag_prev = TAGGED && twins ? cw_shfl(slot & 0xe000u, (unsigned)jprev) : 0u;
+        const uint32_t tag_prev = TAGGED && twins ? cw_shfl(slot & TM, (unsigned)jprev) : 0u;
         cw_syncwarp();
         if (valid && ((ins >> lane) & 1u)) {
             const uint32_t prev = lo ? ((base + (uint32_t)jprev) | tag_prev) : head_old;
-            scr->next[pos & (CW_LZF_BUCKETS - 1u)] = (uint16_t)prev;
-            if (!(grp & ~((2u << lane) - 1u))) scr->head[b] = (uint16_t)(TAGGED ? (pos | (slot & 0xe000u)) : pos);
+            next[pos & PM] = (uint16_t)prev;
+            if (!(grp & ~((2u << lane) - 1u))) head[b] = (uint16_t)(TAGGED ? (pos | (slot & TM)) : pos);
         }
         cw_syncwarp();
         if (pend0 != CW_LZF_NONE || pend1 != CW_LZF_NONE) {
@@ -231,9 +241,9 @@ CW_DEV void cw_lzf_parse_warp(const uint8_t *s, uint32_t n, CwLzfScratch *scr, C
                     const uint32_t p = t ? pend1 : pend0;
                     if (p == CW_LZF_NONE) continue;
                     const uint32_t ps = cw_lzf_slot(cw_lzf_hv(s, p));
-                    const uint32_t pb = ps & (CW_LZF_BUCKETS - 1u);
-                    scr->next[p & (CW_LZF_BUCKETS - 1u)] = scr->head[pb];
-                    scr->head[pb] = (uint16_t)(TAGGED ? (p | (ps & 0xe000u)) : p);
+                    const uint32_t pb = ps & PM;
+                    next[p & PM] = head[pb];
+                    head[pb] = (uint16_t)(TAGGED ? (p | (ps & TM)) : p);
                 }
             }
             cw_syncwarp();

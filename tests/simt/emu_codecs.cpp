@@ -99,7 +99,7 @@ extern "C" uint32_t emu_lz4_compress(const uint8_t *src, uint32_t n, uint8_t *ou
 struct LzfJob {
     const uint8_t *s;
     uint32_t n;
-    CwLzfScratch *scr;
+    uint16_t *tab;
     CwLz4Queue *q;
     uint8_t *out;
     uint32_t out_cap;
@@ -112,14 +112,18 @@ static void lzf_block_body(void *a, int warp)
     const unsigned lane = cw_lane();
     if (warp == 0) {
         uint32_t qh = 0;
-        if (j->tagged) {
-            cw_lzf_table_init<true>(j->scr);
+        if (j->tagged == 12) {
+            cw_lzf_table_init<12>(j->tab);
             cw_syncwarp();
-            cw_lzf_parse_warp<true>(j->s, j->n, j->scr, j->q, qh);
+            cw_lzf_parse_warp<12>(j->s, j->n, j->tab, j->q, qh);
+        } else if (j->tagged == 13) {
+            cw_lzf_table_init<13>(j->tab);
+            cw_syncwarp();
+            cw_lzf_parse_warp<13>(j->s, j->n, j->tab, j->q, qh);
         } else {
-            cw_lzf_table_init<false>(j->scr);
+            cw_lzf_table_init<0>(j->tab);
             cw_syncwarp();
-            cw_lzf_parse_warp<false>(j->s, j->n, j->scr, j->q, qh);
+            cw_lzf_parse_warp<0>(j->s, j->n, j->tab, j->q, qh);
         }
         cw_lz4_q_drain(j->q, qh, lane);
         if (lane == 0) {
@@ -137,7 +141,7 @@ static void lzf_block_body(void *a, int warp)
         }
     }
 }
-// tagged: 1 = the <= 8192-byte table format, 0 = the general one, -1 = what the kernels pick
+// tagged: table format 12 / 13 (tagged entries, chunks <= 4096 / 8192 bytes) or 0 (general), -1 = what the kernels pick
 extern "C" uint32_t emu_lzf_compress_mode(const uint8_t *src, uint32_t n, uint8_t *out, uint32_t out_cap, int tagged)
 {
     if (n == 0) return 0;
@@ -146,8 +150,9 @@ extern "C" uint32_t emu_lzf_compress_mode(const uint8_t *src, uint32_t n, uint8_
     std::vector<uint8_t> scratch(sizeof(CwLzfScratch), 0xA5);  // contents irrelevant on entry
     CwLz4Queue q;
     memset(&q, 0, sizeof q);
-    if (tagged < 0) tagged = n <= CW_LZF_BUCKETS;
-    LzfJob j{(const uint8_t *)staged.data(), n, (CwLzfScratch *)scratch.data(), &q, out, out_cap, {0}, tagged};
+    if (tagged < 0) tagged = cw_lzf_table_format(n);
+    scratch.resize(cw_lzf_table_bytes(tagged));  // exactly what the kernels give the format
+    LzfJob j{(const uint8_t *)staged.data(), n, (uint16_t *)scratch.data(), &q, out, out_cap, {0}, tagged};
     cwemu::run_block(2, lzf_block_body, &j);
     return j.lens[0];
 }

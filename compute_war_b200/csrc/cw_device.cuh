@@ -25,7 +25,6 @@ CW_DEV unsigned cw_ballot(bool p) { return __ballot_sync(CW_FULL, p); }
 CW_DEV uint32_t cw_shfl(uint32_t v, unsigned src) { return __shfl_sync(CW_FULL, v, src); }
 CW_DEV unsigned cw_match_any(uint32_t v) { return __match_any_sync(CW_FULL, v); }
 CW_DEV void cw_syncwarp() { __syncwarp(); }
-CW_DEV uint32_t cw_reduce_or(uint32_t v) { return __reduce_or_sync(CW_FULL, v); }
 CW_DEV int cw_ffs(uint32_t v) { return __ffs(v); }       // 1-based, 0 if none
 CW_DEV int cw_clz(uint32_t v) { return __clz(v); }
 CW_DEV int cw_popc(uint32_t v) { return __popc(v); }

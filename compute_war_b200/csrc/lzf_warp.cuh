@@ -38,10 +38,6 @@
 #define CW_LZF_MAX_OFF 8192u
 #define CW_LZF_MAX_REF 264u
 
-struct CwLzfScratch {
-    uint16_t head[CW_LZF_BUCKETS];  // newest inserted position per bucket (slot & 8191), NONE if empty
-    uint16_t next[CW_LZF_BUCKETS];  // ring: previous position in the same bucket, indexed by pos & 8191
-};
 // Table formats.  BB = 0: plain positions, 8192 buckets + 8192-entry ring (any chunk size).  BB = 13 / 12: tagged
 // entries, 2^BB buckets + 2^BB-entry ring, for chunks of up to 2^BB bytes.  Layout: u16 head[NB], then u16 next[NB].
 CW_HOSTDEV int cw_lzf_table_format(uint32_t chunk) { return chunk <= 4096u ? 12 : (chunk <= CW_LZF_BUCKETS ? 13 : 0); }

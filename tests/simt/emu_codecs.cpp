@@ -147,11 +147,11 @@ extern "C" uint32_t emu_lzf_compress_mode(const uint8_t *src, uint32_t n, uint8_
     if (n == 0) return 0;
     std::vector<uint32_t> staged((n + CW_LZ4_PAD + 3) / 4 + 4, 0);
     memcpy(staged.data(), src, n);
-    std::vector<uint8_t> scratch(sizeof(CwLzfScratch), 0xA5);  // contents irrelevant on entry
+    std::vector<uint8_t> scratch(1, 0xA5);  // sized below; contents irrelevant on entry
     CwLz4Queue q;
     memset(&q, 0, sizeof q);
     if (tagged < 0) tagged = cw_lzf_table_format(n);
-    scratch.resize(cw_lzf_table_bytes(tagged));  // exactly what the kernels give the format
+    scratch.assign(cw_lzf_table_bytes(tagged), 0xA5);  // exactly what the kernels give the format
     LzfJob j{(const uint8_t *)staged.data(), n, (uint16_t *)scratch.data(), &q, out, out_cap, {0}, tagged};
     cwemu::run_block(2, lzf_block_body, &j);
     return j.lens[0];

@@ -130,6 +130,10 @@ CW_DEV void cw_lz4_copy_warp(uint8_t *out, uint32_t dst, const uint8_t *s, uint3
 #ifndef CW_LZ4_PUB_BATCH
 #define CW_LZ4_PUB_BATCH 16u // the parser makes its records visible to the emitter in batches of this many
 #endif
+#ifndef CW_LZ4_CHAIN
+#define CW_LZ4_CHAIN 0  // batched replay of twin-free unit windows (cw_lz4_parse_warp, phase B): +4-9 % on real text, but the
+                        // bigger loop costs 5 % on the synthetic mix (profiles/r01_ab_lz4_speculation.txt); off by default
+#endif
 #define CW_LZ4_REC_END 0xffffu  // cur field of the record that closes a chunk (final literals from anchor)
 
 // parser -> emitter ring, one per parser warp, in shared memory
@@ -166,6 +170,23 @@ CW_DEV void cw_lz4_q_push(CwLz4Queue *q, uint32_t &qh, uint32_t &tailc, uint32_t
         q->rec[qh & (CW_LZ4_QLEN - 1u)][1] = b;
     }
     qh++;
+}
+// parser side: make room for cnt (<= 32) records that their lanes are about to write themselves
+CW_DEV void cw_lz4_q_reserve(CwLz4Queue *q, uint32_t qh, uint32_t &tailc, uint32_t cnt, unsigned lane)
+{
+    if (qh + cnt - tailc <= CW_LZ4_QLEN) return;
+    cw_syncwarp();
+    if (lane == 0) {
+        cw_fence_cta();
+        cw_st_vol(&q->head, qh);
+    }
+    for (;;) {
+        uint32_t t = 0;
+        if (lane == 0) t = cw_ld_vol(&q->tail);
+        tailc = cw_shfl(t, 0);
+        if (qh + cnt - tailc <= CW_LZ4_QLEN) break;
+        cw_spin();
+    }
 }
 CW_DEV void cw_lz4_q_publish(CwLz4Queue *q, uint32_t qh, unsigned lane)
 {
@@ -374,7 +395,55 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
             // ---------------- phase B ----------------
             uint32_t ins = 0, i0 = 0, pend = CW_LZ4_NONE;
             bool restart = false;
-            for (;;) {
+            if (CW_LZ4_CHAIN && spec_on && unit && !twins && tm_all) {
+                // Twin-free unit window: every candidate is the table entry read in phase A, and a lane whose
+                // speculation closed already knows where its match ends.  The parser's walk from match to match is then
+                // one shuffle per match, and the records are written by their own lanes, all at once.  The walk stops at
+                // a match that is still open (the general loop below extends it with the whole warp) and wherever the
+                // general loop would leave the window.
+                const uint32_t closed_all = cw_ballot(tmatch && !(spec & 0x80000000u));
+                const uint32_t my_de = lane + 4u + (spec & 0x7fffffffu);  // lane index of the end of this lane's match
+                const uint32_t anchor0 = anchor;
+                uint32_t chain = 0;
+                for (;;) {
+                    const uint32_t range = ~((1u << i0) - 1u);
+                    const uint32_t hm = tm_all & range;
+                    if (!hm) break;
+                    const unsigned f = (unsigned)cw_ffs(hm) - 1u;
+                    if (!((closed_all >> f) & 1u)) break;
+                    chain |= 1u << f;
+                    ins |= range & ((2u << f) - 1u);
+                    const uint32_t de = cw_shfl(my_de, f);
+                    const uint32_t e = base + de;
+                    spec_on = de - f - 4u < 28u;
+                    anchor = e;
+                    if (e >= mfl1) {
+                        done = true;
+                        break;
+                    }
+                    sbase = e + 1u;
+                    const bool in2 = de < 34u;
+                    ins |= in2 ? 1u << ((de - 2u) & 31u) : 0u;
+                    pend = in2 ? pend : e - 2u;
+                    i0 = de;
+                    if (de < 32u) continue;
+                    restart = true;
+                    break;
+                }
+                if (chain) {
+                    const uint32_t cnt = (uint32_t)cw_popc(chain), below = chain & lower;
+                    cw_lz4_q_reserve(q, qh, tailc, cnt, lane);
+                    // a record's anchor is the end of the chain match before it (the carried-in anchor for the first)
+                    const uint32_t prev_de = cw_shfl(my_de, below ? (unsigned)(31 - cw_clz(below)) : lane);
+                    if ((chain >> lane) & 1u) {
+                        const uint32_t k = (qh + (uint32_t)cw_popc(below)) & (CW_LZ4_QLEN - 1u);
+                        q->rec[k][0] = (below ? base + prev_de : anchor0) | (pos << 16);
+                        q->rec[k][1] = t | ((spec & 0x7fffffffu) << 16);
+                    }
+                    qh += cnt;
+                }
+            }
+            if (!restart && !done) for (;;) {
                 const uint32_t range = ~((1u << i0) - 1u);
                 uint32_t hitm = tm_all & range;
                 uint32_t cand = t, sp = spec;

@@ -83,11 +83,17 @@ def _cases(golden, small):
     return cases
 
 
-def test_lz4_warp_algorithm_byte_identical(emu, golden):
+@pytest.mark.parametrize("chain", [0, 1])
+def test_lz4_warp_algorithm_byte_identical(emu, golden, chain):
+    """chain = 1: the build-time option CW_LZ4_CHAIN (batched replay of twin-free windows; off in the shipped library)"""
+    L = emu
+    if chain:
+        L = _build("libemu_chain.so", ["emu_codecs.cpp", "warp_emu.cpp"], extra=("-DCW_LZ4_CHAIN=1",))
+        L.emu_lz4_compress.restype = C.c_uint32
     for c in _cases(golden, small=True):
         n = len(c)
         out = np.zeros(n + n // 255 + 64, np.uint8)
-        r = emu.emu_lz4_compress(c.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p))
+        r = L.emu_lz4_compress(c.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p))
         blocks, lens = O.compress_chunks(O.COMP_LZ4, c, n)
         assert r == lens[0] and (out[:r] == blocks[0, :r]).all(), n
 

@@ -13,6 +13,7 @@
 
 #include "comp_roles.cuh"
 #include "launch.h"
+#include "role_map.h"
 
 #define CW_LZ4_MAX_PARSERS 16
 #define CW_LZ4_MAX_EMITTERS 4
@@ -37,11 +38,11 @@ template <int HASHLOG, bool ALIGNED, bool DIRECT>
 __global__ void __launch_bounds__((CW_LZ4_MAX_PARSERS + CW_LZ4_MAX_EMITTERS) * 32, 1)
     cw_lz4_kernel(const uint8_t *__restrict__ src, uint32_t chunk, uint64_t n_chunks, uint8_t *__restrict__ dst,
                   uint64_t stride, uint32_t *__restrict__ lens, unsigned long long *work, uint32_t slot_bytes,
-                  uint32_t parsers, uint32_t emitters)
+                  uint32_t parsers, uint32_t emitters, const __grid_constant__ CwRoleMap roles)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bars[32];
-    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const unsigned warp = roles.logical[threadIdx.x >> 5], lane = threadIdx.x & 31u;
     CwLz4Queue *queues = reinterpret_cast<CwLz4Queue *>(smem + (size_t)parsers * slot_bytes);
     if (warp < parsers && lane < 8u) reinterpret_cast<uint32_t *>(&queues[warp])[lane] = 0u;  // head, tail, chunk, op, done
     __syncthreads();
@@ -91,8 +92,16 @@ cudaError_t cw_launch_lz4(const CwDeviceInfo &dev, bool fast, const uint8_t *d_s
     if (ctas > (uint64_t)dev.sm_count) ctas = (uint64_t)dev.sm_count;
     const dim3 grid((unsigned)ctas), block((parsers + emitters) * 32);
     const size_t dyn = (size_t)parsers * (slot + sizeof(CwLz4Queue));
+    // emitters share scheduler 3 (warp w issues from scheduler w % 4), parsers fill the others: parser-only schedulers
+    // keep their instruction caches to the parser loop (CW_LZ4_ROLE_MAP=0: roles in warp order)
+    static const bool grouped = [] {
+        const char *e = getenv("CW_LZ4_ROLE_MAP");
+        return !(e && atoi(e) == 0);
+    }();
+    static const int none[4] = {3, 3, 3, 3}, es[4] = {3, 3, 3, 3};
+    const CwRoleMap roles = make_role_map(parsers, emitters, 0, grouped ? none : nullptr, grouped ? es : nullptr);
 #define CW_GO(HL, AL, DI) \
-    cw_lz4_kernel<HL, AL, DI><<<grid, block, dyn, st>>>(d_src, chunk, n, d_dst, stride, d_lens, work, slot, (uint32_t)parsers, (uint32_t)emitters)
+    cw_lz4_kernel<HL, AL, DI><<<grid, block, dyn, st>>>(d_src, chunk, n, d_dst, stride, d_lens, work, slot, (uint32_t)parsers, (uint32_t)emitters, roles)
     if (direct) {
         if (fast) CW_GO(12, true, true);
         else CW_GO(13, true, true);

@@ -28,6 +28,9 @@
 // hash_warps * 32 lanes * chunk * 148 SMs; 1 warp keeps that window at 39 MB for 8 KB chunks (L2: 126 MB)
 // while still hashing faster than the compressors consume (measured, profiles/).
 #define CW_FUSED_HASH_WARPS_DEFAULT 1
+#ifndef CW_FUSED_TAIL_HELP
+#define CW_FUSED_TAIL_HELP 1  // warps without compress work left join the hash role
+#endif
 #define CW_FUSED_HASH_WARPS_MAX 4
 #define CW_FUSED_MAX_COMP_WARPS 14
 #define CW_FUSED_MAX_THREADS ((CW_FUSED_HASH_WARPS_MAX + CW_FUSED_MAX_COMP_WARPS + 3) * 32)  // + emitters
@@ -107,18 +110,20 @@ __global__ void __launch_bounds__(CW_FUSED_MAX_THREADS, 1)
             else
                 cw_lz4_parser_role<(CALG == CW_C_LZ4 ? 13 : 12), ALIGNED, false>(smem + (size_t)warp * slot_bytes, &queues[warp],
                                                                                  &bars[warp], src, chunk, n_chunks, &work[0]);
-            return;
-        }
-        if (warp < parsers + emitters) {
+            if (!CW_FUSED_TAIL_HELP) return;
+        } else if (warp < parsers + emitters) {
             if (CALG == CW_C_LZF)
                 cw_lzf_emitter_role(warp - parsers, emitters, parsers, smem, slot_bytes, queues, chunk, dst, stride, lens);
             else
                 cw_lz4_emitter_role<false>(warp - parsers, emitters, parsers, smem, slot_bytes, queues, src, chunk, dst, stride,
                                            lens);
-            return;
+            if (!CW_FUSED_TAIL_HELP) return;
         }
     }
     // ------------------------------ hash role ------------------------------
+    // Parser and emitter warps that have run out of chunks end up here too: when the last chunk has been claimed the
+    // hash warp is still up to a group or more behind (one group = 32 chunks = 0.3 ms of hashing for one warp), and on
+    // a slice-sized batch that tail is a fifth of the kernel.
     constexpr int D = cw_digest_len<HALG>();
     for (;;) {
         unsigned long long grp = 0;

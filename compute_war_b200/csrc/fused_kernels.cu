@@ -8,10 +8,8 @@
 //   * hash warps (1 per CTA by default, no shared memory) take groups of 32 consecutive chunks, one chunk per lane,
 //     and run the register-resident Skein / SHA-256 chain of skein.cuh / sha256.cuh straight from global
 //     memory.
-// The two roles are coupled through the counters: a hash warp starts group g only once the compress
-// counter has passed the end of that group, i.e. once those chunks have been (or are being) pulled into
-// L2 by the compress warps' bulk copies.  The window between the two readers is a few MB, far below
-// the 126 MB L2, so every input byte is fetched from HBM once (ncu: dram__bytes_read.sum ~= input bytes);
+// The two roles are coupled through the counters: a hash warp starts group g only while it is within 32 MiB of
+// the compress counter, so whichever role reads a chunk second finds it in L2 (126 MB), not in HBM;
 // the compressors are latency bound and leave most issue slots of the SM idle, which is exactly what the
 // integer-bound hash warps consume.
 // the 3 x 24-round Skein body (11 KB of SASS instead of 36 KB) keeps hash + compressor code inside the instruction cache
@@ -125,6 +123,7 @@ __global__ void __launch_bounds__(CW_FUSED_MAX_THREADS, 1)
     // hash warp is still up to a group or more behind (one group = 32 chunks = 0.3 ms of hashing for one warp), and on
     // a slice-sized batch that tail is a fifth of the kernel.
     constexpr int D = cw_digest_len<HALG>();
+    const unsigned long long lead = (32ull << 20) / chunk;
     for (;;) {
         unsigned long long grp = 0;
         if (lane == 0) grp = atomicAdd(&work[1], 1ull);
@@ -133,8 +132,11 @@ __global__ void __launch_bounds__(CW_FUSED_MAX_THREADS, 1)
         if (first >= n_chunks) break;
         const unsigned long long need = first + 32ull < n_chunks ? first + 32ull : n_chunks;
         if (lane == 0) {
-            // follow the compress warps: wait until this group's chunks have been claimed (-> are in L2)
-            while (*reinterpret_cast<volatile unsigned long long *>(&work[0]) < need) __nanosleep(256);
+            // stay close to the compress warps so that whichever role reads a chunk second finds it in L2: a group may
+            // start once its last chunk is at most `lead` chunks (32 MiB) ahead of the compress counter.  Waiting for the
+            // chunks to be claimed first (lead = 0) leaves the last groups of a batch -- 0.3-0.6 ms of hashing each --
+            // to run after the parsers are done.
+            while (*reinterpret_cast<volatile unsigned long long *>(&work[0]) + lead < need) __nanosleep(256);
         }
         __syncwarp();
         const unsigned long long idx = first + lane;

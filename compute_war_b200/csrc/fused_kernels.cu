@@ -29,7 +29,7 @@
 #ifndef CW_FUSED_TAIL_HELP
 #define CW_FUSED_TAIL_HELP 1  // warps without compress work left join the hash role
 #endif
-#define CW_FUSED_HASH_WARPS_MAX 4
+#define CW_FUSED_HASH_WARPS_MAX 2  // also sizes __launch_bounds__: 19 warps leave ptxas 96 registers and no spills
 #define CW_FUSED_MAX_COMP_WARPS 14
 #define CW_FUSED_MAX_THREADS ((CW_FUSED_HASH_WARPS_MAX + CW_FUSED_MAX_COMP_WARPS + 3) * 32)  // + emitters
 
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(CW_FUSED_MAX_THREADS, 1)
     cw_fused_kernel(const __grid_constant__ CwSkeinIV iv, const uint8_t *__restrict__ src, uint32_t chunk, uint64_t n_chunks,
                     uint8_t *__restrict__ digests, uint8_t *__restrict__ dst, uint64_t stride, uint32_t *__restrict__ lens,
                     unsigned long long *work, uint32_t slot_bytes, uint32_t parsers, uint32_t emitters,
-                    const __grid_constant__ CwRoleMap roles, uint32_t lead_mb)
+                    const __grid_constant__ CwRoleMap roles)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bars[32];
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(CW_FUSED_MAX_THREADS, 1)
     // hash warp is still up to a group or more behind (one group = 32 chunks = 0.3 ms of hashing for one warp), and on
     // a slice-sized batch that tail is a fifth of the kernel.
     constexpr int D = cw_digest_len<HALG>();
-    const unsigned long long lead = ((unsigned long long)lead_mb << 20) / chunk;
+    const unsigned long long lead = (32ull << 20) / chunk;
     for (;;) {
         unsigned long long grp = 0;
         if (lane == 0) grp = atomicAdd(&work[1], 1ull);
@@ -142,17 +142,6 @@ __global__ void __launch_bounds__(CW_FUSED_MAX_THREADS, 1)
         const unsigned long long idx = first + lane;
         if (idx < n_chunks) cw_hash_one<HALG, ALIGNED, ALIGNED>(iv, src + idx * chunk, chunk, digests + idx * D);
     }
-}
-
-// how far (MiB of input) the hash warps may run ahead of the compress counter; both roles read every chunk, the second
-// reader should find it in L2 (126 MB)
-static uint32_t fused_lead_mb()
-{
-    static const uint32_t v = [] {
-        const char *e = getenv("CW_FUSED_LEAD_MB");  // tuning knob for the profiling scripts
-        return e ? (uint32_t)atoi(e) : 32u;
-    }();
-    return v;
 }
 
 static CwRoleMap fused_role_map(int calg, int parsers, int emitters, int hw)
@@ -189,7 +178,7 @@ static cudaError_t launch_one(const CwDeviceInfo &dev, int max_dyn_smem, const C
     const int hw = fused_hash_warps(CALG == CW_C_LZ4_FAST);
     kern<<<(unsigned)ctas, (parsers + emitters + hw) * 32, (size_t)parsers * per, st>>>(
         iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, slot, (uint32_t)parsers, (uint32_t)emitters,
-        fused_role_map(CALG, parsers, emitters, hw), fused_lead_mb());
+        fused_role_map(CALG, parsers, emitters, hw));
     return cudaGetLastError();
 }
 

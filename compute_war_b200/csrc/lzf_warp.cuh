@@ -38,10 +38,20 @@
 #define CW_LZF_MAX_OFF 8192u
 #define CW_LZF_MAX_REF 264u
 
-// Table formats.  BB = 0: plain positions, 8192 buckets + 8192-entry ring (any chunk size).  BB = 13 / 12: tagged
-// entries, 2^BB buckets + 2^BB-entry ring, for chunks of up to 2^BB bytes.  Layout: u16 head[NB], then u16 next[NB].
-CW_HOSTDEV int cw_lzf_table_format(uint32_t chunk) { return chunk <= 4096u ? 12 : (chunk <= CW_LZF_BUCKETS ? 13 : 0); }
-CW_HOSTDEV uint32_t cw_lzf_table_bytes(int bb) { return 4u << (bb ? bb : 13); }
+// Table formats (layout: u16 head[buckets], then u16 next[ring entries]):
+//   0   plain positions, 8192 buckets + 8192-entry ring (any chunk size)
+//   13  tagged entries, 8192 buckets + 8192-entry ring, chunks of up to 8192 bytes: tag = slot bits 13..15
+//   12  tagged entries, 4096 buckets + 4096-entry ring, chunks of up to 4096 bytes: tag = slot bits 12..15
+//   25  tagged entries, 4096 buckets + 8192-entry ring, chunks of up to 8192 bytes: the tag (slot bits 13..15) leaves
+//       slot bit 12 open, so a tag match is confirmed by re-hashing the candidate; 24 KB instead of 32
+#ifndef CW_LZF_FORMAT_8K
+#define CW_LZF_FORMAT_8K 25
+#endif
+CW_HOSTDEV int cw_lzf_table_format(uint32_t chunk) { return chunk <= 4096u ? 12 : (chunk <= CW_LZF_BUCKETS ? CW_LZF_FORMAT_8K : 0); }
+CW_HOSTDEV uint32_t cw_lzf_table_bytes(int fmt)
+{
+    return fmt == 12 ? 16384u : (fmt == 25 ? 24576u : 32768u);
+}
 
 // 24-bit big-endian trigram at p (liblzf's hval) and its 16-bit table slot (IDX with VERY_FAST, HLOG 16)
 CW_DEV uint32_t cw_lzf_hv(const uint8_t *s, uint32_t p)
@@ -73,13 +83,16 @@ CW_DEV void cw_lzf_table_init(uint16_t *tab)
     for (uint32_t i = cw_lane(); i < (1u << (BB ? BB : 13)) / 2u; i += 32u) h[i] = f;
 }
 
-template <int BB>
+// BB: bucket bits (0 = the untagged format with 8192 buckets), RB: ring / position bits
+template <int BB, int RB>
 CW_DEV void cw_lzf_parse_warp(const uint8_t *s, uint32_t n, uint16_t *tab, CwLz4Queue *q, uint32_t &qh)
 {
     constexpr bool TAGGED = BB != 0;
-    constexpr uint32_t NB = 1u << (TAGGED ? BB : 13);  // buckets = ring entries
-    constexpr uint32_t PM = NB - 1u;                   // position / bucket mask
-    constexpr uint32_t TM = 0xffffu & ~PM;             // tag bits of an entry = the slot bits above the bucket index
+    constexpr bool VERIFY = TAGGED && BB < RB;            // the tag does not cover every slot bit above the bucket index
+    constexpr uint32_t NB = 1u << (TAGGED ? BB : 13);     // buckets
+    constexpr uint32_t BM = NB - 1u;                      // bucket mask
+    constexpr uint32_t PM = (1u << (TAGGED ? RB : 13)) - 1u;  // position mask of an entry / ring index mask
+    constexpr uint32_t TM = 0xffffu & ~PM;                // tag bits of an entry = the slot bits from RB up
     uint16_t *const head = tab, *const next = tab + NB;
     const unsigned lane = cw_lane();
     const uint32_t lower = (1u << lane) - 1u;
@@ -95,7 +108,7 @@ CW_DEV void cw_lzf_parse_warp(const uint8_t *s, uint32_t n, uint16_t *tab, CwLz4
         const bool valid = pos < limit;
         const uint32_t hv = cw_lzf_hv(s, valid ? pos : 0u);
         const uint32_t slot = cw_lzf_slot(hv);
-        const uint32_t b = slot & PM;
+        const uint32_t b = slot & BM;
         const uint32_t head_old = head[b];
         uint32_t cq;  // most recent inserted position with this 16-bit slot, CW_LZF_NONE if there is none
         bool tmatch;
@@ -103,7 +116,8 @@ CW_DEV void cw_lzf_parse_warp(const uint8_t *s, uint32_t n, uint16_t *tab, CwLz4
             uint32_t e = valid ? head_old : 0u;
             for (;;) {
                 cq = e & PM;
-                if (cq == 0u || (e & TM) == (slot & TM)) break;
+                if (cq == 0u) break;
+                if ((e & TM) == (slot & TM) && (!VERIFY || cw_lzf_slot(cw_lzf_hv(s, cq)) == slot)) break;
                 e = next[cq];
             }
             tmatch = cq != 0u && cw_lzf_hv(s, cq) == hv;
@@ -142,7 +156,7 @@ CW_DEV void cw_lzf_parse_warp(const uint8_t *s, uint32_t n, uint16_t *tab, CwLz4
             while (rem) {
                 const uint32_t hvL = cw_shfl(hv, (unsigned)cw_ffs(rem) - 1u);
                 const uint32_t slotL = cw_lzf_slot(hvL);
-                const bool s13 = valid && b == (slotL & PM), s16 = valid && slot == slotL, se = valid && hv == hvL;
+                const bool s13 = valid && b == (slotL & BM), s16 = valid && slot == slotL, se = valid && hv == hvL;
                 const uint32_t m13 = cw_ballot(s13), m16 = cw_ballot(s16), me = cw_ballot(se);
                 if (s13) M13 = m13;
                 if (s16) M16 = m16;
@@ -237,7 +251,7 @@ CW_DEV void cw_lzf_parse_warp(const uint8_t *s, uint32_t n, uint16_t *tab, CwLz4
                     const uint32_t p = t ? pend1 : pend0;
                     if (p == CW_LZF_NONE) continue;
                     const uint32_t ps = cw_lzf_slot(cw_lzf_hv(s, p));
-                    const uint32_t pb = ps & PM;
+                    const uint32_t pb = ps & BM;
                     next[p & PM] = head[pb];
                     head[pb] = (uint16_t)(TAGGED ? (p | (ps & TM)) : p);
                 }

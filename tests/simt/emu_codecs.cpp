@@ -112,19 +112,14 @@ static void lzf_block_body(void *a, int warp)
     const unsigned lane = cw_lane();
     if (warp == 0) {
         uint32_t qh = 0;
-        if (j->tagged == 12) {
-            cw_lzf_table_init<12>(j->tab);
-            cw_syncwarp();
-            cw_lzf_parse_warp<12>(j->s, j->n, j->tab, j->q, qh);
-        } else if (j->tagged == 13) {
-            cw_lzf_table_init<13>(j->tab);
-            cw_syncwarp();
-            cw_lzf_parse_warp<13>(j->s, j->n, j->tab, j->q, qh);
-        } else {
-            cw_lzf_table_init<0>(j->tab);
-            cw_syncwarp();
-            cw_lzf_parse_warp<0>(j->s, j->n, j->tab, j->q, qh);
-        }
+        if (j->tagged == 12 || j->tagged == 25) cw_lzf_table_init<12>(j->tab);
+        else if (j->tagged == 13) cw_lzf_table_init<13>(j->tab);
+        else cw_lzf_table_init<0>(j->tab);
+        cw_syncwarp();
+        if (j->tagged == 12) cw_lzf_parse_warp<12, 12>(j->s, j->n, j->tab, j->q, qh);
+        else if (j->tagged == 25) cw_lzf_parse_warp<12, 13>(j->s, j->n, j->tab, j->q, qh);
+        else if (j->tagged == 13) cw_lzf_parse_warp<13, 13>(j->s, j->n, j->tab, j->q, qh);
+        else cw_lzf_parse_warp<0, 13>(j->s, j->n, j->tab, j->q, qh);
         cw_lz4_q_drain(j->q, qh, lane);
         if (lane == 0) {
             cw_fence_cta();
@@ -141,7 +136,7 @@ static void lzf_block_body(void *a, int warp)
         }
     }
 }
-// tagged: table format 12 / 13 (tagged entries, chunks <= 4096 / 8192 bytes) or 0 (general), -1 = what the kernels pick
+// tagged: table format of lzf_warp.cuh (12, 13, 25 or 0), -1 = what the kernels pick
 extern "C" uint32_t emu_lzf_compress_mode(const uint8_t *src, uint32_t n, uint8_t *out, uint32_t out_cap, int tagged)
 {
     if (n == 0) return 0;

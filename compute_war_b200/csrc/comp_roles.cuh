@@ -131,6 +131,7 @@ __device__ __forceinline__ void cw_lzf_parser_role(uint8_t *s, CwLz4Queue *q, ui
         }
         if (ALIGNED && lane == 0) cw_bulk_load(s, src + g * chunk, chunk, bar);
         if (bb == 12 || bb == 25) cw_lzf_table_init<12>(tab);
+        else if (bb == 24) cw_lzf_table_init<11>(tab);
         else if (bb == 13) cw_lzf_table_init<13>(tab);
         else cw_lzf_table_init<0>(tab);
         if (ALIGNED) {
@@ -143,6 +144,7 @@ __device__ __forceinline__ void cw_lzf_parser_role(uint8_t *s, CwLz4Queue *q, ui
         __syncwarp();
         if (bb == 12) cw_lzf_parse_warp<12, 12>(s, chunk, tab, q, qh);
         else if (bb == 25) cw_lzf_parse_warp<12, 13>(s, chunk, tab, q, qh);
+        else if (bb == 24) cw_lzf_parse_warp<11, 13>(s, chunk, tab, q, qh);
         else if (bb == 13) cw_lzf_parse_warp<13, 13>(s, chunk, tab, q, qh);
         else cw_lzf_parse_warp<0, 13>(s, chunk, tab, q, qh);
     }

@@ -44,13 +44,14 @@
 //   12  tagged entries, 4096 buckets + 4096-entry ring, chunks of up to 4096 bytes: tag = slot bits 12..15
 //   25  tagged entries, 4096 buckets + 8192-entry ring, chunks of up to 8192 bytes: the tag (slot bits 13..15) leaves
 //       slot bit 12 open, so a tag match is confirmed by re-hashing the candidate; 24 KB instead of 32
+//   24  the same with 2048 buckets (slot bits 11 and 12 open): 20 KB
 #ifndef CW_LZF_FORMAT_8K
 #define CW_LZF_FORMAT_8K 25
 #endif
 CW_HOSTDEV int cw_lzf_table_format(uint32_t chunk) { return chunk <= 4096u ? 12 : (chunk <= CW_LZF_BUCKETS ? CW_LZF_FORMAT_8K : 0); }
 CW_HOSTDEV uint32_t cw_lzf_table_bytes(int fmt)
 {
-    return fmt == 12 ? 16384u : (fmt == 25 ? 24576u : 32768u);
+    return fmt == 12 ? 16384u : (fmt == 25 ? 24576u : (fmt == 24 ? 20480u : 32768u));
 }
 
 // 24-bit big-endian trigram at p (liblzf's hval) and its 16-bit table slot (IDX with VERY_FAST, HLOG 16)

@@ -113,11 +113,13 @@ static void lzf_block_body(void *a, int warp)
     if (warp == 0) {
         uint32_t qh = 0;
         if (j->tagged == 12 || j->tagged == 25) cw_lzf_table_init<12>(j->tab);
+        else if (j->tagged == 24) cw_lzf_table_init<11>(j->tab);
         else if (j->tagged == 13) cw_lzf_table_init<13>(j->tab);
         else cw_lzf_table_init<0>(j->tab);
         cw_syncwarp();
         if (j->tagged == 12) cw_lzf_parse_warp<12, 12>(j->s, j->n, j->tab, j->q, qh);
         else if (j->tagged == 25) cw_lzf_parse_warp<12, 13>(j->s, j->n, j->tab, j->q, qh);
+        else if (j->tagged == 24) cw_lzf_parse_warp<11, 13>(j->s, j->n, j->tab, j->q, qh);
         else if (j->tagged == 13) cw_lzf_parse_warp<13, 13>(j->s, j->n, j->tab, j->q, qh);
         else cw_lzf_parse_warp<0, 13>(j->s, j->n, j->tab, j->q, qh);
         cw_lz4_q_drain(j->q, qh, lane);

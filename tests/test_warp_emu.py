@@ -134,7 +134,7 @@ def test_lzf_warp_algorithm_byte_identical(emu, golden):
         out = np.zeros(n + 64, np.uint8)
         blocks, lens = O.compress_chunks(O.COMP_LZF, c, n)
         # every table format the size allows (lzf_warp.cuh: 12, 13, 25 = 4096 buckets + 8192-entry ring, 0 = general)
-        for tagged in ([12, 13, 25, 0] if n <= 4096 else [13, 25, 0] if n <= 8192 else [0]):
+        for tagged in ([12, 13, 25, 24, 0] if n <= 4096 else [13, 25, 24, 0] if n <= 8192 else [0]):
             out[:] = 0
             r = emu.emu_lzf_compress_mode(c.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p), n - 1, tagged)
             assert r == lens[0], (n, tagged, r, lens[0])

@@ -12,7 +12,8 @@ __host__ __device__ constexpr uint32_t cw_lz4_chunk_pad(uint32_t chunk) { return
 // lies in global memory); q: this warp's queue (zeroed by the caller before the CTA-wide barrier).
 template <int HASHLOG, bool ALIGNED, bool DIRECT>
 __device__ __forceinline__ void cw_lz4_parser_role(uint8_t *s, CwLz4Queue *q, uint64_t *bar, const uint8_t *__restrict__ src,
-                                                   uint32_t chunk, uint64_t n_chunks, unsigned long long *work)
+                                                   uint32_t chunk, uint64_t n_chunks, unsigned long long *work,
+                                                   uint32_t qlen = CW_LZ4_QLEN)
 {
     const unsigned lane = threadIdx.x & 31u;
     if (DIRECT) {
@@ -32,7 +33,7 @@ __device__ __forceinline__ void cw_lz4_parser_role(uint8_t *s, CwLz4Queue *q, ui
                 q->chunk_hi = (uint32_t)(g >> 32);
             }
             __syncwarp();
-            cw_lz4_parse_warp<HASHLOG, true>(src + g * chunk, chunk, table, q, qh);
+            cw_lz4_parse_warp<HASHLOG, true>(src + g * chunk, chunk, table, q, qh, qlen);
         }
         cw_lz4_q_drain(q, qh, lane);
         if (lane == 0) {
@@ -71,7 +72,7 @@ __device__ __forceinline__ void cw_lz4_parser_role(uint8_t *s, CwLz4Queue *q, ui
             for (uint32_t i = lane; i < chunk; i += 32u) s[i] = gp[i];
         }
         __syncwarp();
-        cw_lz4_parse_warp<HASHLOG, false>(s, chunk, table, q, qh);
+        cw_lz4_parse_warp<HASHLOG, false>(s, chunk, table, q, qh, qlen);
     }
     cw_lz4_q_drain(q, qh, lane);
     if (lane == 0) {
@@ -86,18 +87,18 @@ template <bool DIRECT>
 __device__ __forceinline__ void cw_lz4_emitter_role(unsigned e, unsigned emitters, unsigned parsers, uint8_t *smem,
                                                     uint32_t slot_bytes, CwLz4Queue *queues, const uint8_t *__restrict__ src,
                                                     uint32_t chunk, uint8_t *__restrict__ dst, uint64_t stride,
-                                                    uint32_t *__restrict__ lens)
+                                                    uint32_t *__restrict__ lens, uint32_t qlen = CW_LZ4_QLEN)
 {
     const unsigned lane = threadIdx.x & 31u;
     for (;;) {
         bool all_done = true;
         uint32_t did = 0;
         for (unsigned p = e; p < parsers; p += emitters) {
-            CwLz4Queue *q = &queues[p];
+            CwLz4Queue *q = cw_lz4_queue_at(queues, p, qlen);
             uint32_t d = 0;
             if (lane == 0) d = cw_ld_vol(&q->done);  // read BEFORE the head: done is set after the last publish
             d = __shfl_sync(0xffffffffu, d, 0);
-            const uint32_t cnt = cw_lz4_emit_batch<DIRECT>(q, DIRECT ? src : smem + (size_t)p * slot_bytes, chunk, dst, stride, lens);
+            const uint32_t cnt = cw_lz4_emit_batch<DIRECT>(q, DIRECT ? src : smem + (size_t)p * slot_bytes, chunk, dst, stride, lens, qlen);
             did += cnt;
             if (!(d && cnt == 0u)) all_done = false;
         }
@@ -109,7 +110,8 @@ __device__ __forceinline__ void cw_lz4_emitter_role(unsigned e, unsigned emitter
 // LZF parser role; slot = [chunk | 16 B pad | table of cw_lzf_table_bytes(format)], one queue per parser as for LZ4
 template <bool ALIGNED>
 __device__ __forceinline__ void cw_lzf_parser_role(uint8_t *s, CwLz4Queue *q, uint64_t *bar, const uint8_t *__restrict__ src,
-                                                   uint32_t chunk, uint64_t n_chunks, unsigned long long *work)
+                                                   uint32_t chunk, uint64_t n_chunks, unsigned long long *work,
+                                                   uint32_t qlen = CW_LZ4_QLEN)
 {
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t chunk_pad = (chunk + 16u + 15u) & ~15u;
@@ -142,11 +144,11 @@ __device__ __forceinline__ void cw_lzf_parser_role(uint8_t *s, CwLz4Queue *q, ui
             for (uint32_t i = lane; i < chunk; i += 32u) s[i] = gp[i];
         }
         __syncwarp();
-        if (bb == 12) cw_lzf_parse_warp<12, 12>(s, chunk, tab, q, qh);
-        else if (bb == 25) cw_lzf_parse_warp<12, 13>(s, chunk, tab, q, qh);
-        else if (bb == 24) cw_lzf_parse_warp<11, 13>(s, chunk, tab, q, qh);
-        else if (bb == 13) cw_lzf_parse_warp<13, 13>(s, chunk, tab, q, qh);
-        else cw_lzf_parse_warp<0, 13>(s, chunk, tab, q, qh);
+        if (bb == 12) cw_lzf_parse_warp<12, 12>(s, chunk, tab, q, qh, qlen);
+        else if (bb == 25) cw_lzf_parse_warp<12, 13>(s, chunk, tab, q, qh, qlen);
+        else if (bb == 24) cw_lzf_parse_warp<11, 13>(s, chunk, tab, q, qh, qlen);
+        else if (bb == 13) cw_lzf_parse_warp<13, 13>(s, chunk, tab, q, qh, qlen);
+        else cw_lzf_parse_warp<0, 13>(s, chunk, tab, q, qh, qlen);
     }
     cw_lz4_q_drain(q, qh, lane);
     if (lane == 0) {
@@ -158,18 +160,19 @@ __device__ __forceinline__ void cw_lzf_parser_role(uint8_t *s, CwLz4Queue *q, ui
 // LZF emitter role: same protocol as cw_lz4_emitter_role
 __device__ __forceinline__ void cw_lzf_emitter_role(unsigned e, unsigned emitters, unsigned parsers, uint8_t *smem,
                                                     uint32_t slot_bytes, CwLz4Queue *queues, uint32_t chunk,
-                                                    uint8_t *__restrict__ dst, uint64_t stride, uint32_t *__restrict__ lens)
+                                                    uint8_t *__restrict__ dst, uint64_t stride, uint32_t *__restrict__ lens,
+                                                    uint32_t qlen = CW_LZ4_QLEN)
 {
     const unsigned lane = threadIdx.x & 31u;
     for (;;) {
         bool all_done = true;
         uint32_t did = 0;
         for (unsigned p = e; p < parsers; p += emitters) {
-            CwLz4Queue *q = &queues[p];
+            CwLz4Queue *q = cw_lz4_queue_at(queues, p, qlen);
             uint32_t d = 0;
             if (lane == 0) d = cw_ld_vol(&q->done);  // read BEFORE the head: done is set after the last publish
             d = __shfl_sync(0xffffffffu, d, 0);
-            const uint32_t cnt = cw_lzf_emit_batch(q, smem + (size_t)p * slot_bytes, chunk, chunk - 1u, dst, stride, lens);
+            const uint32_t cnt = cw_lzf_emit_batch(q, smem + (size_t)p * slot_bytes, chunk, chunk - 1u, dst, stride, lens, qlen);
             did += cnt;
             if (!(d && cnt == 0u)) all_done = false;
         }

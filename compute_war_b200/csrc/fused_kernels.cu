@@ -60,12 +60,19 @@ static int fused_emitters(bool fast)
     return v > 0 ? v : 2;
 }
 
+// records per parser -> emitter ring: LZF is short of shared memory (32: 7 parsers per SM at 8 KiB instead of 6)
+template <int CALG>
+__host__ __device__ constexpr uint32_t cw_fused_qlen()
+{
+    return CALG == CW_C_LZF ? 32u : CW_LZ4_QLEN;
+}
+
 template <int CALG>
 __host__ __device__ constexpr uint32_t cw_slot_bytes(uint32_t chunk)
 {
     return (CALG == CW_C_LZF ? ((chunk + 16u + 15u) & ~15u) + cw_lzf_table_bytes(cw_lzf_table_format(chunk))
                              : cw_lz4_chunk_pad(chunk) + (2u << (CALG == CW_C_LZ4 ? 13 : 12))) +
-           (uint32_t)sizeof(CwLz4Queue);
+           cw_lz4_queue_bytes(cw_fused_qlen<CALG>());
 }
 
 // "3;3,3" -> hash warp on scheduler 3, two emitters on scheduler 3 (tuning knob CW_ROLE_MAP; "0" = warp order)
@@ -99,22 +106,23 @@ __global__ void __launch_bounds__(CW_FUSED_MAX_THREADS, 1)
     {
         // slot_bytes excludes the queue: queues sit behind the slots
         CwLz4Queue *queues = reinterpret_cast<CwLz4Queue *>(smem + (size_t)parsers * slot_bytes);
-        if (warp < parsers && lane < 8u) reinterpret_cast<uint32_t *>(&queues[warp])[lane] = 0u;
+        constexpr uint32_t QL = cw_fused_qlen<CALG>();
+        CwLz4Queue *myq = cw_lz4_queue_at(queues, warp < parsers ? warp : 0u, QL);
+        if (warp < parsers && lane < 8u) reinterpret_cast<uint32_t *>(myq)[lane] = 0u;
         __syncthreads();
         if (warp < parsers) {
             if (CALG == CW_C_LZF)
-                cw_lzf_parser_role<ALIGNED>(smem + (size_t)warp * slot_bytes, &queues[warp], &bars[warp], src, chunk, n_chunks,
-                                            &work[0]);
+                cw_lzf_parser_role<ALIGNED>(smem + (size_t)warp * slot_bytes, myq, &bars[warp], src, chunk, n_chunks, &work[0], QL);
             else
-                cw_lz4_parser_role<(CALG == CW_C_LZ4 ? 13 : 12), ALIGNED, false>(smem + (size_t)warp * slot_bytes, &queues[warp],
-                                                                                 &bars[warp], src, chunk, n_chunks, &work[0]);
+                cw_lz4_parser_role<(CALG == CW_C_LZ4 ? 13 : 12), ALIGNED, false>(smem + (size_t)warp * slot_bytes, myq, &bars[warp],
+                                                                                 src, chunk, n_chunks, &work[0], QL);
             if (!CW_FUSED_TAIL_HELP) return;
         } else if (warp < parsers + emitters) {
             if (CALG == CW_C_LZF)
-                cw_lzf_emitter_role(warp - parsers, emitters, parsers, smem, slot_bytes, queues, chunk, dst, stride, lens);
+                cw_lzf_emitter_role(warp - parsers, emitters, parsers, smem, slot_bytes, queues, chunk, dst, stride, lens, QL);
             else
                 cw_lz4_emitter_role<false>(warp - parsers, emitters, parsers, smem, slot_bytes, queues, src, chunk, dst, stride,
-                                           lens);
+                                           lens, QL);
             if (!CW_FUSED_TAIL_HELP) return;
         }
     }
@@ -167,7 +175,7 @@ static cudaError_t launch_one(const CwDeviceInfo &dev, int max_dyn_smem, const C
 {
     auto kern = cw_fused_kernel<HALG, CALG, ALIGNED>;
     const uint32_t per = cw_slot_bytes<CALG>(chunk);  // slot + queue
-    const uint32_t slot = per - (uint32_t)sizeof(CwLz4Queue);
+    const uint32_t slot = per - cw_lz4_queue_bytes(cw_fused_qlen<CALG>());
     int parsers = max_dyn_smem / (int)per;
     if (parsers < 1) return cudaErrorInvalidValue;
     if (parsers > CW_FUSED_MAX_COMP_WARPS) parsers = CW_FUSED_MAX_COMP_WARPS;

@@ -38,19 +38,20 @@ template <int HASHLOG, bool ALIGNED, bool DIRECT>
 __global__ void __launch_bounds__((CW_LZ4_MAX_PARSERS + CW_LZ4_MAX_EMITTERS) * 32, 1)
     cw_lz4_kernel(const uint8_t *__restrict__ src, uint32_t chunk, uint64_t n_chunks, uint8_t *__restrict__ dst,
                   uint64_t stride, uint32_t *__restrict__ lens, unsigned long long *work, uint32_t slot_bytes,
-                  uint32_t parsers, uint32_t emitters, const __grid_constant__ CwRoleMap roles)
+                  uint32_t parsers, uint32_t emitters, const __grid_constant__ CwRoleMap roles, uint32_t qlen)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bars[32];
     const unsigned warp = roles.logical[threadIdx.x >> 5], lane = threadIdx.x & 31u;
     CwLz4Queue *queues = reinterpret_cast<CwLz4Queue *>(smem + (size_t)parsers * slot_bytes);
-    if (warp < parsers && lane < 8u) reinterpret_cast<uint32_t *>(&queues[warp])[lane] = 0u;  // head, tail, chunk, op, done
+    if (warp < parsers && lane < 8u) reinterpret_cast<uint32_t *>(cw_lz4_queue_at(queues, warp, qlen))[lane] = 0u;  // header
     __syncthreads();
     if (warp < parsers)
-        cw_lz4_parser_role<HASHLOG, ALIGNED, DIRECT>(smem + (size_t)warp * slot_bytes, &queues[warp], &bars[warp], src, chunk,
-                                                     n_chunks, work);
+        cw_lz4_parser_role<HASHLOG, ALIGNED, DIRECT>(smem + (size_t)warp * slot_bytes, cw_lz4_queue_at(queues, warp, qlen),
+                                                     &bars[warp], src, chunk, n_chunks, work, qlen);
     else
-        cw_lz4_emitter_role<DIRECT>(warp - parsers, emitters, parsers, smem, slot_bytes, queues, src, chunk, dst, stride, lens);
+        cw_lz4_emitter_role<DIRECT>(warp - parsers, emitters, parsers, smem, slot_bytes, queues, src, chunk, dst, stride, lens,
+                                    qlen);
 }
 
 static int g_lz4_max_smem = 0;
@@ -79,7 +80,11 @@ cudaError_t cw_launch_lz4(const CwDeviceInfo &dev, bool fast, const uint8_t *d_s
     // (measured: +0.8 % at 16 KB, +1.4 % at 32 KB, +2.7 % at 64 KB); bigger chunks keep the reference's table
     if (chunk > CW_LZ4_DIRECT_ABOVE) fast = false;
     const uint32_t slot = (direct ? 0u : cw_lz4_chunk_pad(chunk)) + (2u << (fast ? 12 : 13));
-    int parsers = g_lz4_max_smem / (int)(slot + sizeof(CwLz4Queue));
+    // a ring of 32 records instead of 64 where that buys another parser (4 KiB chunks: 11 instead of 10)
+    uint32_t qlen = CW_LZ4_QLEN;
+    if (g_lz4_max_smem / (int)(slot + cw_lz4_queue_bytes(32u)) > g_lz4_max_smem / (int)(slot + cw_lz4_queue_bytes(CW_LZ4_QLEN))) qlen = 32u;
+    if (const char *e = getenv("CW_LZ4_QLEN")) qlen = (uint32_t)atoi(e) == 32u ? 32u : CW_LZ4_QLEN;  // tuning knob
+    int parsers = g_lz4_max_smem / (int)(slot + cw_lz4_queue_bytes(qlen));
     if (parsers < 1) return cudaErrorInvalidValue;
     if (parsers > CW_LZ4_MAX_PARSERS) parsers = CW_LZ4_MAX_PARSERS;
     if (const char *e = getenv("CW_LZ4_PARSERS")) {  // tuning knob for the profiling scripts
@@ -91,7 +96,7 @@ cudaError_t cw_launch_lz4(const CwDeviceInfo &dev, bool fast, const uint8_t *d_s
     uint64_t ctas = (n + (uint64_t)parsers - 1) / (uint64_t)parsers;
     if (ctas > (uint64_t)dev.sm_count) ctas = (uint64_t)dev.sm_count;
     const dim3 grid((unsigned)ctas), block((parsers + emitters) * 32);
-    const size_t dyn = (size_t)parsers * (slot + sizeof(CwLz4Queue));
+    const size_t dyn = (size_t)parsers * (slot + cw_lz4_queue_bytes(qlen));
     // emitters share scheduler 3 (warp w issues from scheduler w % 4), parsers fill the others: parser-only schedulers
     // keep their instruction caches to the parser loop (CW_LZ4_ROLE_MAP=0: roles in warp order)
     static const bool grouped = [] {
@@ -101,7 +106,7 @@ cudaError_t cw_launch_lz4(const CwDeviceInfo &dev, bool fast, const uint8_t *d_s
     static const int none[4] = {3, 3, 3, 3}, es[4] = {3, 3, 3, 3};
     const CwRoleMap roles = make_role_map(parsers, emitters, 0, grouped ? none : nullptr, grouped ? es : nullptr);
 #define CW_GO(HL, AL, DI) \
-    cw_lz4_kernel<HL, AL, DI><<<grid, block, dyn, st>>>(d_src, chunk, n, d_dst, stride, d_lens, work, slot, (uint32_t)parsers, (uint32_t)emitters, roles)
+    cw_lz4_kernel<HL, AL, DI><<<grid, block, dyn, st>>>(d_src, chunk, n, d_dst, stride, d_lens, work, slot, (uint32_t)parsers, (uint32_t)emitters, roles, qlen)
     if (direct) {
         if (fast) CW_GO(12, true, true);
         else CW_GO(13, true, true);

@@ -126,7 +126,8 @@ CW_DEV void cw_lz4_copy_warp(uint8_t *out, uint32_t dst, const uint8_t *s, uint3
     if (lane < len - done) out[dst + done + lane] = cw_lz4_src8<DIRECT>(s, src + done + lane);
 }
 
-#define CW_LZ4_QLEN 64u        // records per parser ring (power of two)
+#define CW_LZ4_QLEN 64u  // records per parser ring (power of two); kernels short of shared memory run rings of 32:
+                         // the functions below take the ring length, and a queue then occupies cw_lz4_queue_bytes(qlen)
 #ifndef CW_LZ4_PUB_BATCH
 #define CW_LZ4_PUB_BATCH 16u // the parser makes its records visible to the emitter in batches of this many
 #endif
@@ -144,14 +145,20 @@ struct CwLz4Queue {
     uint32_t op;                 // emitter: bytes of that chunk written so far
     uint32_t done;               // parser has exited
     uint32_t pad[2];
-    uint32_t rec[CW_LZ4_QLEN][2];  // {anchor | cur << 16, cand | fwd << 16}
+    uint32_t rec[CW_LZ4_QLEN][2];  // {anchor | cur << 16, cand | fwd << 16}; only the first qlen entries exist in a short ring
 };
+CW_HOSTDEV uint32_t cw_lz4_queue_bytes(uint32_t qlen) { return 32u + 8u * qlen; }
+// queue p of an array of rings of qlen records each
+CW_DEV CwLz4Queue *cw_lz4_queue_at(CwLz4Queue *base, uint32_t p, uint32_t qlen)
+{
+    return reinterpret_cast<CwLz4Queue *>(reinterpret_cast<uint8_t *>(base) + (size_t)p * cw_lz4_queue_bytes(qlen));
+}
 
 // parser side: push one record; lane `writer` holds the values (qh = records pushed so far, tailc = cached tail)
 CW_DEV void cw_lz4_q_push(CwLz4Queue *q, uint32_t &qh, uint32_t &tailc, uint32_t a, uint32_t b, unsigned lane,
-                          unsigned writer)
+                          unsigned writer, uint32_t qlen = CW_LZ4_QLEN)
 {
-    if (qh - tailc >= CW_LZ4_QLEN) {  // ring looks full: publish what we have and wait for the emitter
+    if (qh - tailc >= qlen) {  // ring looks full: publish what we have and wait for the emitter
         cw_syncwarp();
         if (lane == 0) {
             cw_fence_cta();
@@ -161,20 +168,21 @@ CW_DEV void cw_lz4_q_push(CwLz4Queue *q, uint32_t &qh, uint32_t &tailc, uint32_t
             uint32_t t = 0;
             if (lane == 0) t = cw_ld_vol(&q->tail);
             tailc = cw_shfl(t, 0);
-            if (qh - tailc < CW_LZ4_QLEN) break;
+            if (qh - tailc < qlen) break;
             cw_spin();
         }
     }
     if (lane == writer) {
-        q->rec[qh & (CW_LZ4_QLEN - 1u)][0] = a;
-        q->rec[qh & (CW_LZ4_QLEN - 1u)][1] = b;
+        q->rec[qh & (qlen - 1u)][0] = a;
+        q->rec[qh & (qlen - 1u)][1] = b;
     }
     qh++;
 }
 // parser side: make room for cnt (<= 32) records that their lanes are about to write themselves
-CW_DEV void cw_lz4_q_reserve(CwLz4Queue *q, uint32_t qh, uint32_t &tailc, uint32_t cnt, unsigned lane)
+CW_DEV void cw_lz4_q_reserve(CwLz4Queue *q, uint32_t qh, uint32_t &tailc, uint32_t cnt, unsigned lane,
+                             uint32_t qlen = CW_LZ4_QLEN)
 {
-    if (qh + cnt - tailc <= CW_LZ4_QLEN) return;
+    if (qh + cnt - tailc <= qlen) return;
     cw_syncwarp();
     if (lane == 0) {
         cw_fence_cta();
@@ -184,7 +192,7 @@ CW_DEV void cw_lz4_q_reserve(CwLz4Queue *q, uint32_t qh, uint32_t &tailc, uint32
         uint32_t t = 0;
         if (lane == 0) t = cw_ld_vol(&q->tail);
         tailc = cw_shfl(t, 0);
-        if (qh + cnt - tailc <= CW_LZ4_QLEN) break;
+        if (qh + cnt - tailc <= qlen) break;
         cw_spin();
     }
 }
@@ -213,7 +221,7 @@ CW_DEV void cw_lz4_q_drain(CwLz4Queue *q, uint32_t qh, unsigned lane)
 // Returns the number of records consumed (same value in every lane).
 template <bool DIRECT>
 CW_DEV uint32_t cw_lz4_emit_batch(CwLz4Queue *q, const uint8_t *s, uint32_t n, uint8_t *dst_base, uint64_t stride,
-                                  uint32_t *lens)
+                                  uint32_t *lens, uint32_t qlen = CW_LZ4_QLEN)
 {
     const uint32_t nw = n >> 2;
     const unsigned lane = cw_lane();
@@ -235,7 +243,7 @@ CW_DEV uint32_t cw_lz4_emit_batch(CwLz4Queue *q, const uint8_t *s, uint32_t n, u
     const bool mine = lane < m;
     uint32_t anchor = 0, cur = 0, cnd = 0, fwd = 0;
     if (mine) {
-        const uint32_t r0 = q->rec[(tl + lane) & (CW_LZ4_QLEN - 1u)][0], r1 = q->rec[(tl + lane) & (CW_LZ4_QLEN - 1u)][1];
+        const uint32_t r0 = q->rec[(tl + lane) & (qlen - 1u)][0], r1 = q->rec[(tl + lane) & (qlen - 1u)][1];
         anchor = r0 & 0xffffu;
         cur = r0 >> 16;
         cnd = r1 & 0xffffu;
@@ -299,7 +307,8 @@ CW_DEV uint32_t cw_lz4_emit_batch(CwLz4Queue *q, const uint8_t *s, uint32_t n, u
 // table: zeroed u16[1 << HASHLOG] in shared memory.  qh: records pushed so far on this queue (kept by the
 // caller across chunks).  The caller sets q->chunk_lo/hi before and drains the queue before reusing s.
 template <int HASHLOG, bool DIRECT>
-CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwLz4Queue *q, uint32_t &qh)
+CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwLz4Queue *q, uint32_t &qh,
+                              uint32_t qlen = CW_LZ4_QLEN)
 {
     const uint32_t nw = n >> 2;
     const unsigned lane = cw_lane();
@@ -432,11 +441,11 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
                 }
                 if (chain) {
                     const uint32_t cnt = (uint32_t)cw_popc(chain), below = chain & lower;
-                    cw_lz4_q_reserve(q, qh, tailc, cnt, lane);
+                    cw_lz4_q_reserve(q, qh, tailc, cnt, lane, qlen);
                     // a record's anchor is the end of the chain match before it (the carried-in anchor for the first)
                     const uint32_t prev_de = cw_shfl(my_de, below ? (unsigned)(31 - cw_clz(below)) : lane);
                     if ((chain >> lane) & 1u) {
-                        const uint32_t k = (qh + (uint32_t)cw_popc(below)) & (CW_LZ4_QLEN - 1u);
+                        const uint32_t k = (qh + (uint32_t)cw_popc(below)) & (qlen - 1u);
                         q->rec[k][0] = (below ? base + prev_de : anchor0) | (pos << 16);
                         q->rec[k][1] = t | ((spec & 0x7fffffffu) << 16);
                     }
@@ -489,7 +498,7 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
                 spec_on = fwd < 28u;
                 // everything else about this sequence (backward extension, lengths, bytes) is the emitter's job;
                 // the matching lane itself holds the candidate, so it writes the record
-                cw_lz4_q_push(q, qh, tailc, anchor | (cur << 16), cand | (fwd << 16), lane, f);
+                cw_lz4_q_push(q, qh, tailc, anchor | (cur << 16), cand | (fwd << 16), lane, f, qlen);
                 anchor = e;
                 if (e >= mfl1) {  // "if (ip > mflimit) break" -> last literals
                     done = true;
@@ -531,6 +540,6 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
         }
     }
     // ---- end of chunk: the final literal run [anchor, n) ----
-    cw_lz4_q_push(q, qh, tailc, anchor | (CW_LZ4_REC_END << 16), 0u, lane, 0u);
+    cw_lz4_q_push(q, qh, tailc, anchor | (CW_LZ4_REC_END << 16), 0u, lane, 0u, qlen);
     cw_lz4_q_publish(q, qh, lane);
 }

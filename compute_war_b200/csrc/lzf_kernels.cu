@@ -38,18 +38,19 @@ template <bool ALIGNED>
 __global__ void __launch_bounds__((CW_LZF_MAX_WARPS + 3) * 32, 1)
     cw_lzf_kernel(const uint8_t *__restrict__ src, uint32_t chunk, uint64_t n_chunks, uint8_t *__restrict__ dst,
                   uint64_t stride, uint32_t *__restrict__ lens, unsigned long long *work, uint32_t slot_bytes, uint32_t parsers,
-                  uint32_t emitters)
+                  uint32_t emitters, uint32_t qlen)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bars[32];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     CwLz4Queue *queues = reinterpret_cast<CwLz4Queue *>(smem + (size_t)parsers * slot_bytes);
-    if (warp < parsers && lane < 8u) reinterpret_cast<uint32_t *>(&queues[warp])[lane] = 0u;
+    if (warp < parsers && lane < 8u) reinterpret_cast<uint32_t *>(cw_lz4_queue_at(queues, warp, qlen))[lane] = 0u;
     __syncthreads();
     if (warp < parsers)
-        cw_lzf_parser_role<ALIGNED>(smem + (size_t)warp * slot_bytes, &queues[warp], &bars[warp], src, chunk, n_chunks, work);
+        cw_lzf_parser_role<ALIGNED>(smem + (size_t)warp * slot_bytes, cw_lz4_queue_at(queues, warp, qlen), &bars[warp], src, chunk,
+                                    n_chunks, work, qlen);
     else
-        cw_lzf_emitter_role(warp - parsers, emitters, parsers, smem, slot_bytes, queues, chunk, dst, stride, lens);
+        cw_lzf_emitter_role(warp - parsers, emitters, parsers, smem, slot_bytes, queues, chunk, dst, stride, lens, qlen);
 }
 
 static int g_lzf_max_smem = 0;
@@ -68,7 +69,10 @@ cudaError_t cw_lzf_configure(const CwDeviceInfo &dev)
 cudaError_t cw_launch_lzf(const CwDeviceInfo &dev, const uint8_t *d_src, uint32_t chunk, uint64_t n, uint8_t *d_dst,
                           uint64_t stride, uint32_t *d_lens, unsigned long long *work, cudaStream_t st)
 {
-    const uint32_t slot = lzf_slot_bytes(chunk), per = slot + (uint32_t)sizeof(CwLz4Queue);
+    // rings of 32 records: LZF is the kernel shortest of shared memory (8 KiB chunks: 7 parsers per SM instead of 6)
+    uint32_t qlen = 32u;
+    if (const char *e = getenv("CW_LZ4_QLEN")) qlen = (uint32_t)atoi(e) == 32u ? 32u : CW_LZ4_QLEN;  // tuning knob
+    const uint32_t slot = lzf_slot_bytes(chunk), per = slot + cw_lz4_queue_bytes(qlen);
     int parsers = g_lzf_max_smem / (int)per;
     if (parsers < 1) return cudaErrorInvalidValue;
     if (parsers > CW_LZF_MAX_WARPS) parsers = CW_LZF_MAX_WARPS;
@@ -81,9 +85,9 @@ cudaError_t cw_launch_lzf(const CwDeviceInfo &dev, const uint8_t *d_src, uint32_
     const size_t dyn = (size_t)parsers * per;
     if (aligned)
         cw_lzf_kernel<true><<<(unsigned)ctas, threads, dyn, st>>>(d_src, chunk, n, d_dst, stride, d_lens, work, slot,
-                                                                  (uint32_t)parsers, (uint32_t)emitters);
+                                                                  (uint32_t)parsers, (uint32_t)emitters, qlen);
     else
         cw_lzf_kernel<false><<<(unsigned)ctas, threads, dyn, st>>>(d_src, chunk, n, d_dst, stride, d_lens, work, slot,
-                                                                   (uint32_t)parsers, (uint32_t)emitters);
+                                                                   (uint32_t)parsers, (uint32_t)emitters, qlen);
     return cudaGetLastError();
 }

@@ -86,7 +86,8 @@ CW_DEV void cw_lzf_table_init(uint16_t *tab)
 
 // BB: bucket bits (0 = the untagged format with 8192 buckets), RB: ring / position bits
 template <int BB, int RB>
-CW_DEV void cw_lzf_parse_warp(const uint8_t *s, uint32_t n, uint16_t *tab, CwLz4Queue *q, uint32_t &qh)
+CW_DEV void cw_lzf_parse_warp(const uint8_t *s, uint32_t n, uint16_t *tab, CwLz4Queue *q, uint32_t &qh,
+                              uint32_t qlen = CW_LZ4_QLEN)
 {
     constexpr bool TAGGED = BB != 0;
     constexpr bool VERIFY = TAGGED && BB < RB;            // the tag does not cover every slot bit above the bucket index
@@ -211,7 +212,7 @@ CW_DEV void cw_lzf_parse_warp(const uint8_t *s, uint32_t n, uint16_t *tab, CwLz4
             uint32_t len;
             if (maxlen > 16u) len = fm <= 18u ? fm : (fm < maxlen ? fm : (maxlen > 19u ? maxlen : 19u));
             else len = fm < maxlen ? fm : (maxlen > 3u ? maxlen : 3u);
-            cw_lz4_q_push(q, qh, tailc, anchor | (cur << 16), ref | (len << 16), lane, 0u);
+            cw_lz4_q_push(q, qh, tailc, anchor | (cur << 16), ref | (len << 16), lane, 0u, qlen);
             e = cur + len;
             anchor = e;
             if (e >= limit) {  // "if (ip >= in_end - 2) break"
@@ -267,7 +268,7 @@ CW_DEV void cw_lzf_parse_warp(const uint8_t *s, uint32_t n, uint16_t *tab, CwLz4
     }
     // liblzf's length rule can carry the last match to the very end of the input (anchor == n, 17 bits for a 64 KB
     // chunk), so the closing record keeps its anchor in the second word
-    cw_lz4_q_push(q, qh, tailc, CW_LZ4_REC_END << 16, anchor | (ended_by_match ? 0x80000000u : 0u), lane, 0u);
+    cw_lz4_q_push(q, qh, tailc, CW_LZ4_REC_END << 16, anchor | (ended_by_match ? 0x80000000u : 0u), lane, 0u, qlen);
     cw_lz4_q_publish(q, qh, lane);
 }
 
@@ -283,7 +284,7 @@ CW_DEV void cw_lzf_parse_warp(const uint8_t *s, uint32_t n, uint16_t *tab, CwLz4
 #define CW_LZF_LIT_SELF 32u  // literal runs up to this long (one run header) are copied by the recording lane itself
 
 CW_DEV uint32_t cw_lzf_emit_batch(CwLz4Queue *q, const uint8_t *s, uint32_t n, uint32_t out_len, uint8_t *dst_base,
-                                  uint64_t stride, uint32_t *lens)
+                                  uint64_t stride, uint32_t *lens, uint32_t qlen = CW_LZ4_QLEN)
 {
     const unsigned lane = cw_lane();
     uint32_t hd = 0, tl = 0;
@@ -305,7 +306,7 @@ CW_DEV uint32_t cw_lzf_emit_batch(CwLz4Queue *q, const uint8_t *s, uint32_t n, u
     uint32_t anchor = 0, cur = 0, ref = 0, len = 0;
     bool by_match = false;  // closing record: the last match ran into the end of the input
     if (mine) {
-        const uint32_t r0 = q->rec[(tl + lane) & (CW_LZ4_QLEN - 1u)][0], r1 = q->rec[(tl + lane) & (CW_LZ4_QLEN - 1u)][1];
+        const uint32_t r0 = q->rec[(tl + lane) & (qlen - 1u)][0], r1 = q->rec[(tl + lane) & (qlen - 1u)][1];
         anchor = r0 & 0xffffu;
         cur = r0 >> 16;
         ref = r1 & 0xffffu;

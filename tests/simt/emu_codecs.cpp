@@ -11,6 +11,10 @@
 #define HAVE_LZF 1
 #endif
 
+// ring length the parser / emitter pairs below run with (the kernels use 64, or 32 where shared memory is short)
+static uint32_t g_qlen = CW_LZ4_QLEN;
+extern "C" void emu_set_qlen(uint32_t qlen) { g_qlen = qlen == 32u ? 32u : CW_LZ4_QLEN; }
+
 struct Job {
     const uint8_t *s;
     uint32_t n;
@@ -41,10 +45,10 @@ static void lz4_block_body(void *a, int warp)
     if (warp == 0) {
         uint32_t qh = 0;
         if (j->direct) {
-            if (j->hashlog == 12) cw_lz4_parse_warp<12, true>(j->s, j->n, j->table, j->q, qh);
-            else cw_lz4_parse_warp<13, true>(j->s, j->n, j->table, j->q, qh);
-        } else if (j->hashlog == 12) cw_lz4_parse_warp<12, false>(j->s, j->n, j->table, j->q, qh);
-        else cw_lz4_parse_warp<13, false>(j->s, j->n, j->table, j->q, qh);
+            if (j->hashlog == 12) cw_lz4_parse_warp<12, true>(j->s, j->n, j->table, j->q, qh, g_qlen);
+            else cw_lz4_parse_warp<13, true>(j->s, j->n, j->table, j->q, qh, g_qlen);
+        } else if (j->hashlog == 12) cw_lz4_parse_warp<12, false>(j->s, j->n, j->table, j->q, qh, g_qlen);
+        else cw_lz4_parse_warp<13, false>(j->s, j->n, j->table, j->q, qh, g_qlen);
         cw_lz4_q_drain(j->q, qh, lane);
         if (lane == 0) {
             cw_fence_cta();
@@ -55,8 +59,8 @@ static void lz4_block_body(void *a, int warp)
             uint32_t d = 0;
             if (lane == 0) d = cw_ld_vol(&j->q->done);
             d = cw_shfl(d, 0);
-            const uint32_t cnt = j->direct ? cw_lz4_emit_batch<true>(j->q, j->s, j->n, j->out, 0, j->lens)
-                                           : cw_lz4_emit_batch<false>(j->q, j->s, j->n, j->out, 0, j->lens);
+            const uint32_t cnt = j->direct ? cw_lz4_emit_batch<true>(j->q, j->s, j->n, j->out, 0, j->lens, g_qlen)
+                                           : cw_lz4_emit_batch<false>(j->q, j->s, j->n, j->out, 0, j->lens, g_qlen);
             if (d && cnt == 0) break;
             if (!cnt) cw_spin();
         }
@@ -117,11 +121,11 @@ static void lzf_block_body(void *a, int warp)
         else if (j->tagged == 13) cw_lzf_table_init<13>(j->tab);
         else cw_lzf_table_init<0>(j->tab);
         cw_syncwarp();
-        if (j->tagged == 12) cw_lzf_parse_warp<12, 12>(j->s, j->n, j->tab, j->q, qh);
-        else if (j->tagged == 25) cw_lzf_parse_warp<12, 13>(j->s, j->n, j->tab, j->q, qh);
-        else if (j->tagged == 24) cw_lzf_parse_warp<11, 13>(j->s, j->n, j->tab, j->q, qh);
-        else if (j->tagged == 13) cw_lzf_parse_warp<13, 13>(j->s, j->n, j->tab, j->q, qh);
-        else cw_lzf_parse_warp<0, 13>(j->s, j->n, j->tab, j->q, qh);
+        if (j->tagged == 12) cw_lzf_parse_warp<12, 12>(j->s, j->n, j->tab, j->q, qh, g_qlen);
+        else if (j->tagged == 25) cw_lzf_parse_warp<12, 13>(j->s, j->n, j->tab, j->q, qh, g_qlen);
+        else if (j->tagged == 24) cw_lzf_parse_warp<11, 13>(j->s, j->n, j->tab, j->q, qh, g_qlen);
+        else if (j->tagged == 13) cw_lzf_parse_warp<13, 13>(j->s, j->n, j->tab, j->q, qh, g_qlen);
+        else cw_lzf_parse_warp<0, 13>(j->s, j->n, j->tab, j->q, qh, g_qlen);
         cw_lz4_q_drain(j->q, qh, lane);
         if (lane == 0) {
             cw_fence_cta();
@@ -132,7 +136,7 @@ static void lzf_block_body(void *a, int warp)
             uint32_t d = 0;
             if (lane == 0) d = cw_ld_vol(&j->q->done);
             d = cw_shfl(d, 0);
-            const uint32_t cnt = cw_lzf_emit_batch(j->q, j->s, j->n, j->out_cap, j->out, 0, j->lens);
+            const uint32_t cnt = cw_lzf_emit_batch(j->q, j->s, j->n, j->out_cap, j->out, 0, j->lens, g_qlen);
             if (d && cnt == 0) break;
             if (!cnt) cw_spin();
         }

@@ -59,6 +59,25 @@ def test_device_hash_source_on_host(hosthash):
         assert out.tobytes() == O.sha256(bb), n
 
 
+def test_short_rings(emu, golden):
+    """the kernels that are short of shared memory run parser -> emitter rings of 32 records instead of 64"""
+    emu.emu_set_qlen(32)
+    try:
+        blob = golden["blob"]
+        for c in [blob[:8192].copy(), blob[20000:24096].copy(), O.synth(8192, 3, 1), blob[:65536].copy()]:
+            n = len(c)
+            for alg, fn in ((O.COMP_LZ4, None), (O.COMP_LZF, None)):
+                blocks, lens = O.compress_chunks(alg, c, n)
+                out = np.zeros(n + n // 255 + 64, np.uint8)
+                if alg == O.COMP_LZ4:
+                    r = emu.emu_lz4_compress(c.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p))
+                else:
+                    r = emu.emu_lzf_compress(c.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p), n - 1)
+                assert r == lens[0] and (out[:r] == blocks[0, :r]).all(), (alg, n)
+    finally:
+        emu.emu_set_qlen(64)
+
+
 def _cases(golden, small):
     rng = np.random.default_rng(3)
     cases = []

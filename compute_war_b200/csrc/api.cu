@@ -56,12 +56,13 @@ struct cw_ctx {
     CwSkeinIV iv{};
     cudaStream_t stream = nullptr;
     std::atomic<uint64_t> launches{0};
+    // work counters of the persistent kernels: a ring of kWorkRing pairs.  Launches on different caller streams are not
+    // ordered with each other, so every entry carries an event recorded behind the launch that used it; an entry is
+    // handed out again only after that launch has finished
     unsigned long long *d_work = nullptr;
+    cudaEvent_t work_ev[kWorkRing] = {};
+    bool work_used[kWorkRing] = {};
     int work_next = 0;
-    unsigned long long *d_pack = nullptr;  // scratch of cw_pack_dev (tile totals)
-    size_t pack_cap = 0;
-    uint32_t *d_dedup = nullptr;  // slot table of cw_dedup_dev
-    size_t dedup_slots = 0;
     std::mutex mu;       // guards work ring, profiling lists, last_error
     std::mutex host_mu;  // one host-buffer pipeline at a time per context
     std::string last_error;
@@ -77,7 +78,8 @@ struct cw_ctx {
     std::mutex q_mu;
     std::condition_variable q_cv, done_cv;
     std::deque<Job> queue;
-    std::map<cw_ticket, int> finished;
+    std::map<cw_ticket, int> finished;  // status of completed jobs nobody has waited for yet
+    cw_ticket done_upto = 0;            // jobs complete in ticket order (one worker)
     cw_ticket next_ticket = 1;
     bool stop = false;
 };
@@ -107,12 +109,24 @@ int check_common(const cw_ctx *ctx, size_t chunk, size_t n, const void *src)
     return CW_OK;
 }
 
-unsigned long long *next_work(cw_ctx *ctx)
+// a pair of zeroed-by-the-caller work counters for one launch on stream st; work_done() must follow the launch
+struct WorkSlot {
+    unsigned long long *p;
+    int idx;
+};
+WorkSlot next_work(cw_ctx *ctx)
 {
     std::lock_guard<std::mutex> g(ctx->mu);
-    unsigned long long *p = ctx->d_work + 2 * ctx->work_next;  // two counters per launch
-    ctx->work_next = (ctx->work_next + 1) % kWorkRing;
-    return p;
+    const int i = ctx->work_next;
+    ctx->work_next = (i + 1) % kWorkRing;
+    if (ctx->work_used[i]) cudaEventSynchronize(ctx->work_ev[i]);  // kWorkRing launches later: normally long finished
+    ctx->work_used[i] = false;
+    return WorkSlot{ctx->d_work + 2 * i, i};  // two counters per launch
+}
+void work_done(cw_ctx *ctx, const WorkSlot &w, cudaStream_t st)
+{
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (cudaEventRecord(ctx->work_ev[w.idx], st) == cudaSuccess) ctx->work_used[w.idx] = true;
 }
 
 struct ProfScope {
@@ -162,20 +176,22 @@ int do_compress_dev(cw_ctx *ctx, cw_comp_alg alg, cw_mode mode, const void *d_sr
     if (stride < cw_compress_bound(alg, chunk)) return CW_ERR_ARG;
     if (n == 0) return CW_OK;
     if (alg == CW_COMP_LZ4) {
-        unsigned long long *w = next_work(ctx);
-        CW_CUDA(ctx, cudaMemsetAsync(w, 0, sizeof *w, st));
+        const WorkSlot w = next_work(ctx);
+        CW_CUDA(ctx, cudaMemsetAsync(w.p, 0, sizeof *w.p, st));
         ProfScope ps(ctx, st);
         CW_CUDA(ctx, cw_launch_lz4(ctx->dev, mode == CW_MODE_FAST, (const uint8_t *)d_src, (uint32_t)chunk, n, (uint8_t *)d_dst, stride, d_lens,
-                                   w, st));
+                                   w.p, st));
+        work_done(ctx, w, st);
         ctx->launches++;
         return CW_OK;
     }
     if (alg == CW_COMP_LZF) {
-        unsigned long long *w = next_work(ctx);
-        CW_CUDA(ctx, cudaMemsetAsync(w, 0, sizeof *w, st));
+        const WorkSlot w = next_work(ctx);
+        CW_CUDA(ctx, cudaMemsetAsync(w.p, 0, sizeof *w.p, st));
         ProfScope ps(ctx, st);
         CW_CUDA(ctx, cw_launch_lzf(ctx->dev, (const uint8_t *)d_src, (uint32_t)chunk, n, (uint8_t *)d_dst, stride, d_lens,
-                                   w, st));
+                                   w.p, st));
+        work_done(ctx, w, st);
         ctx->launches++;
         return CW_OK;
     }
@@ -188,11 +204,12 @@ int do_fused_dev(cw_ctx *ctx, cw_hash_alg halg, cw_comp_alg calg, cw_mode mode, 
     if ((int)halg < 0 || (int)halg > 2 || (int)calg < 0 || (int)calg > 1 || (int)mode < 0 || (int)mode > 1) return CW_ERR_ARG;
     if (stride < cw_compress_bound(calg, chunk)) return CW_ERR_ARG;
     if (n == 0) return CW_OK;
-    unsigned long long *w = next_work(ctx);
-    CW_CUDA(ctx, cudaMemsetAsync(w, 0, 2 * sizeof *w, st));
+    const WorkSlot w = next_work(ctx);
+    CW_CUDA(ctx, cudaMemsetAsync(w.p, 0, 2 * sizeof *w.p, st));
     ProfScope ps(ctx, st);
     CW_CUDA(ctx, cw_launch_fused(ctx->dev, (int)halg, (int)calg, mode == CW_MODE_FAST, ctx->iv, (const uint8_t *)d_src, (uint32_t)chunk, n,
-                                 (uint8_t *)d_dig, (uint8_t *)d_dst, stride, d_lens, w, st));
+                                 (uint8_t *)d_dig, (uint8_t *)d_dst, stride, d_lens, w.p, st));
+    work_done(ctx, w, st);
     ctx->launches++;
     return CW_OK;
 }
@@ -287,12 +304,15 @@ void worker_loop(cw_ctx *ctx)
             ctx->queue.pop_front();
         }
         int rc = host_pass(ctx, true, true, j.halg, j.calg, j.mode, j.src, j.chunk, j.n, j.digests, j.dst, j.stride, j.lens);
-        if (j.cb) j.cb(j.ticket, rc, j.user);
         {
+            // the status is visible before the callback runs, so the callback itself may call cw_wait; a job with a
+            // callback keeps no entry (its status was delivered), so callback-only callers do not grow the map
             std::lock_guard<std::mutex> lk(ctx->q_mu);
-            ctx->finished[j.ticket] = rc;
+            if (!j.cb) ctx->finished[j.ticket] = rc;
+            ctx->done_upto = j.ticket;
         }
         ctx->done_cv.notify_all();
+        if (j.cb) j.cb(j.ticket, rc, j.user);
     }
 }
 
@@ -340,6 +360,7 @@ int cw_init(cw_ctx **out, int device)
     cw_make_skein_iv(&ctx->iv);
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_work, 2 * kWorkRing * sizeof(unsigned long long)) == cudaSuccess;
+    for (int i = 0; ok && i < kWorkRing; i++) ok = cudaEventCreateWithFlags(&ctx->work_ev[i], cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; ok && i < kSlots; i++) {
         ok = cudaStreamCreateWithFlags(&ctx->slots[i].st, cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->slots[i].done, cudaEventDisableTiming) == cudaSuccess;
@@ -381,8 +402,8 @@ void cw_shutdown(cw_ctx *ctx)
     }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->d_work) cudaFree(ctx->d_work);
-    if (ctx->d_pack) cudaFree(ctx->d_pack);
-    if (ctx->d_dedup) cudaFree(ctx->d_dedup);
+    for (auto e : ctx->work_ev)
+        if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -506,9 +527,11 @@ int cw_wait(cw_ctx *ctx, cw_ticket ticket)
     if (!ctx) return CW_ERR_ARG;
     std::unique_lock<std::mutex> lk(ctx->q_mu);
     if (ticket == 0 || ticket >= ctx->next_ticket) return CW_ERR_ARG;
-    ctx->done_cv.wait(lk, [&] { return ctx->finished.count(ticket) != 0; });
-    int rc = ctx->finished[ticket];
-    ctx->finished.erase(ticket);
+    ctx->done_cv.wait(lk, [&] { return ctx->done_upto >= ticket; });
+    auto it = ctx->finished.find(ticket);
+    if (it == ctx->finished.end()) return CW_ERR_ARG;  // already waited for, or its status went to the completion callback
+    const int rc = it->second;
+    ctx->finished.erase(it);
     return rc;
 }
 
@@ -522,11 +545,12 @@ int cw_decompress_dev(cw_ctx *ctx, cw_comp_alg alg, const void *d_blocks, size_t
     if (n == 0) return CW_OK;
     CW_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-    unsigned long long *w = next_work(ctx);
-    CW_CUDA(ctx, cudaMemsetAsync(w, 0, sizeof *w, st));
+    const WorkSlot w = next_work(ctx);
+    CW_CUDA(ctx, cudaMemsetAsync(w.p, 0, sizeof *w.p, st));
     ProfScope ps(ctx, st);
     CW_CUDA(ctx, cw_launch_decode(ctx->dev, (int)alg, (const uint8_t *)d_blocks, stride, d_lens, (uint32_t)chunk, n,
-                                  (uint8_t *)d_out, d_out_lens, w, st));
+                                  (uint8_t *)d_out, d_out_lens, w.p, st));
+    work_done(ctx, w, st);
     ctx->launches++;
     return CW_OK;
 }
@@ -573,20 +597,18 @@ int cw_pack_dev(cw_ctx *ctx, const void *d_blocks, size_t stride, const uint32_t
     if (n == 0) return CW_OK;
     CW_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    // the tile totals live in a per-call allocation ordered on the caller's stream (stream-ordered allocator), so calls
+    // on different streams or from different threads never share scratch
     const size_t need = ((n + 1023) / 1024 + 1) * sizeof(unsigned long long);
-    {
-        std::lock_guard<std::mutex> g(ctx->mu);
-        if (ctx->pack_cap < need) {
-            if (ctx->d_pack) cudaFree(ctx->d_pack);
-    if (ctx->d_dedup) cudaFree(ctx->d_dedup);
-            ctx->d_pack = nullptr;
-            ctx->pack_cap = 0;
-            if (cudaMalloc(&ctx->d_pack, need) != cudaSuccess) return CW_ERR_NOMEM;
-            ctx->pack_cap = need;
-        }
+    unsigned long long *scratch = nullptr;
+    if (cudaMallocAsync(&scratch, need, st) != cudaSuccess) {
+        cudaGetLastError();
+        return CW_ERR_NOMEM;
     }
-    CW_CUDA(ctx, cw_launch_pack((const uint8_t *)d_blocks, stride, d_lens, (const uint8_t *)d_src, (uint32_t)chunk, n,
-                                (uint8_t *)d_packed, packed_cap, (unsigned long long *)d_offsets, ctx->d_pack, st));
+    const cudaError_t le = cw_launch_pack((const uint8_t *)d_blocks, stride, d_lens, (const uint8_t *)d_src, (uint32_t)chunk, n,
+                                          (uint8_t *)d_packed, packed_cap, (unsigned long long *)d_offsets, scratch, st);
+    cudaFreeAsync(scratch, st);
+    if (le != cudaSuccess) return fail(ctx, le, "cw_launch_pack");
     ctx->launches += 3;
     return CW_OK;
 }
@@ -656,18 +678,16 @@ int cw_dedup_dev(cw_ctx *ctx, const void *d_digests, size_t D, size_t n, uint32_
     CW_CUDA(ctx, cudaSetDevice(ctx->device));
     size_t slots = 1024;
     while (slots < 2 * n) slots <<= 1;
-    {
-        std::lock_guard<std::mutex> g(ctx->mu);
-        if (ctx->dedup_slots < slots) {
-            if (ctx->d_dedup) cudaFree(ctx->d_dedup);
-            ctx->d_dedup = nullptr;
-            ctx->dedup_slots = 0;
-            if (cudaMalloc(&ctx->d_dedup, slots * sizeof(uint32_t)) != cudaSuccess) return CW_ERR_NOMEM;
-            ctx->dedup_slots = slots;
-        }
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    uint32_t *table = nullptr;  // per-call slot table, ordered on the caller's stream (see cw_pack_dev)
+    if (cudaMallocAsync(&table, slots * sizeof(uint32_t), st) != cudaSuccess) {
+        cudaGetLastError();
+        return CW_ERR_NOMEM;
     }
-    CW_CUDA(ctx, cw_launch_dedup((const uint8_t *)d_digests, (uint32_t)D, n, ctx->d_dedup, (uint32_t)slots, d_first,
-                                 (unsigned long long *)d_n_unique, stream ? (cudaStream_t)stream : ctx->stream));
+    const cudaError_t le = cw_launch_dedup((const uint8_t *)d_digests, (uint32_t)D, n, table, (uint32_t)slots, d_first,
+                                           (unsigned long long *)d_n_unique, st);
+    cudaFreeAsync(table, st);
+    if (le != cudaSuccess) return fail(ctx, le, "cw_launch_dedup");
     if (n) ctx->launches += 2;
     return CW_OK;
 }

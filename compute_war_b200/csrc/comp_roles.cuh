@@ -3,6 +3,7 @@
 // (lz4_warp.cuh).  Used by lz4_kernels.cu and fused_kernels.cu.
 #pragma once
 #include "lz4_warp.cuh"
+#include "lz4_fast.cuh"
 #include "lzf_warp.cuh"
 #include "stage.cuh"
 
@@ -10,7 +11,8 @@ __host__ __device__ constexpr uint32_t cw_lz4_chunk_pad(uint32_t chunk) { return
 
 // LZ4 parser role.  s: this warp's slot [chunk | pad | table] (DIRECT: [table] only, the chunk is read where it
 // lies in global memory); q: this warp's queue (zeroed by the caller before the CTA-wide barrier).
-template <int HASHLOG, bool ALIGNED, bool DIRECT>
+// FAST: the window-parallel parse of lz4_fast.cuh instead of the reference's sequential parse.
+template <int HASHLOG, bool ALIGNED, bool DIRECT, bool FAST = false>
 __device__ __forceinline__ void cw_lz4_parser_role(uint8_t *s, CwLz4Queue *q, uint64_t *bar, const uint8_t *__restrict__ src,
                                                    uint32_t chunk, uint64_t n_chunks, unsigned long long *work,
                                                    uint32_t qlen = CW_LZ4_QLEN)
@@ -33,7 +35,8 @@ __device__ __forceinline__ void cw_lz4_parser_role(uint8_t *s, CwLz4Queue *q, ui
                 q->chunk_hi = (uint32_t)(g >> 32);
             }
             __syncwarp();
-            cw_lz4_parse_warp<HASHLOG, true>(src + g * chunk, chunk, table, q, qh, qlen);
+            if (FAST) cw_lz4f_parse_warp<HASHLOG, true>(src + g * chunk, chunk, table, q, qh, qlen);
+            else cw_lz4_parse_warp<HASHLOG, true>(src + g * chunk, chunk, table, q, qh, qlen);
         }
         cw_lz4_q_drain(q, qh, lane);
         if (lane == 0) {
@@ -72,7 +75,8 @@ __device__ __forceinline__ void cw_lz4_parser_role(uint8_t *s, CwLz4Queue *q, ui
             for (uint32_t i = lane; i < chunk; i += 32u) s[i] = gp[i];
         }
         __syncwarp();
-        cw_lz4_parse_warp<HASHLOG, false>(s, chunk, table, q, qh, qlen);
+        if (FAST) cw_lz4f_parse_warp<HASHLOG, false>(s, chunk, table, q, qh, qlen);
+        else cw_lz4_parse_warp<HASHLOG, false>(s, chunk, table, q, qh, qlen);
     }
     cw_lz4_q_drain(q, qh, lane);
     if (lane == 0) {

@@ -28,6 +28,7 @@ CW_DEV void cw_syncwarp() { __syncwarp(); }
 CW_DEV int cw_ffs(uint32_t v) { return __ffs(v); }       // 1-based, 0 if none
 CW_DEV int cw_clz(uint32_t v) { return __clz(v); }
 CW_DEV int cw_popc(uint32_t v) { return __popc(v); }
+CW_DEV uint32_t cw_brev(uint32_t v) { return __brev(v); }
 CW_DEV uint32_t cw_funnel_r(uint32_t lo, uint32_t hi, unsigned sh) { return __funnelshift_r(lo, hi, sh); }
 // read-only global loads
 CW_DEV uint32_t cw_ldg32(const uint32_t *p) { return __ldg(p); }

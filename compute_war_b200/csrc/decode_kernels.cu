@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(CW_DEC_MAX_WARPS * 32, 1)
         if (len == 0u && alg == 1) {  // LZF "stored raw"
             for (uint32_t i = lane; i < chunk; i += 32u) o[i] = b[i];
             got = chunk;
-        } else if (len > in_cap) {
+        } else if (len > in_cap || (uint64_t)len > stride) {  // longer than the codec's bound or than its own slot: malformed
             got = 0u;
         } else {
             if (((reinterpret_cast<uintptr_t>(b) & 3u) == 0)) {

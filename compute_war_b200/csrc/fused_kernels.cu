@@ -46,7 +46,16 @@ static int fused_hash_warps(bool fast)
     return v > 0 ? v : (fast ? 2 : CW_FUSED_HASH_WARPS_DEFAULT);
 }
 
-enum { CW_C_LZ4 = 0, CW_C_LZF = 1, CW_C_LZ4_FAST = 2 };  // LZ4 with the reference's 13-bit table / LZF / LZ4 with a 12-bit table
+// compressor variants of the fused kernel: LZ4 compat (the reference's parse, 13-bit table, chunk staged) / LZF /
+// LZ4 fast (window-parallel parse of lz4_fast.cuh) with a 12-bit and a 13-bit table / the two LZ4 modes for chunks
+// > 16 KiB, which are read where they lie (DIRECT; fast mode then uses a 14-bit table)
+enum { CW_C_LZ4 = 0, CW_C_LZF = 1, CW_C_LZ4_FAST = 2, CW_C_LZ4_FAST13 = 3, CW_C_LZ4_DIRECT = 4, CW_C_LZ4_FAST_DIRECT = 5 };
+__host__ __device__ constexpr bool cw_c_direct(int c) { return c == CW_C_LZ4_DIRECT || c == CW_C_LZ4_FAST_DIRECT; }
+__host__ __device__ constexpr bool cw_c_fast(int c) { return c == CW_C_LZ4_FAST || c == CW_C_LZ4_FAST13 || c == CW_C_LZ4_FAST_DIRECT; }
+__host__ __device__ constexpr int cw_c_hashlog(int c)
+{
+    return c == CW_C_LZ4_FAST ? 12 : c == CW_C_LZ4_FAST_DIRECT ? 14 : 13;
+}
 
 #define CW_FUSED_EMITTERS_DEFAULT 3  // emitter warps per CTA
 static int fused_emitters(bool fast)
@@ -71,7 +80,7 @@ template <int CALG>
 __host__ __device__ constexpr uint32_t cw_slot_bytes(uint32_t chunk)
 {
     return (CALG == CW_C_LZF ? ((chunk + 16u + 15u) & ~15u) + cw_lzf_table_bytes(cw_lzf_table_format(chunk))
-                             : cw_lz4_chunk_pad(chunk) + (2u << (CALG == CW_C_LZ4 ? 13 : 12))) +
+                             : (cw_c_direct(CALG) ? 0u : cw_lz4_chunk_pad(chunk)) + (2u << cw_c_hashlog(CALG))) +
            cw_lz4_queue_bytes(cw_fused_qlen<CALG>());
 }
 
@@ -114,15 +123,15 @@ __global__ void __launch_bounds__(CW_FUSED_MAX_THREADS, 1)
             if (CALG == CW_C_LZF)
                 cw_lzf_parser_role<ALIGNED>(smem + (size_t)warp * slot_bytes, myq, &bars[warp], src, chunk, n_chunks, &work[0], QL);
             else
-                cw_lz4_parser_role<(CALG == CW_C_LZ4 ? 13 : 12), ALIGNED, false>(smem + (size_t)warp * slot_bytes, myq, &bars[warp],
-                                                                                 src, chunk, n_chunks, &work[0], QL);
+                cw_lz4_parser_role<cw_c_hashlog(CALG), ALIGNED, cw_c_direct(CALG), cw_c_fast(CALG)>(
+                    smem + (size_t)warp * slot_bytes, myq, &bars[warp], src, chunk, n_chunks, &work[0], QL);
             if (!CW_FUSED_TAIL_HELP) return;
         } else if (warp < parsers + emitters) {
             if (CALG == CW_C_LZF)
                 cw_lzf_emitter_role(warp - parsers, emitters, parsers, smem, slot_bytes, queues, chunk, dst, stride, lens, QL);
             else
-                cw_lz4_emitter_role<false>(warp - parsers, emitters, parsers, smem, slot_bytes, queues, src, chunk, dst, stride,
-                                           lens, QL);
+                cw_lz4_emitter_role<cw_c_direct(CALG)>(warp - parsers, emitters, parsers, smem, slot_bytes, queues, src, chunk, dst,
+                                                       stride, lens, QL);
             if (!CW_FUSED_TAIL_HELP) return;
         }
     }
@@ -179,11 +188,11 @@ static cudaError_t launch_one(const CwDeviceInfo &dev, int max_dyn_smem, const C
     int parsers = max_dyn_smem / (int)per;
     if (parsers < 1) return cudaErrorInvalidValue;
     if (parsers > CW_FUSED_MAX_COMP_WARPS) parsers = CW_FUSED_MAX_COMP_WARPS;
-    int emitters = fused_emitters(CALG == CW_C_LZ4_FAST);
+    int emitters = fused_emitters(cw_c_fast(CALG));
     if (emitters > parsers) emitters = parsers;
     uint64_t ctas = (n + (uint64_t)parsers - 1) / (uint64_t)parsers;
     if (ctas > (uint64_t)dev.sm_count) ctas = (uint64_t)dev.sm_count;
-    const int hw = fused_hash_warps(CALG == CW_C_LZ4_FAST);
+    const int hw = fused_hash_warps(cw_c_fast(CALG));
     kern<<<(unsigned)ctas, (parsers + emitters + hw) * 32, (size_t)parsers * per, st>>>(
         iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, slot, (uint32_t)parsers, (uint32_t)emitters,
         fused_role_map(CALG, parsers, emitters, hw));
@@ -209,15 +218,16 @@ cudaError_t cw_fused_configure(const CwDeviceInfo &dev)
 #define CW_CFG(H, C)                                                  \
     if (e == cudaSuccess) e = configure_one<H, C, true>(m);           \
     if (e == cudaSuccess) e = configure_one<H, C, false>(m);
-    CW_CFG(CW_K_SKEIN512, CW_C_LZ4)
-    CW_CFG(CW_K_SKEIN512, CW_C_LZF)
-    CW_CFG(CW_K_SKEIN512, CW_C_LZ4_FAST)
-    CW_CFG(CW_K_SKEIN256_128, CW_C_LZ4)
-    CW_CFG(CW_K_SKEIN256_128, CW_C_LZF)
-    CW_CFG(CW_K_SKEIN256_128, CW_C_LZ4_FAST)
-    CW_CFG(CW_K_SHA256, CW_C_LZ4)
-    CW_CFG(CW_K_SHA256, CW_C_LZF)
-    CW_CFG(CW_K_SHA256, CW_C_LZ4_FAST)
+#define CW_CFG_D(H, C) \
+    if (e == cudaSuccess) e = configure_one<H, C, true>(m);
+#define CW_CFG_H(H)                                                                                                    \
+    CW_CFG(H, CW_C_LZ4) CW_CFG(H, CW_C_LZF) CW_CFG(H, CW_C_LZ4_FAST) CW_CFG(H, CW_C_LZ4_FAST13) CW_CFG_D(H, CW_C_LZ4_DIRECT) \
+        CW_CFG_D(H, CW_C_LZ4_FAST_DIRECT)
+    CW_CFG_H(CW_K_SKEIN512)
+    CW_CFG_H(CW_K_SKEIN256_128)
+    CW_CFG_H(CW_K_SHA256)
+#undef CW_CFG_H
+#undef CW_CFG_D
 #undef CW_CFG
     return e;
 }
@@ -228,14 +238,19 @@ static cudaError_t launch_h(int calg, bool aligned, const CwDeviceInfo &dev, con
                             unsigned long long *work, cudaStream_t st)
 {
     const int m = g_fused_max_smem;
-    if (calg == CW_C_LZ4_FAST)
-        return aligned ? launch_one<HALG, CW_C_LZ4_FAST, true>(dev, m, iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, st)
-                       : launch_one<HALG, CW_C_LZ4_FAST, false>(dev, m, iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, st);
-    if (calg == CW_C_LZ4)
-        return aligned ? launch_one<HALG, CW_C_LZ4, true>(dev, m, iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, st)
-                       : launch_one<HALG, CW_C_LZ4, false>(dev, m, iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, st);
-    return aligned ? launch_one<HALG, CW_C_LZF, true>(dev, m, iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, st)
-                   : launch_one<HALG, CW_C_LZF, false>(dev, m, iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, st);
+#define CW_ARGS dev, m, iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, st
+#define CW_BOTH(C) return aligned ? launch_one<HALG, C, true>(CW_ARGS) : launch_one<HALG, C, false>(CW_ARGS)
+    switch (calg) {
+    case CW_C_LZ4_FAST: CW_BOTH(CW_C_LZ4_FAST);
+    case CW_C_LZ4_FAST13: CW_BOTH(CW_C_LZ4_FAST13);
+    case CW_C_LZ4: CW_BOTH(CW_C_LZ4);
+    case CW_C_LZF: CW_BOTH(CW_C_LZF);
+    case CW_C_LZ4_DIRECT: return launch_one<HALG, CW_C_LZ4_DIRECT, true>(CW_ARGS);
+    case CW_C_LZ4_FAST_DIRECT: return launch_one<HALG, CW_C_LZ4_FAST_DIRECT, true>(CW_ARGS);
+    }
+#undef CW_BOTH
+#undef CW_ARGS
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t cw_launch_fused(const CwDeviceInfo &dev, int halg, int calg, bool fast, const CwSkeinIV &iv, const uint8_t *d_src,
@@ -243,16 +258,20 @@ cudaError_t cw_launch_fused(const CwDeviceInfo &dev, int halg, int calg, bool fa
                             uint32_t *d_lens, unsigned long long *work, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
-    if (calg == CW_C_LZ4 && chunk > 16384u) {
-        // big chunks: the stand-alone LZ4 kernel reads the chunk in place (DIRECT) and keeps 13 chunks per SM in
-        // flight, the fused kernel would stage them and keep 2; run it and the hash kernel back to back instead
-        cudaError_t e = cw_launch_lz4(dev, fast, d_src, chunk, n, d_dst, stride, d_lens, &work[0], st);
-        if (e != cudaSuccess) return e;
-        return cw_launch_hash(halg, iv, d_src, chunk, n, d_digests, st);
-    }
-    if (calg == CW_C_LZ4 && fast) calg = CW_C_LZ4_FAST;  // fast mode of LZF is the compat kernel
     const bool aligned = (chunk % 16u == 0) && ((reinterpret_cast<uintptr_t>(d_src) & 15u) == 0) &&
                          ((reinterpret_cast<uintptr_t>(d_digests) & 15u) == 0);
+    if (calg == CW_C_LZ4 && chunk > 16384u) {
+        // big chunks (the 64 KiB blocks of BASELINE configs[2]) are not staged: parsers, emitters and hash warps all read
+        // the chunk where it lies, which keeps 13 (fast: 6) chunks per SM in flight instead of 2, in ONE launch
+        if (aligned) calg = fast ? CW_C_LZ4_FAST_DIRECT : CW_C_LZ4_DIRECT;
+        else {
+            // ragged sizes / unaligned buffers cannot use the in-place parser: stand-alone kernels back to back
+            cudaError_t e = cw_launch_lz4(dev, fast, d_src, chunk, n, d_dst, stride, d_lens, &work[0], st);
+            if (e != cudaSuccess) return e;
+            return cw_launch_hash(halg, iv, d_src, chunk, n, d_digests, st);
+        }
+    } else if (calg == CW_C_LZ4 && fast)  // fast mode of LZF is the compat kernel
+        calg = cw_lz4f_hashlog(chunk) == 12 ? CW_C_LZ4_FAST : CW_C_LZ4_FAST13;
     switch (halg) {
     case CW_K_SKEIN512: return launch_h<CW_K_SKEIN512>(calg, aligned, dev, iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, st);
     case CW_K_SKEIN256_128: return launch_h<CW_K_SKEIN256_128>(calg, aligned, dev, iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, st);

@@ -9,6 +9,7 @@
 // number of parsers is whatever fits in the SM's 227 KB: at 8 KB chunks 9 with the reference's 8192-entry
 // table (compat) and 13 with the 4096-entry table of fast mode.  A few EMITTER warps (no slot of their own)
 // turn the parsers' match records into output bytes.
+// compat mode runs the exact sequential parse (lz4_warp.cuh), fast mode the window-parallel parse (lz4_fast.cuh).
 #include <cstdlib>
 
 #include "comp_roles.cuh"
@@ -34,7 +35,7 @@ static int lz4_emitters()
 
 // DIRECT (chunks > CW_LZ4_DIRECT_ABOVE bytes, e.g. the 64 KB blocks of BASELINE configs[2]): a slot holds only the
 // table; parsers and emitters read the chunk where it lies (L2), which keeps 13 chunks per SM in flight instead of 2.
-template <int HASHLOG, bool ALIGNED, bool DIRECT>
+template <int HASHLOG, bool ALIGNED, bool DIRECT, bool FAST>
 __global__ void __launch_bounds__((CW_LZ4_MAX_PARSERS + CW_LZ4_MAX_EMITTERS) * 32, 1)
     cw_lz4_kernel(const uint8_t *__restrict__ src, uint32_t chunk, uint64_t n_chunks, uint8_t *__restrict__ dst,
                   uint64_t stride, uint32_t *__restrict__ lens, unsigned long long *work, uint32_t slot_bytes,
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__((CW_LZ4_MAX_PARSERS + CW_LZ4_MAX_EMITTERS) * 3
     if (warp < parsers && lane < 8u) reinterpret_cast<uint32_t *>(cw_lz4_queue_at(queues, warp, qlen))[lane] = 0u;  // header
     __syncthreads();
     if (warp < parsers)
-        cw_lz4_parser_role<HASHLOG, ALIGNED, DIRECT>(smem + (size_t)warp * slot_bytes, cw_lz4_queue_at(queues, warp, qlen),
+        cw_lz4_parser_role<HASHLOG, ALIGNED, DIRECT, FAST>(smem + (size_t)warp * slot_bytes, cw_lz4_queue_at(queues, warp, qlen),
                                                      &bars[warp], src, chunk, n_chunks, work, qlen);
     else
         cw_lz4_emitter_role<DIRECT>(warp - parsers, emitters, parsers, smem, slot_bytes, queues, src, chunk, dst, stride, lens,
@@ -59,14 +60,15 @@ static int g_lz4_max_smem = 0;
 cudaError_t cw_lz4_configure(const CwDeviceInfo &dev)
 {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, cw_lz4_kernel<13, true, false>);
+    cudaError_t e = cudaFuncGetAttributes(&fa, cw_lz4_kernel<13, true, false, false>);
     if (e != cudaSuccess) return e;
     g_lz4_max_smem = (int)dev.smem_optin - (int)fa.sharedSizeBytes;  // opt-in limit covers static + dynamic
     const int m = g_lz4_max_smem;
-#define CW_CFG(HL, AL, DI) \
-    if ((e = cudaFuncSetAttribute(cw_lz4_kernel<HL, AL, DI>, cudaFuncAttributeMaxDynamicSharedMemorySize, m)) != cudaSuccess) return e;
-    CW_CFG(13, true, false) CW_CFG(13, false, false) CW_CFG(12, true, false) CW_CFG(12, false, false)
-    CW_CFG(13, true, true) CW_CFG(12, true, true)
+#define CW_CFG(HL, AL, DI, FA) \
+    if ((e = cudaFuncSetAttribute(cw_lz4_kernel<HL, AL, DI, FA>, cudaFuncAttributeMaxDynamicSharedMemorySize, m)) != cudaSuccess) return e;
+    CW_CFG(13, true, false, false) CW_CFG(13, false, false, false) CW_CFG(13, true, true, false)
+    CW_CFG(12, true, false, true) CW_CFG(12, false, false, true) CW_CFG(13, true, false, true) CW_CFG(13, false, false, true)
+    CW_CFG(14, true, true, true) CW_CFG(14, false, false, true)
 #undef CW_CFG
     return cudaSuccess;
 }
@@ -76,10 +78,9 @@ cudaError_t cw_launch_lz4(const CwDeviceInfo &dev, bool fast, const uint8_t *d_s
 {
     const bool aligned = ((chunk & 15u) == 0) && ((reinterpret_cast<uintptr_t>(d_src) & 15u) == 0);
     const bool direct = aligned && chunk > CW_LZ4_DIRECT_ABOVE;
-    // the 4096-entry table of fast mode stays within 1 % of the reference's ratio only up to 16 KB chunks
-    // (measured: +0.8 % at 16 KB, +1.4 % at 32 KB, +2.7 % at 64 KB); bigger chunks keep the reference's table
-    if (chunk > CW_LZ4_DIRECT_ABOVE) fast = false;
-    const uint32_t slot = (direct ? 0u : cw_lz4_chunk_pad(chunk)) + (2u << (fast ? 12 : 13));
+    // compat: the reference's 13-bit table.  fast: 12 / 13 / 14 bits by chunk size (lz4_fast.cuh)
+    const int hashlog = fast ? cw_lz4f_hashlog(chunk) : 13;
+    const uint32_t slot = (direct ? 0u : cw_lz4_chunk_pad(chunk)) + (2u << hashlog);
     // a ring of 32 records instead of 64 where that buys another parser (4 KiB chunks: 11 instead of 10)
     uint32_t qlen = CW_LZ4_QLEN;
     if (g_lz4_max_smem / (int)(slot + cw_lz4_queue_bytes(32u)) > g_lz4_max_smem / (int)(slot + cw_lz4_queue_bytes(CW_LZ4_QLEN))) qlen = 32u;
@@ -105,17 +106,21 @@ cudaError_t cw_launch_lz4(const CwDeviceInfo &dev, bool fast, const uint8_t *d_s
     }();
     static const int none[4] = {3, 3, 3, 3}, es[4] = {3, 3, 3, 3};
     const CwRoleMap roles = make_role_map(parsers, emitters, 0, grouped ? none : nullptr, grouped ? es : nullptr);
-#define CW_GO(HL, AL, DI) \
-    cw_lz4_kernel<HL, AL, DI><<<grid, block, dyn, st>>>(d_src, chunk, n, d_dst, stride, d_lens, work, slot, (uint32_t)parsers, (uint32_t)emitters, roles, qlen)
-    if (direct) {
-        if (fast) CW_GO(12, true, true);
-        else CW_GO(13, true, true);
-    } else if (fast) {
-        if (aligned) CW_GO(12, true, false);
-        else CW_GO(12, false, false);
+#define CW_GO(HL, AL, DI, FA) \
+    cw_lz4_kernel<HL, AL, DI, FA><<<grid, block, dyn, st>>>(d_src, chunk, n, d_dst, stride, d_lens, work, slot, (uint32_t)parsers, (uint32_t)emitters, roles, qlen)
+    if (!fast) {
+        if (direct) CW_GO(13, true, true, false);
+        else if (aligned) CW_GO(13, true, false, false);
+        else CW_GO(13, false, false, false);
+    } else if (hashlog == 12) {
+        if (aligned) CW_GO(12, true, false, true);
+        else CW_GO(12, false, false, true);
+    } else if (hashlog == 13) {
+        if (aligned) CW_GO(13, true, false, true);
+        else CW_GO(13, false, false, true);
     } else {
-        if (aligned) CW_GO(13, true, false);
-        else CW_GO(13, false, false);
+        if (direct) CW_GO(14, true, true, true);
+        else CW_GO(14, false, false, true);
     }
 #undef CW_GO
     return cudaGetLastError();

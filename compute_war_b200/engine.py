@@ -86,6 +86,11 @@ def load_library():
     return L
 
 
+def device_count() -> int:
+    """CUDA devices the library sees (0 without a GPU; raises if the library is not built)"""
+    return int(load_library().cw_device_count())
+
+
 def digest_bytes(hash_alg: int) -> int:
     return {HASH_SKEIN512: 64, HASH_SKEIN256_128: 16, HASH_SHA256: 32}[hash_alg]
 

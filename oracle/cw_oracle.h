@@ -40,6 +40,11 @@ void cwo_sha256(const uint8_t *msg, size_t len, uint8_t out[32]);
  * fresh table) for inputs < 65547 bytes -- call sites HashAndCompress.cpp:349-355, experiment.cpp:249.
  * Returns bytes written, 0 if dst_cap is too small. */
 int cwo_lz4_compress(const uint8_t *src, int n, uint8_t *dst, int dst_cap);
+/* The ENGINE's own fast-mode LZ4 parse (csrc/lz4_fast.cuh), restated in scalar form -- not a reference algorithm: the
+ * reference constrains fast mode only through its decoder and its size (see cw_oracle.c).  hashlog: table bits,
+ * cwo_lz4_fast_hashlog(chunk) = what the kernels pick.  Returns bytes written, 0 if dst_cap < bound. */
+int cwo_lz4_fast_hashlog(size_t chunk);
+int cwo_lz4_fast_compress(const uint8_t *src, int n, uint8_t *dst, int dst_cap, int hashlog);
 /* LZ4 block decoder, bounds-checked; returns decoded size or <0 on malformed input
  * (role of LZ4_decompress_safe, experiment.cpp:256). */
 int cwo_lz4_decompress(const uint8_t *src, int n, uint8_t *dst, int dst_cap);

@@ -50,6 +50,10 @@ def lib():
         L.cwo_sha256.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         L.cwo_lz4_compress.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.cwo_lz4_compress.restype = C.c_int
+        L.cwo_lz4_fast_compress.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        L.cwo_lz4_fast_compress.restype = C.c_int
+        L.cwo_lz4_fast_hashlog.argtypes = [C.c_size_t]
+        L.cwo_lz4_fast_hashlog.restype = C.c_int
         L.cwo_lz4_decompress.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.cwo_lz4_decompress.restype = C.c_int
         L.cwo_lzf_compress.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint]
@@ -114,6 +118,20 @@ def hash_chunks(alg: int, data, chunk: int) -> np.ndarray:
     if n:
         lib().cwo_hash_chunks(alg, _ptr(d), chunk, n, _ptr(out))
     return out
+
+
+def lz4_fast_chunks(data, chunk: int, stride: int | None = None, hashlog: int = 0):
+    """the ENGINE's fast-mode LZ4 parse restated on the CPU (not a reference algorithm): (blocks[n, stride], lens[n])"""
+    d = _as_u8(data)
+    n = len(d) // chunk
+    stride = stride or compress_bound(COMP_LZ4, chunk)
+    hashlog = hashlog or int(lib().cwo_lz4_fast_hashlog(chunk))
+    blocks = np.zeros((n, stride), np.uint8)
+    lens = np.zeros(n, np.uint32)
+    for i in range(n):
+        lens[i] = lib().cwo_lz4_fast_compress(d[i * chunk:].ctypes.data_as(C.c_void_p), chunk,
+                                              blocks[i].ctypes.data_as(C.c_void_p), stride, hashlog)
+    return blocks, lens
 
 
 def compress_chunks(alg: int, data, chunk: int, stride: int | None = None):

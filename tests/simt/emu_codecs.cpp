@@ -5,6 +5,7 @@
 #include <vector>
 #include "warp_emu.h"
 #include "../../compute_war_b200/csrc/lz4_warp.cuh"
+#include "../../compute_war_b200/csrc/lz4_fast.cuh"
 #include "../../compute_war_b200/csrc/decode_warp.cuh"
 #if __has_include("../../compute_war_b200/csrc/lzf_warp.cuh")
 #include "../../compute_war_b200/csrc/lzf_warp.cuh"
@@ -13,6 +14,7 @@
 
 // ring length the parser / emitter pairs below run with (the kernels use 64, or 32 where shared memory is short)
 static uint32_t g_qlen = CW_LZ4_QLEN;
+extern "C" void emu_set_store_winner(int lowest_lane) { cwemu::g_descending_lanes = lowest_lane ? 1 : 0; }
 extern "C" void emu_set_qlen(uint32_t qlen) { g_qlen = qlen == 32u ? 32u : CW_LZ4_QLEN; }
 
 struct Job {
@@ -36,6 +38,7 @@ struct Lz4Job {
     uint32_t lens[1];
     int hashlog;
     int direct;
+    int fast;
 };
 
 static void lz4_block_body(void *a, int warp)
@@ -44,7 +47,14 @@ static void lz4_block_body(void *a, int warp)
     const unsigned lane = cw_lane();
     if (warp == 0) {
         uint32_t qh = 0;
-        if (j->direct) {
+        if (j->fast) {  // fast mode: the window-parallel parse of csrc/lz4_fast.cuh
+            if (j->direct) {
+                if (j->hashlog == 14) cw_lz4f_parse_warp<14, true>(j->s, j->n, j->table, j->q, qh, g_qlen);
+                else cw_lz4f_parse_warp<13, true>(j->s, j->n, j->table, j->q, qh, g_qlen);
+            } else if (j->hashlog == 12) cw_lz4f_parse_warp<12, false>(j->s, j->n, j->table, j->q, qh, g_qlen);
+            else if (j->hashlog == 13) cw_lz4f_parse_warp<13, false>(j->s, j->n, j->table, j->q, qh, g_qlen);
+            else cw_lz4f_parse_warp<14, false>(j->s, j->n, j->table, j->q, qh, g_qlen);
+        } else if (j->direct) {
             if (j->hashlog == 12) cw_lz4_parse_warp<12, true>(j->s, j->n, j->table, j->q, qh, g_qlen);
             else cw_lz4_parse_warp<13, true>(j->s, j->n, j->table, j->q, qh, g_qlen);
         } else if (j->hashlog == 12) cw_lz4_parse_warp<12, false>(j->s, j->n, j->table, j->q, qh, g_qlen);
@@ -74,8 +84,33 @@ extern "C" uint32_t emu_lz4_compress_hl(const uint8_t *src, uint32_t n, uint8_t 
     std::vector<uint16_t> table(1u << hashlog, 0);
     CwLz4Queue q;
     memset(&q, 0, sizeof q);
-    Lz4Job j{(const uint8_t *)staged.data(), n, table.data(), &q, out, {0}, hashlog, 0};
+    Lz4Job j{(const uint8_t *)staged.data(), n, table.data(), &q, out, {0}, hashlog, 0, 0};
     cwemu::run_block(2, lz4_block_body, &j);
+    return j.lens[0];
+}
+
+// fast mode (csrc/lz4_fast.cuh); hashlog 0 = what the kernels pick for the chunk size
+extern "C" uint32_t emu_lz4_fast(const uint8_t *src, uint32_t n, uint8_t *out, int hashlog, int direct)
+{
+    if (!hashlog) hashlog = cw_lz4f_hashlog(n);
+    std::vector<uint16_t> table(1u << hashlog, 0);
+    CwLz4Queue q;
+    memset(&q, 0, sizeof q);
+    if (!direct) {
+        std::vector<uint32_t> staged((n + CW_LZ4_PAD + 3) / 4 + 4, 0);
+        memcpy(staged.data(), src, n);
+        Lz4Job j{(const uint8_t *)staged.data(), n, table.data(), &q, out, {0}, hashlog, 0, 1};
+        cwemu::run_block(2, lz4_block_body, &j);
+        return j.lens[0];
+    }
+    const size_t page = 4096, span = (n + page - 1) / page * page + page;  // chunk ends at a PROT_NONE guard page
+    uint8_t *map = (uint8_t *)mmap(nullptr, span + page, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    mprotect(map + span, page, PROT_NONE);
+    uint8_t *exact = map + span - n;
+    memcpy(exact, src, n);
+    Lz4Job j{(const uint8_t *)exact, n, table.data(), &q, out, {0}, hashlog, 1, 1};
+    cwemu::run_block(2, lz4_block_body, &j);
+    munmap(map, span + page);
     return j.lens[0];
 }
 
@@ -91,7 +126,7 @@ extern "C" uint32_t emu_lz4_compress_direct(const uint8_t *src, uint32_t n, uint
     std::vector<uint16_t> table(1u << hashlog, 0);
     CwLz4Queue q;
     memset(&q, 0, sizeof q);
-    Lz4Job j{(const uint8_t *)exact, n, table.data(), &q, out, {0}, hashlog, 1};
+    Lz4Job j{(const uint8_t *)exact, n, table.data(), &q, out, {0}, hashlog, 1, 0};
     cwemu::run_block(2, lz4_block_body, &j);
     munmap(map, span + page);
     return j.lens[0];

@@ -4,6 +4,7 @@
 namespace cwemu {
 
 thread_local Block *g_block = nullptr;
+int g_descending_lanes = 0;  // 1: fibres of a warp run from lane 31 down, so of several same-address stores lane 0's survives
 
 static void trampoline()
 {
@@ -40,7 +41,8 @@ void run_block(int nwarps, void (*body)(void *, int), void *arg)
     int live = nf, idle_rounds = 0;
     while (live) {
         const uint64_t p0 = b->progress;
-        for (int i = 0; i < nf; i++) {
+        for (int k = 0; k < nf; k++) {
+            const int i = g_descending_lanes ? (k & ~31) + 31 - (k & 31) : k;
             if (b->finished[i]) continue;
             b->cur = i;
             swapcontext(&b->sched, &b->ctx[i]);

@@ -38,6 +38,9 @@ struct Block {
 };
 
 extern thread_local Block *g_block;
+// Which of several stores of one warp to the same address survives is undefined in CUDA; the emulator can run the lanes
+// in either order so that algorithms that tolerate any winner are checked with both extremes.
+extern int g_descending_lanes;
 
 inline void yield_fibre()
 {
@@ -91,6 +94,12 @@ static inline void cw_syncwarp() { (void)cwemu::collective(0); }
 static inline int cw_ffs(uint32_t v) { return v ? __builtin_ctz(v) + 1 : 0; }
 static inline int cw_clz(uint32_t v) { return v ? __builtin_clz(v) : 32; }
 static inline int cw_popc(uint32_t v) { return __builtin_popcount(v); }
+static inline uint32_t cw_brev(uint32_t v)
+{
+    uint32_t r = 0;
+    for (int i = 0; i < 32; i++) r |= ((v >> i) & 1u) << (31 - i);
+    return r;
+}
 static inline uint32_t cw_funnel_r(uint32_t lo, uint32_t hi, unsigned sh)
 {
     sh &= 31u;

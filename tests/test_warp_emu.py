@@ -145,6 +145,48 @@ def test_lz4_direct_mode_and_fast_table(emu, golden):
     assert tot_fast <= 1.01 * tot_ref
 
 
+@pytest.mark.parametrize("lowest_lane_wins", [1, 0])
+def test_lz4_fast_parse_on_emulator(emu, golden, lowest_lane_wins):
+    """fast mode (csrc/lz4_fast.cuh on the warp emulator): byte-identical to its scalar restatement in the oracle whichever
+    lane wins a same-address store race, every block restored by the reference's LZ4_decompress_safe (oracle/_ref/ref_cli
+    when it is built, the restated decoder otherwise), every table size, staged and in-place (DIRECT) source"""
+    emu.emu_lz4_fast.restype = C.c_uint32
+    emu.emu_set_store_winner(lowest_lane_wins)
+    try:
+        cases = _cases(golden, small=True)
+        if not lowest_lane_wins:
+            cases = cases[::3]
+        for c in cases:
+            n = len(c)
+            for hl, direct in ((0, 0), (13, 0), (14, 1 if n % 4 == 0 else 0)):
+                out = np.zeros(n + n // 255 + 64, np.uint8)
+                r = emu.emu_lz4_fast(c.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p), hl, direct)
+                blocks, lens = O.lz4_fast_chunks(c, n, hashlog=hl) if n else (None, [0])
+                assert r == lens[0] and (out[:r] == blocks[0, :r]).all(), (n, hl, direct)
+                assert O.verify_roundtrip(O.COMP_LZ4, c, n, out[None, :], np.array([r], np.uint32)) == 0, (n, hl)
+    finally:
+        emu.emu_set_store_winner(0)
+
+
+def test_lz4_fast_restatement_ratio_and_reference_decoder(golden):
+    """the restated fast parse over the golden corpus sample: every block decodes with the reference's decoder and every
+    file stays within 1 % of the reference's compressed size at 4 K / 8 K / 64 K (the bound north_star sets)"""
+    ref, blob = golden["ref"], golden["blob"]
+    for ent in ref["files"]:
+        d = blob[ent["offset"]: ent["offset"] + ent["size"]]
+        for chunk in (4096, 8192, 65536):
+            rec = ref["corpus"][ent["name"]][str(chunk)]
+            if rec["n"] == 0:
+                continue
+            blocks, lens = O.lz4_fast_chunks(d, chunk)
+            if O.have_ref_cli():
+                back = O.ref_decompress_chunks(O.COMP_LZ4, chunk, blocks, lens)
+                assert (back == d[: len(back)]).all() and len(back) == rec["n"] * chunk
+            else:
+                assert O.verify_roundtrip(O.COMP_LZ4, d, chunk, blocks, lens) == 0
+            assert int(lens.sum()) <= 1.01 * sum(rec["lz4_lens"]), (ent["name"], chunk)
+
+
 def test_lzf_warp_algorithm_byte_identical(emu, golden):
     if not hasattr(emu, "emu_lzf_compress"):
         pytest.skip("LZF warp kernel not built yet")

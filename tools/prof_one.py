@@ -14,6 +14,7 @@ import oracle_lib as O
 what, cls = sys.argv[1], sys.argv[2]
 N = int(sys.argv[3]) if len(sys.argv) > 3 else 16384
 chunk = int(sys.argv[4]) if len(sys.argv) > 4 else 8192
+MODE = int(os.environ.get("CW_MODE", "0"))  # 1: fast mode
 L = O.lib()
 L.cwo_synth_class.argtypes = [C.c_uint64, C.c_uint64]
 L.cwo_synth_class.restype = C.c_uint
@@ -46,10 +47,10 @@ lens = torch.empty(n, dtype=torch.int32, device=dev)
 dig = torch.empty(n * 64, dtype=torch.uint8, device=dev)
 for _ in range(2):
     if what == "fused":
-        eng.hash_compress_dev(cw.HASH_SKEIN512, comp, 0, src.data_ptr(), chunk, n, dig.data_ptr(), blocks.data_ptr(), stride,
+        eng.hash_compress_dev(cw.HASH_SKEIN512, comp, MODE, src.data_ptr(), chunk, n, dig.data_ptr(), blocks.data_ptr(), stride,
                               lens.data_ptr(), s)
     else:
-        eng.compress_dev(comp, 0, src.data_ptr(), chunk, n, blocks.data_ptr(), stride, lens.data_ptr(), s)
+        eng.compress_dev(comp, MODE, src.data_ptr(), chunk, n, blocks.data_ptr(), stride, lens.data_ptr(), s)
     torch.cuda.synchronize()
 print("ok", what, cls, n)
 eng.close()

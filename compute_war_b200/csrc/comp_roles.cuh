@@ -11,8 +11,7 @@ __host__ __device__ constexpr uint32_t cw_lz4_chunk_pad(uint32_t chunk) { return
 
 // LZ4 parser role.  s: this warp's slot [chunk | pad | table] (DIRECT: [table] only, the chunk is read where it
 // lies in global memory); q: this warp's queue (zeroed by the caller before the CTA-wide barrier).
-// FAST: the window-parallel parse of lz4_fast.cuh instead of the reference's sequential parse.
-template <int HASHLOG, bool ALIGNED, bool DIRECT, bool FAST = false>
+template <int HASHLOG, bool ALIGNED, bool DIRECT>
 __device__ __forceinline__ void cw_lz4_parser_role(uint8_t *s, CwLz4Queue *q, uint64_t *bar, const uint8_t *__restrict__ src,
                                                    uint32_t chunk, uint64_t n_chunks, unsigned long long *work,
                                                    uint32_t qlen = CW_LZ4_QLEN)
@@ -35,8 +34,7 @@ __device__ __forceinline__ void cw_lz4_parser_role(uint8_t *s, CwLz4Queue *q, ui
                 q->chunk_hi = (uint32_t)(g >> 32);
             }
             __syncwarp();
-            if (FAST) cw_lz4f_parse_warp<HASHLOG, true>(src + g * chunk, chunk, table, q, qh, qlen);
-            else cw_lz4_parse_warp<HASHLOG, true>(src + g * chunk, chunk, table, q, qh, qlen);
+            cw_lz4_parse_warp<HASHLOG, true>(src + g * chunk, chunk, table, q, qh, qlen);
         }
         cw_lz4_q_drain(q, qh, lane);
         if (lane == 0) {
@@ -75,8 +73,7 @@ __device__ __forceinline__ void cw_lz4_parser_role(uint8_t *s, CwLz4Queue *q, ui
             for (uint32_t i = lane; i < chunk; i += 32u) s[i] = gp[i];
         }
         __syncwarp();
-        if (FAST) cw_lz4f_parse_warp<HASHLOG, false>(s, chunk, table, q, qh, qlen);
-        else cw_lz4_parse_warp<HASHLOG, false>(s, chunk, table, q, qh, qlen);
+        cw_lz4_parse_warp<HASHLOG, false>(s, chunk, table, q, qh, qlen);
     }
     cw_lz4_q_drain(q, qh, lane);
     if (lane == 0) {
@@ -108,6 +105,79 @@ __device__ __forceinline__ void cw_lz4_emitter_role(unsigned e, unsigned emitter
         }
         if (all_done) break;
         if (!did) cw_spin();
+    }
+}
+
+// LZ4 fast mode (lz4_fast.cuh): a TEAM of nteam warps stages, parses and emits a chunk; no queues, no emitter warps.
+// slot of a team: [chunk | pad | table | CwLz4fTeam | nteam x CwLz4fScratch] (DIRECT: no chunk, it is read where it lies).
+__host__ __device__ constexpr uint32_t cw_lz4f_slot_bytes(uint32_t chunk, int hashlog, bool direct, uint32_t nteam)
+{
+    return (direct ? 0u : cw_lz4_chunk_pad(chunk)) + (2u << hashlog) + (uint32_t)sizeof(CwLz4fTeam) +
+           nteam * (uint32_t)sizeof(CwLz4fScratch);
+}
+// barrier of the warps of one team (hardware barrier `id`, 1..15); a team of one warp needs none
+__device__ __forceinline__ void cw_lz4f_team_sync(unsigned id, unsigned nteam)
+{
+    if (nteam == 1u) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nteam * 32u) : "memory");
+}
+// rank: this warp's index inside its team; bar_id: the team's hardware barrier; bar: the team's mbarrier
+template <int HASHLOG, bool ALIGNED, bool DIRECT>
+__device__ __forceinline__ void cw_lz4f_team_role(uint8_t *s, uint64_t *bar, unsigned rank, unsigned nteam, unsigned bar_id,
+                                                  const uint8_t *__restrict__ src, uint32_t chunk, uint64_t n_chunks,
+                                                  unsigned long long *work, uint8_t *__restrict__ dst, uint64_t stride,
+                                                  uint32_t *__restrict__ lens)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t chunk_pad = DIRECT ? 0u : cw_lz4_chunk_pad(chunk);
+    uint16_t *table = reinterpret_cast<uint16_t *>(s + chunk_pad);
+    CwLz4fTeam *team = reinterpret_cast<CwLz4fTeam *>(s + chunk_pad + (2u << HASHLOG));
+    CwLz4fScratch *scr = reinterpret_cast<CwLz4fScratch *>(team + 1) + rank;
+    if (rank == 0u) {
+        if (lane == 0) {
+            for (unsigned r = 0; r < CW_LZ4F_MAX_TEAM; r++) {
+                cw_lz4f_tok_init(&team->tok_table[r]);
+                cw_lz4f_tok_init(&team->tok_walk[r]);
+                cw_lz4f_tok_init(&team->tok_emit[r]);
+            }
+            cw_mbar_init(bar, 1);  // also fences the initialisations above
+        }
+        if (!DIRECT)
+            for (uint32_t i = chunk + lane; i < chunk_pad; i += 32u) s[i] = 0;
+    }
+    cw_lz4f_team_sync(bar_id, nteam);
+    uint32_t phase = 0, seen = 0;  // seen: arrivals consumed on this warp's tokens
+    for (;;) {
+        // the slot is free (barrier at the end of the loop): next chunk index, tokens, bulk copy, zeroed table
+        if (rank == 0u && lane == 0) {
+            const unsigned long long g = atomicAdd(work, 1ull);
+            team->chunk_lo = (uint32_t)g;
+            team->chunk_hi = (uint32_t)(g >> 32);
+            team->ip = 1u;
+            team->op = 0u;
+            if (!DIRECT && ALIGNED && g < n_chunks) cw_bulk_load(s, src + g * chunk, chunk, bar);
+        }
+        {
+            uint4 *t4 = reinterpret_cast<uint4 *>(table);
+            for (uint32_t i = rank * 32u + lane; i < (2u << HASHLOG) / 16u; i += nteam * 32u) t4[i] = make_uint4(0, 0, 0, 0);
+        }
+        cw_lz4f_team_sync(bar_id, nteam);
+        const unsigned long long g = (unsigned long long)team->chunk_lo | ((unsigned long long)team->chunk_hi << 32);
+        if (g >= n_chunks) break;
+        if (!DIRECT) {
+            if (ALIGNED) {
+                cw_mbar_wait(bar, phase);
+                phase ^= 1u;
+            } else {
+                const uint8_t *gp = src + g * chunk;
+                for (uint32_t i = rank * 32u + lane; i < chunk; i += nteam * 32u) s[i] = gp[i];
+                cw_lz4f_team_sync(bar_id, nteam);
+            }
+        }
+        const uint32_t len =
+            cw_lz4f_team_chunk<HASHLOG, DIRECT>(DIRECT ? src + g * chunk : s, chunk, table, team, scr, dst + g * stride, rank, nteam, seen);
+        if (len != CW_LZ4_NONE && lane == 0) lens[g] = len;
+        cw_lz4f_team_sync(bar_id, nteam);  // every warp is done with the slot before it is refilled
     }
 }
 

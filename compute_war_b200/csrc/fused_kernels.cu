@@ -32,6 +32,10 @@
 #define CW_FUSED_HASH_WARPS_MAX 2  // also sizes __launch_bounds__: 19 warps leave ptxas 96 registers and no spills
 #define CW_FUSED_MAX_COMP_WARPS 14
 #define CW_FUSED_MAX_THREADS ((CW_FUSED_HASH_WARPS_MAX + CW_FUSED_MAX_COMP_WARPS + 3) * 32)  // + emitters
+// fast mode: teams of warps per chunk (lz4_fast.cuh), no emitters: 26 compress warps + 2 hash warps = 896 threads, which
+// leaves ptxas 72 registers -- the hash role then runs without the next-block prefetch of skein.cuh (16 registers)
+#define CW_FUSED_FAST_COMP_WARPS 26
+#define CW_FUSED_FAST_THREADS ((CW_FUSED_HASH_WARPS_MAX + CW_FUSED_FAST_COMP_WARPS) * 32)
 
 // measured on the synthetic mix (profiles/r01_tune_emitters_hashwarps.txt): the 9-parser compat kernel is best
 // with 1 hash warp + 3 emitters, the 13-parser fast kernel with 2 + 2
@@ -77,8 +81,9 @@ __host__ __device__ constexpr uint32_t cw_fused_qlen()
 }
 
 template <int CALG>
-__host__ __device__ constexpr uint32_t cw_slot_bytes(uint32_t chunk)
+__host__ __device__ constexpr uint32_t cw_slot_bytes(uint32_t chunk, uint32_t nteam = 1)
 {
+    if (cw_c_fast(CALG)) return cw_lz4f_slot_bytes(chunk, cw_c_hashlog(CALG), cw_c_direct(CALG), nteam);  // no queue
     return (CALG == CW_C_LZF ? ((chunk + 16u + 15u) & ~15u) + cw_lzf_table_bytes(cw_lzf_table_format(chunk))
                              : (cw_c_direct(CALG) ? 0u : cw_lz4_chunk_pad(chunk)) + (2u << cw_c_hashlog(CALG))) +
            cw_lz4_queue_bytes(cw_fused_qlen<CALG>());
@@ -103,7 +108,7 @@ static bool parse_role_env(int *hs, int *es)
 
 // logical warps [0, parsers): parsers; [parsers, parsers + emitters): emitters; the rest: hash
 template <int HALG, int CALG, bool ALIGNED>
-__global__ void __launch_bounds__(CW_FUSED_MAX_THREADS, 1)
+__global__ void __launch_bounds__(cw_c_fast(CALG) ? CW_FUSED_FAST_THREADS : CW_FUSED_MAX_THREADS, 1)
     cw_fused_kernel(const __grid_constant__ CwSkeinIV iv, const uint8_t *__restrict__ src, uint32_t chunk, uint64_t n_chunks,
                     uint8_t *__restrict__ digests, uint8_t *__restrict__ dst, uint64_t stride, uint32_t *__restrict__ lens,
                     unsigned long long *work, uint32_t slot_bytes, uint32_t parsers, uint32_t emitters,
@@ -112,7 +117,17 @@ __global__ void __launch_bounds__(CW_FUSED_MAX_THREADS, 1)
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bars[32];
     const unsigned warp = roles.logical[threadIdx.x >> 5], lane = threadIdx.x & 31u;
-    {
+    if constexpr (cw_c_fast(CALG)) {
+        // fast mode: `emitters` carries the team size; a team of warps stages, parses and emits a chunk on its own
+        // (lz4_fast.cuh), no queues, no emitter warps
+        if (warp < parsers) {
+            const unsigned nteam = emitters, t = warp / nteam;
+            cw_lz4f_team_role<cw_c_hashlog(CALG), ALIGNED, cw_c_direct(CALG)>(smem + (size_t)t * slot_bytes, &bars[t], warp - t * nteam,
+                                                                              nteam, 1u + t, src, chunk, n_chunks, &work[0], dst,
+                                                                              stride, lens);
+            if (!CW_FUSED_TAIL_HELP) return;
+        }
+    } else {
         // slot_bytes excludes the queue: queues sit behind the slots
         CwLz4Queue *queues = reinterpret_cast<CwLz4Queue *>(smem + (size_t)parsers * slot_bytes);
         constexpr uint32_t QL = cw_fused_qlen<CALG>();
@@ -123,7 +138,7 @@ __global__ void __launch_bounds__(CW_FUSED_MAX_THREADS, 1)
             if (CALG == CW_C_LZF)
                 cw_lzf_parser_role<ALIGNED>(smem + (size_t)warp * slot_bytes, myq, &bars[warp], src, chunk, n_chunks, &work[0], QL);
             else
-                cw_lz4_parser_role<cw_c_hashlog(CALG), ALIGNED, cw_c_direct(CALG), cw_c_fast(CALG)>(
+                cw_lz4_parser_role<cw_c_hashlog(CALG), ALIGNED, cw_c_direct(CALG)>(
                     smem + (size_t)warp * slot_bytes, myq, &bars[warp], src, chunk, n_chunks, &work[0], QL);
             if (!CW_FUSED_TAIL_HELP) return;
         } else if (warp < parsers + emitters) {
@@ -157,7 +172,7 @@ __global__ void __launch_bounds__(CW_FUSED_MAX_THREADS, 1)
         }
         __syncwarp();
         const unsigned long long idx = first + lane;
-        if (idx < n_chunks) cw_hash_one<HALG, ALIGNED, ALIGNED>(iv, src + idx * chunk, chunk, digests + idx * D);
+        if (idx < n_chunks) cw_hash_one<HALG, ALIGNED, ALIGNED, !cw_c_fast(CALG)>(iv, src + idx * chunk, chunk, digests + idx * D);
     }
 }
 
@@ -183,16 +198,31 @@ static cudaError_t launch_one(const CwDeviceInfo &dev, int max_dyn_smem, const C
                               uint32_t *d_lens, unsigned long long *work, cudaStream_t st)
 {
     auto kern = cw_fused_kernel<HALG, CALG, ALIGNED>;
+    const int hw = fused_hash_warps(cw_c_fast(CALG));
+    if (cw_c_fast(CALG)) {
+        // teams of nteam warps, one slot per team; the kernel's `emitters` argument carries the team size
+        int nteam = cw_lz4f_team_size();
+        const uint32_t fslot = cw_slot_bytes<CALG>(chunk, (uint32_t)nteam);
+        int teams = max_dyn_smem / (int)fslot;
+        if (teams < 1) return cudaErrorInvalidValue;
+        if (nteam > 1 && teams > 15) teams = 15;  // one hardware barrier per team
+        if (teams * nteam > CW_FUSED_FAST_COMP_WARPS) teams = CW_FUSED_FAST_COMP_WARPS / nteam;
+        uint64_t fctas = (n + (uint64_t)teams - 1) / (uint64_t)teams;
+        if (fctas > (uint64_t)dev.sm_count) fctas = (uint64_t)dev.sm_count;
+        kern<<<(unsigned)fctas, (teams * nteam + hw) * 32, (size_t)teams * fslot, st>>>(
+            iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, fslot, (uint32_t)(teams * nteam), (uint32_t)nteam,
+            make_role_map(teams * nteam, 0, hw, nullptr, nullptr));
+        return cudaGetLastError();
+    }
     const uint32_t per = cw_slot_bytes<CALG>(chunk);  // slot + queue
     const uint32_t slot = per - cw_lz4_queue_bytes(cw_fused_qlen<CALG>());
     int parsers = max_dyn_smem / (int)per;
     if (parsers < 1) return cudaErrorInvalidValue;
     if (parsers > CW_FUSED_MAX_COMP_WARPS) parsers = CW_FUSED_MAX_COMP_WARPS;
-    int emitters = fused_emitters(cw_c_fast(CALG));
+    int emitters = fused_emitters(false);
     if (emitters > parsers) emitters = parsers;
     uint64_t ctas = (n + (uint64_t)parsers - 1) / (uint64_t)parsers;
     if (ctas > (uint64_t)dev.sm_count) ctas = (uint64_t)dev.sm_count;
-    const int hw = fused_hash_warps(cw_c_fast(CALG));
     kern<<<(unsigned)ctas, (parsers + emitters + hw) * 32, (size_t)parsers * per, st>>>(
         iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, slot, (uint32_t)parsers, (uint32_t)emitters,
         fused_role_map(CALG, parsers, emitters, hw));

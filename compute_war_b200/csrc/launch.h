@@ -21,6 +21,7 @@ void cw_make_skein_iv(CwSkeinIV *iv);
 cudaError_t cw_launch_lz4(const CwDeviceInfo &dev, bool fast, const uint8_t *d_src, uint32_t chunk, uint64_t n, uint8_t *d_dst,
                           uint64_t stride, uint32_t *d_lens, unsigned long long *work, cudaStream_t st);
 cudaError_t cw_lz4_configure(const CwDeviceInfo &dev);
+int cw_lz4f_team_size();  // warps per chunk in fast mode (CW_LZ4F_TEAM, default 2)
 
 // synth.cu
 cudaError_t cw_launch_synth(uint8_t *d_dst, uint32_t chunk, uint64_t first_chunk, uint64_t n, uint64_t seed,

@@ -9,7 +9,8 @@
 // number of parsers is whatever fits in the SM's 227 KB: at 8 KB chunks 9 with the reference's 8192-entry
 // table (compat) and 13 with the 4096-entry table of fast mode.  A few EMITTER warps (no slot of their own)
 // turn the parsers' match records into output bytes.
-// compat mode runs the exact sequential parse (lz4_warp.cuh), fast mode the window-parallel parse (lz4_fast.cuh).
+// compat mode runs the exact sequential parse (lz4_warp.cuh) with parser and emitter warps; fast mode runs
+// cw_lz4f_kernel below: the window-parallel parse of lz4_fast.cuh by self-contained teams of warps.
 #include <cstdlib>
 
 #include "comp_roles.cuh"
@@ -35,7 +36,7 @@ static int lz4_emitters()
 
 // DIRECT (chunks > CW_LZ4_DIRECT_ABOVE bytes, e.g. the 64 KB blocks of BASELINE configs[2]): a slot holds only the
 // table; parsers and emitters read the chunk where it lies (L2), which keeps 13 chunks per SM in flight instead of 2.
-template <int HASHLOG, bool ALIGNED, bool DIRECT, bool FAST>
+template <int HASHLOG, bool ALIGNED, bool DIRECT>
 __global__ void __launch_bounds__((CW_LZ4_MAX_PARSERS + CW_LZ4_MAX_EMITTERS) * 32, 1)
     cw_lz4_kernel(const uint8_t *__restrict__ src, uint32_t chunk, uint64_t n_chunks, uint8_t *__restrict__ dst,
                   uint64_t stride, uint32_t *__restrict__ lens, unsigned long long *work, uint32_t slot_bytes,
@@ -48,27 +49,64 @@ __global__ void __launch_bounds__((CW_LZ4_MAX_PARSERS + CW_LZ4_MAX_EMITTERS) * 3
     if (warp < parsers && lane < 8u) reinterpret_cast<uint32_t *>(cw_lz4_queue_at(queues, warp, qlen))[lane] = 0u;  // header
     __syncthreads();
     if (warp < parsers)
-        cw_lz4_parser_role<HASHLOG, ALIGNED, DIRECT, FAST>(smem + (size_t)warp * slot_bytes, cw_lz4_queue_at(queues, warp, qlen),
+        cw_lz4_parser_role<HASHLOG, ALIGNED, DIRECT>(smem + (size_t)warp * slot_bytes, cw_lz4_queue_at(queues, warp, qlen),
                                                      &bars[warp], src, chunk, n_chunks, work, qlen);
     else
         cw_lz4_emitter_role<DIRECT>(warp - parsers, emitters, parsers, smem, slot_bytes, queues, src, chunk, dst, stride, lens,
                                     qlen);
 }
 
-static int g_lz4_max_smem = 0;
+// fast mode (lz4_fast.cuh): teams of `nteam` warps, one chunk per team at a time; every team stages, parses and emits
+// on its own.  As many teams as slots fit into the SM's shared memory (and hardware barriers: 15).
+#define CW_LZ4F_MAX_WARPS 26  // 832 threads: ptxas may use 78 registers
+#define CW_LZ4F_MAX_TEAMS 15
+#ifndef CW_LZ4F_TEAM_DEFAULT
+#define CW_LZ4F_TEAM_DEFAULT 2
+#endif
+template <int HASHLOG, bool ALIGNED, bool DIRECT>
+__global__ void __launch_bounds__(CW_LZ4F_MAX_WARPS * 32, 1)
+    cw_lz4f_kernel(const uint8_t *__restrict__ src, uint32_t chunk, uint64_t n_chunks, uint8_t *__restrict__ dst, uint64_t stride,
+                   uint32_t *__restrict__ lens, unsigned long long *work, uint32_t slot_bytes, uint32_t nteam)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bars[CW_LZ4F_MAX_WARPS];
+    const unsigned warp = threadIdx.x >> 5, t = warp / nteam;
+    cw_lz4f_team_role<HASHLOG, ALIGNED, DIRECT>(smem + (size_t)t * slot_bytes, &bars[t], warp - t * nteam, nteam, 1u + t, src, chunk,
+                                                n_chunks, work, dst, stride, lens);
+}
+
+int cw_lz4f_team_size()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("CW_LZ4F_TEAM");  // tuning knob for the profiling scripts
+        v = e ? atoi(e) : CW_LZ4F_TEAM_DEFAULT;
+        if (v < 1) v = 1;
+        if (v > 4) v = 4;
+    }
+    return v;
+}
+
+static int g_lz4_max_smem = 0, g_lz4f_max_smem = 0;
 
 cudaError_t cw_lz4_configure(const CwDeviceInfo &dev)
 {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, cw_lz4_kernel<13, true, false, false>);
+    cudaError_t e = cudaFuncGetAttributes(&fa, cw_lz4_kernel<13, true, false>);
     if (e != cudaSuccess) return e;
     g_lz4_max_smem = (int)dev.smem_optin - (int)fa.sharedSizeBytes;  // opt-in limit covers static + dynamic
     const int m = g_lz4_max_smem;
-#define CW_CFG(HL, AL, DI, FA) \
-    if ((e = cudaFuncSetAttribute(cw_lz4_kernel<HL, AL, DI, FA>, cudaFuncAttributeMaxDynamicSharedMemorySize, m)) != cudaSuccess) return e;
-    CW_CFG(13, true, false, false) CW_CFG(13, false, false, false) CW_CFG(13, true, true, false)
-    CW_CFG(12, true, false, true) CW_CFG(12, false, false, true) CW_CFG(13, true, false, true) CW_CFG(13, false, false, true)
-    CW_CFG(14, true, true, true) CW_CFG(14, false, false, true)
+#define CW_CFG(HL, AL, DI) \
+    if ((e = cudaFuncSetAttribute(cw_lz4_kernel<HL, AL, DI>, cudaFuncAttributeMaxDynamicSharedMemorySize, m)) != cudaSuccess) return e;
+    CW_CFG(13, true, false) CW_CFG(13, false, false) CW_CFG(13, true, true)
+#undef CW_CFG
+    if ((e = cudaFuncGetAttributes(&fa, cw_lz4f_kernel<12, true, false>)) != cudaSuccess) return e;
+    g_lz4f_max_smem = (int)dev.smem_optin - (int)fa.sharedSizeBytes;
+    const int mf = g_lz4f_max_smem;
+#define CW_CFG(HL, AL, DI) \
+    if ((e = cudaFuncSetAttribute(cw_lz4f_kernel<HL, AL, DI>, cudaFuncAttributeMaxDynamicSharedMemorySize, mf)) != cudaSuccess) return e;
+    CW_CFG(12, true, false) CW_CFG(12, false, false) CW_CFG(13, true, false) CW_CFG(13, false, false)
+    CW_CFG(14, true, true) CW_CFG(14, false, false)
 #undef CW_CFG
     return cudaSuccess;
 }
@@ -78,8 +116,38 @@ cudaError_t cw_launch_lz4(const CwDeviceInfo &dev, bool fast, const uint8_t *d_s
 {
     const bool aligned = ((chunk & 15u) == 0) && ((reinterpret_cast<uintptr_t>(d_src) & 15u) == 0);
     const bool direct = aligned && chunk > CW_LZ4_DIRECT_ABOVE;
-    // compat: the reference's 13-bit table.  fast: 12 / 13 / 14 bits by chunk size (lz4_fast.cuh)
-    const int hashlog = fast ? cw_lz4f_hashlog(chunk) : 13;
+    if (fast) {
+        // 12 / 13 / 14 table bits by chunk size (lz4_fast.cuh); teams of warps, no emitters
+        const int hl = cw_lz4f_hashlog(chunk);
+        int nteam = cw_lz4f_team_size();
+        const uint32_t fslot = cw_lz4f_slot_bytes(chunk, hl, direct, (uint32_t)nteam);
+        int teams = g_lz4f_max_smem / (int)fslot;
+        if (teams < 1) return cudaErrorInvalidValue;
+        if (nteam > 1 && teams > CW_LZ4F_MAX_TEAMS) teams = CW_LZ4F_MAX_TEAMS;
+        if (teams * nteam > CW_LZ4F_MAX_WARPS) teams = CW_LZ4F_MAX_WARPS / nteam;
+        if (const char *e = getenv("CW_LZ4_PARSERS")) {  // tuning knob for the profiling scripts
+            const int v = atoi(e);
+            if (v > 0 && v < teams) teams = v;
+        }
+        uint64_t fctas = (n + (uint64_t)teams - 1) / (uint64_t)teams;
+        if (fctas > (uint64_t)dev.sm_count) fctas = (uint64_t)dev.sm_count;
+#define CW_GOF(HL, AL, DI)                                                                                                    \
+    cw_lz4f_kernel<HL, AL, DI><<<(unsigned)fctas, teams * nteam * 32, (size_t)teams * fslot, st>>>(d_src, chunk, n, d_dst, stride, \
+                                                                                                 d_lens, work, fslot, (uint32_t)nteam)
+        if (hl == 12) {
+            if (aligned) CW_GOF(12, true, false);
+            else CW_GOF(12, false, false);
+        } else if (hl == 13) {
+            if (aligned) CW_GOF(13, true, false);
+            else CW_GOF(13, false, false);
+        } else {
+            if (direct) CW_GOF(14, true, true);
+            else CW_GOF(14, false, false);
+        }
+#undef CW_GOF
+        return cudaGetLastError();
+    }
+    const int hashlog = 13;  // compat: the reference's 13-bit table
     const uint32_t slot = (direct ? 0u : cw_lz4_chunk_pad(chunk)) + (2u << hashlog);
     // a ring of 32 records instead of 64 where that buys another parser (4 KiB chunks: 11 instead of 10)
     uint32_t qlen = CW_LZ4_QLEN;
@@ -106,22 +174,11 @@ cudaError_t cw_launch_lz4(const CwDeviceInfo &dev, bool fast, const uint8_t *d_s
     }();
     static const int none[4] = {3, 3, 3, 3}, es[4] = {3, 3, 3, 3};
     const CwRoleMap roles = make_role_map(parsers, emitters, 0, grouped ? none : nullptr, grouped ? es : nullptr);
-#define CW_GO(HL, AL, DI, FA) \
-    cw_lz4_kernel<HL, AL, DI, FA><<<grid, block, dyn, st>>>(d_src, chunk, n, d_dst, stride, d_lens, work, slot, (uint32_t)parsers, (uint32_t)emitters, roles, qlen)
-    if (!fast) {
-        if (direct) CW_GO(13, true, true, false);
-        else if (aligned) CW_GO(13, true, false, false);
-        else CW_GO(13, false, false, false);
-    } else if (hashlog == 12) {
-        if (aligned) CW_GO(12, true, false, true);
-        else CW_GO(12, false, false, true);
-    } else if (hashlog == 13) {
-        if (aligned) CW_GO(13, true, false, true);
-        else CW_GO(13, false, false, true);
-    } else {
-        if (direct) CW_GO(14, true, true, true);
-        else CW_GO(14, false, false, true);
-    }
+#define CW_GO(HL, AL, DI) \
+    cw_lz4_kernel<HL, AL, DI><<<grid, block, dyn, st>>>(d_src, chunk, n, d_dst, stride, d_lens, work, slot, (uint32_t)parsers, (uint32_t)emitters, roles, qlen)
+    if (direct) CW_GO(13, true, true);
+    else if (aligned) CW_GO(13, true, false);
+    else CW_GO(13, false, false);
 #undef CW_GO
     return cudaGetLastError();
 }

@@ -364,10 +364,9 @@ int cwo_lz4_fast_compress(const uint8_t *src, int n_, uint8_t *dst, int cap, int
         for (uint32_t sbase = 0; sbase <= last; sbase += W * SW) {
             uint32_t cand[SW][W], v[SW][W], h[SW][W];
             int ok[SW][W], live[SW];
-            if (ip >= sbase + W * SW) continue; /* whole group inside a match */
             for (int j = 0; j < SW; j++) {
                 const uint32_t base = sbase + j * W;
-                live[j] = base <= last && ip < base + W;
+                live[j] = base <= last; /* every position is looked up and inserted, inside a match or not */
                 if (!live[j]) continue;
                 for (int l = 0; l < W; l++) {
                     const uint32_t p = base + l;

@@ -47,14 +47,7 @@ static void lz4_block_body(void *a, int warp)
     const unsigned lane = cw_lane();
     if (warp == 0) {
         uint32_t qh = 0;
-        if (j->fast) {  // fast mode: the window-parallel parse of csrc/lz4_fast.cuh
-            if (j->direct) {
-                if (j->hashlog == 14) cw_lz4f_parse_warp<14, true>(j->s, j->n, j->table, j->q, qh, g_qlen);
-                else cw_lz4f_parse_warp<13, true>(j->s, j->n, j->table, j->q, qh, g_qlen);
-            } else if (j->hashlog == 12) cw_lz4f_parse_warp<12, false>(j->s, j->n, j->table, j->q, qh, g_qlen);
-            else if (j->hashlog == 13) cw_lz4f_parse_warp<13, false>(j->s, j->n, j->table, j->q, qh, g_qlen);
-            else cw_lz4f_parse_warp<14, false>(j->s, j->n, j->table, j->q, qh, g_qlen);
-        } else if (j->direct) {
+        if (j->direct) {
             if (j->hashlog == 12) cw_lz4_parse_warp<12, true>(j->s, j->n, j->table, j->q, qh, g_qlen);
             else cw_lz4_parse_warp<13, true>(j->s, j->n, j->table, j->q, qh, g_qlen);
         } else if (j->hashlog == 12) cw_lz4_parse_warp<12, false>(j->s, j->n, j->table, j->q, qh, g_qlen);
@@ -89,29 +82,57 @@ extern "C" uint32_t emu_lz4_compress_hl(const uint8_t *src, uint32_t n, uint8_t 
     return j.lens[0];
 }
 
-// fast mode (csrc/lz4_fast.cuh); hashlog 0 = what the kernels pick for the chunk size
-extern "C" uint32_t emu_lz4_fast(const uint8_t *src, uint32_t n, uint8_t *out, int hashlog, int direct)
+// fast mode (csrc/lz4_fast.cuh): a team of nteam warps parses and emits one chunk
+struct Lz4fJob {
+    const uint8_t *s;
+    uint32_t n;
+    uint16_t *table;
+    CwLz4fTeam *team;
+    CwLz4fScratch *scr;  // one per warp
+    uint8_t *out;
+    uint32_t len;
+    int hashlog, direct, nteam;
+};
+static void lz4f_body(void *a, int warp)
+{
+    Lz4fJob *j = (Lz4fJob *)a;
+    uint32_t r, seen = 0;
+    const uint32_t rank = (uint32_t)warp, nt = (uint32_t)j->nteam;
+    if (j->direct) {
+        if (j->hashlog == 14) r = cw_lz4f_team_chunk<14, true>(j->s, j->n, j->table, j->team, j->scr + warp, j->out, rank, nt, seen);
+        else r = cw_lz4f_team_chunk<13, true>(j->s, j->n, j->table, j->team, j->scr + warp, j->out, rank, nt, seen);
+    } else if (j->hashlog == 12) r = cw_lz4f_team_chunk<12, false>(j->s, j->n, j->table, j->team, j->scr + warp, j->out, rank, nt, seen);
+    else if (j->hashlog == 13) r = cw_lz4f_team_chunk<13, false>(j->s, j->n, j->table, j->team, j->scr + warp, j->out, rank, nt, seen);
+    else r = cw_lz4f_team_chunk<14, false>(j->s, j->n, j->table, j->team, j->scr + warp, j->out, rank, nt, seen);
+    if (r != CW_LZ4_NONE && cw_lane() == 0) j->len = r;
+}
+// hashlog 0 = what the kernels pick for the chunk size; nteam = warps per chunk
+extern "C" uint32_t emu_lz4_fast(const uint8_t *src, uint32_t n, uint8_t *out, int hashlog, int direct, int nteam)
 {
     if (!hashlog) hashlog = cw_lz4f_hashlog(n);
+    if (nteam < 1) nteam = 1;
     std::vector<uint16_t> table(1u << hashlog, 0);
-    CwLz4Queue q;
-    memset(&q, 0, sizeof q);
+    std::vector<CwLz4fScratch> scr(nteam);
+    memset(scr.data(), 0xA5, sizeof(CwLz4fScratch) * nteam);
+    CwLz4fTeam team;
+    memset(&team, 0, sizeof team);
+    team.ip = 1;
     if (!direct) {
         std::vector<uint32_t> staged((n + CW_LZ4_PAD + 3) / 4 + 4, 0);
         memcpy(staged.data(), src, n);
-        Lz4Job j{(const uint8_t *)staged.data(), n, table.data(), &q, out, {0}, hashlog, 0, 1};
-        cwemu::run_block(2, lz4_block_body, &j);
-        return j.lens[0];
+        Lz4fJob j{(const uint8_t *)staged.data(), n, table.data(), &team, scr.data(), out, 0xffffffffu, hashlog, 0, nteam};
+        cwemu::run_block(nteam, lz4f_body, &j);
+        return j.len;
     }
     const size_t page = 4096, span = (n + page - 1) / page * page + page;  // chunk ends at a PROT_NONE guard page
     uint8_t *map = (uint8_t *)mmap(nullptr, span + page, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
     mprotect(map + span, page, PROT_NONE);
     uint8_t *exact = map + span - n;
     memcpy(exact, src, n);
-    Lz4Job j{(const uint8_t *)exact, n, table.data(), &q, out, {0}, hashlog, 1, 1};
-    cwemu::run_block(2, lz4_block_body, &j);
+    Lz4fJob j{(const uint8_t *)exact, n, table.data(), &team, scr.data(), out, 0xffffffffu, hashlog, 1, nteam};
+    cwemu::run_block(nteam, lz4f_body, &j);
     munmap(map, span + page);
-    return j.lens[0];
+    return j.len;
 }
 
 // DIRECT mode: the chunk is read in place, nothing readable behind it (n must be a multiple of 4)

@@ -159,10 +159,12 @@ def test_lz4_fast_parse_on_emulator(emu, golden, lowest_lane_wins):
         for c in cases:
             n = len(c)
             for hl, direct in ((0, 0), (13, 0), (14, 1 if n % 4 == 0 else 0)):
-                out = np.zeros(n + n // 255 + 64, np.uint8)
-                r = emu.emu_lz4_fast(c.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p), hl, direct)
                 blocks, lens = O.lz4_fast_chunks(c, n, hashlog=hl) if n else (None, [0])
-                assert r == lens[0] and (out[:r] == blocks[0, :r]).all(), (n, hl, direct)
+                # one to four warps per chunk (the kernels run teams of 1-4)
+                for nteam in (1, 2, 3, 4):
+                    out = np.zeros(n + n // 255 + 64, np.uint8)
+                    r = emu.emu_lz4_fast(c.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p), hl, direct, nteam)
+                    assert r == lens[0] and (out[:r] == blocks[0, :r]).all(), (n, hl, direct, nteam)
                 assert O.verify_roundtrip(O.COMP_LZ4, c, n, out[None, :], np.array([r], np.uint32)) == 0, (n, hl)
     finally:
         emu.emu_set_store_winner(0)

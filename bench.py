@@ -56,12 +56,20 @@ def cpu_sample_chunks(threads: int) -> int:
     return int(min(max(n, 32768), 524288))
 
 
+CPU_CHECK = {}  # comp_bytes / digest_fnv of the last reference run (whole-sample check values)
+
+
 def run_cpu_reference(n_chunks: int, threads: int, reps: int):
-    """-> (list of seconds per rep, kind, ratio).  Uses oracle/_ref/ref_cli when present, else the C oracle port."""
+    """-> (list of seconds per rep, kind, ratio).  Uses oracle/_ref/ref_cli (its Skein compiled for x86-64-v3 when the
+    host runs that) when present, else the C oracle port."""
     import oracle_lib as O
     if O.have_ref_cli():
-        out = O.ref_cli("bench", "skein512", "lz4", str(CHUNK), str(n_chunks), str(threads), "0", hex(SEED), str(reps))
+        exe = O.ref_cli_bench_exe()
+        out = subprocess.check_output([exe, "bench", "skein512", "lz4", str(CHUNK), str(n_chunks), str(threads), "0", hex(SEED),
+                                       str(reps)], text=True)
         recs = [json.loads(l) for l in out.strip().splitlines() if l.startswith("{")]
+        CPU_CHECK.update({"n_chunks": n_chunks, "comp_bytes": recs[-1].get("comp_bytes"), "digest_fnv": recs[-1].get("digest_fnv"),
+                          "build": "x86-64-v3" if exe.endswith("_v3") else "portable -O2"})
         return [r["seconds"] for r in recs], "reference", recs[-1]["ratio"]
     data = O.synth(CHUNK, 0, n_chunks, SEED)
     secs = []
@@ -89,7 +97,8 @@ def reference_arm(args, rank: int, world: int):
         "vs_baseline": None, "dtype": "u64/u8", "data": "synthetic",
         "config": {"workload": "fused skein512+lz4, 8 KiB chunks, synthetic mixed-entropy stream (CPU: bounded sample)",
                    "chunk_bytes": CHUNK, "sample_chunks": n, "compression_ratio": ratio},
-        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": threads, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": threads, "kind": kind, "sample": sample,
+                         "build": CPU_CHECK.get("build")},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -182,6 +191,178 @@ def bind_to_gpu_numa_node(props):
         return {"bound": False, "why": type(e).__name__}
 
 
+
+# ------------------------------------------------------------------------------------------------
+# the other BASELINE.json configs (rank 0, N = 1): short device-resident runs, each with its own parity check
+# ------------------------------------------------------------------------------------------------
+
+# algorithmic integer work per input byte: Skein-512 1090 ops64 = 2180 int32 ops per 64-byte block,
+# Skein-256 574 ops64 per 32-byte block, SHA-256 ~1900 int32 ops per 64-byte compression; + 1 output / padding block
+def int_ops_per_chunk(hash_name: str, chunk: int) -> float:
+    if hash_name == "skein512":
+        return ((chunk + 63) // 64 + 1) * 2180.0
+    if hash_name == "skein256-128":
+        return ((chunk + 31) // 32 + 1) * 1148.0
+    return ((chunk + 9 + 63) // 64) * 1900.0
+
+
+def fnv_of_bytes(b) -> int:
+    """ref_cli's digest check value: h = h * 1099511628211 + byte over all digest bytes, mod 2^64, h0 = 0"""
+    import numpy as np
+    a = np.ascontiguousarray(b, np.uint8).ravel().astype(np.uint64)
+    n = len(a)
+    P = np.uint64(1099511628211)
+    with np.errstate(over="ignore"):
+        pw = np.empty(n + 1, np.uint64)
+        pw[0] = 1
+        # powers by doubling: pw[i] = P^i
+        filled = 1
+        while filled < n + 1:
+            m = min(filled, n + 1 - filled)
+            pw[filled: filled + m] = pw[:m] * pw[filled - 1] * P
+            filled += m
+        h = (a * pw[n - 1:: -1][:n]).sum(dtype=np.uint64) if n else np.uint64(0)
+    return int(h)
+
+
+def run_configs(eng, cw, O, torch, np, dev, stream, peaks, int_peak, steps: int):
+    """-> list of per-config dicts.  Throughput is device resident (CUDA events on `stream`, `steps` launches after one
+    warm-up); every entry carries the parity check that was run on its own data before timing."""
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    out = []
+    HN = {cw.HASH_SKEIN512: "skein512", cw.HASH_SKEIN256_128: "skein256-128", cw.HASH_SHA256: "sha256"}
+    CN = {cw.COMP_LZ4: "lz4", cw.COMP_LZF: "lzf"}
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / steps
+
+    def corpus(which, chunk, min_bytes):
+        files = [f for f in O.corpus_files() if os.path.basename(os.path.dirname(f)) in which]
+        if not files:
+            return None, 0, 0
+        d = np.concatenate([np.fromfile(f, np.uint8)[: os.path.getsize(f) // chunk * chunk] for f in files])  # whole chunks only
+        reps = max(1, -(-min_bytes // len(d)))
+        return np.tile(d, reps), reps, len(d) // chunk
+
+    def hash_entry(name, data_h, chunk, halg, extra):
+        n = len(data_h) // chunk
+        src = torch.from_numpy(data_h[: n * chunk]).to(dev)
+        D = cw.digest_bytes(halg)
+        dig = torch.empty(n * D, dtype=torch.uint8, device=dev)
+        ms = timed(lambda: eng.hash_dev(halg, src.data_ptr(), chunk, n, dig.data_ptr(), stream))
+        k = min(n, 512)
+        ok = bool((dig.view(n, D)[:k].cpu().numpy() == O.hash_chunks(halg, data_h[: k * chunk], chunk)).all())
+        gbs = n * chunk / ms / 1e6
+        tops = n * int_ops_per_chunk(HN[halg], chunk) / ms / 1e9
+        e = {"config": name, "hash": HN[halg], "chunk_bytes": chunk, "chunks": n, "GBps": gbs, "ms": ms,
+             "parity_first_chunks_vs_oracle": ok, "roofline": {"bound": "int_pipe", "achieved_tops": tops, "peak_tops": int_peak,
+                                                               "frac": tops / int_peak if int_peak else None}}
+        e.update(extra)
+        out.append(e)
+
+    def comp_entry(name, data_h, chunk, calg, mode, halg, extra):
+        n = len(data_h) // chunk
+        src = torch.from_numpy(data_h[: n * chunk]).to(dev)
+        stride = cw.compress_bound(calg, chunk)
+        blocks = torch.empty(n * stride, dtype=torch.uint8, device=dev)
+        lens = torch.empty(n, dtype=torch.int32, device=dev)
+        D = cw.digest_bytes(halg) if halg is not None else 0
+        dig = torch.empty(max(n * D, 1), dtype=torch.uint8, device=dev)
+        if halg is None:
+            fn = lambda: eng.compress_dev(calg, mode, src.data_ptr(), chunk, n, blocks.data_ptr(), stride, lens.data_ptr(), stream)
+        else:
+            fn = lambda: eng.hash_compress_dev(halg, calg, mode, src.data_ptr(), chunk, n, dig.data_ptr(), blocks.data_ptr(), stride,
+                                               lens.data_ptr(), stream)
+        ms = timed(fn)
+        k = min(n, 64 if chunk > 8192 else 256)
+        lens_h = lens[:k].cpu().numpy().astype(np.uint32)
+        blk_h = blocks.view(n, stride)[:k].cpu().numpy()
+        samp = data_h[: k * chunk]
+        ol = O.compress_chunks(calg, samp, chunk)[1]
+        if mode == cw.MODE_COMPAT:
+            ob = O.compress_chunks(calg, samp, chunk)[0]
+            ok = bool((lens_h == ol).all() and all((blk_h[i, : ol[i]] == ob[i, : ol[i]]).all() for i in range(k)))
+            how = "first chunks byte-identical to the oracle (= reference library output)"
+        else:
+            ok = O.verify_roundtrip(calg, samp, chunk, blk_h, lens_h) == 0
+            how = "first chunks decode back (restated decoder)"
+            if O.have_ref_cli():
+                back = O.ref_decompress_chunks(calg, chunk, blk_h, lens_h)
+                ok = ok and len(back) == len(samp) and bool((back == samp).all())
+                how = "first chunks restored by the reference's own decompressor (ref_cli)"
+            if calg == cw.COMP_LZ4:
+                fb, fl = O.lz4_fast_chunks(samp, chunk)
+                ok = ok and bool((lens_h == fl).all() and all((blk_h[i, : fl[i]] == fb[i, : fl[i]]).all() for i in range(k)))
+                how += " and byte-identical to the restated fast parse"
+        if halg is not None:
+            ok = ok and bool((dig.view(n, D)[:k].cpu().numpy() == O.hash_chunks(halg, samp, chunk)).all())
+        # all blocks of the set decode back on the device
+        back = torch.empty(n * chunk, dtype=torch.uint8, device=dev)
+        bl = torch.empty(n, dtype=torch.int32, device=dev)
+        eng.decompress_dev(calg, blocks.data_ptr(), stride, lens.data_ptr(), chunk, n, back.data_ptr(), bl.data_ptr(), stream)
+        torch.cuda.synchronize()
+        rt = bool((bl == chunk).all().item()) and bool(torch.equal(back, src)) if calg == cw.COMP_LZ4 else None
+        lh = lens.cpu().numpy().astype(np.int64)
+        ratio = float(np.where(lh == 0, chunk, lh).sum()) / (n * chunk)
+        ref_ratio_sample = float(np.where(ol == 0, chunk, ol.astype(np.int64)).sum()) / (k * chunk)
+        my_ratio_sample = float(np.where(lens_h == 0, chunk, lens_h.astype(np.int64)).sum()) / (k * chunk)
+        gbs = n * chunk / ms / 1e6
+        alg_bpb = 1.0 + ratio + (4 + D) / chunk
+        e = {"config": name, "comp": CN[calg], "mode": "fast" if mode else "compat", "chunk_bytes": chunk, "chunks": n,
+             "GBps": gbs, "ms": ms, "compression_ratio": ratio, "size_vs_reference_on_sample": my_ratio_sample / ref_ratio_sample,
+             "parity": ok, "parity_how": how, "device_roundtrip_all_blocks": rt}
+        if halg is not None:
+            tops = n * int_ops_per_chunk(HN[halg], chunk) / ms / 1e9
+            e["hash"] = HN[halg]
+            e["roofline"] = {"bound": "int_pipe", "achieved_tops": tops, "peak_tops": int_peak, "frac": tops / int_peak if int_peak else None,
+                             "hbm": {"achieved": gbs * alg_bpb, "peak": hbm_peak, "frac": gbs * alg_bpb / hbm_peak}}
+        else:
+            e["roofline"] = {"bound": "hbm", "achieved": gbs * alg_bpb, "peak": hbm_peak, "frac": gbs * alg_bpb / hbm_peak}
+        e.update(extra)
+        out.append(e)
+        del src, blocks, lens, dig, back, bl
+
+    GiB = 1 << 30
+    # configs[0/1]: Skein-512 (and the tools' Skein-256/128) digests of 4 KiB chunks over dataset/canterbury
+    d, reps, per = corpus(("canterbury",), 4096, GiB // 2)
+    if d is not None:
+        for h in (cw.HASH_SKEIN512, cw.HASH_SKEIN256_128):
+            hash_entry("configs[0]: 4 KiB chunks of dataset/canterbury", d, 4096, h, {"corpus_chunks": per, "tiled_x": reps})
+    # configs[1]: Skein-512 + SHA-256 over dataset/canterbury-large
+    d, reps, per = corpus(("canterbury-large",), 8192, GiB)
+    if d is not None:
+        for h in (cw.HASH_SKEIN512, cw.HASH_SHA256):
+            hash_entry("configs[1]: 8 KiB chunks of dataset/canterbury-large (E.coli absent from the mount)", d, 8192, h,
+                       {"corpus_chunks": per, "tiled_x": reps})
+    # configs[2]: LZ4, independent 64 KiB blocks, compat + fast (Silesia is not in the mount: Canterbury + large stand in)
+    d, reps, per = corpus(("canterbury", "canterbury-large"), 65536, GiB)
+    syn64 = O.synth(65536, 0, 8192)
+    for mode in (cw.MODE_COMPAT, cw.MODE_FAST):
+        if d is not None:
+            comp_entry("configs[2]: LZ4 64 KiB blocks, canterbury + canterbury-large (Silesia absent)", d, 65536, cw.COMP_LZ4, mode, None,
+                       {"corpus_chunks": per, "tiled_x": reps})
+        comp_entry("configs[2]: LZ4 64 KiB blocks, synthetic mix", syn64, 65536, cw.COMP_LZ4, mode, None, {})
+    # configs[3]: fused hc_sklz4 / hc_sklzf / hc_shlz4 at 8 KiB, real corpus tiled and the synthetic mix
+    d, reps, per = corpus(("canterbury", "canterbury-large"), 8192, GiB // 4)
+    syn8 = O.synth(8192, 0, 32768)
+    for halg, calg, modes in ((cw.HASH_SKEIN512, cw.COMP_LZ4, (0, 1)), (cw.HASH_SKEIN512, cw.COMP_LZF, (0,)),
+                              (cw.HASH_SHA256, cw.COMP_LZ4, (0, 1))):
+        tag = "hc_" + {"skein512": "sk", "sha256": "sh"}[HN[halg]] + CN[calg]
+        for mode in modes:
+            if d is not None:
+                comp_entry(f"configs[3]: {tag} 8 KiB, canterbury + canterbury-large", d, 8192, calg, mode, halg,
+                           {"corpus_chunks": per, "tiled_x": reps})
+            comp_entry(f"configs[3]: {tag} 8 KiB, synthetic mix", syn8, 8192, calg, mode, halg, {})
+    return out
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -191,6 +372,7 @@ def main():
     ap.add_argument("--chunks-per-gpu", type=int, default=CHUNKS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config table (BASELINE configs 0-3)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 1)
@@ -328,63 +510,99 @@ def main():
         f_dig = dig.view(n, DIGEST)[torch.as_tensor(sel, device=dev)].cpu().numpy()
         fast_ok = bool(O.verify_roundtrip(O.COMP_LZ4, src_h, CHUNK, f_blk, f_lens) == 0 and (f_dig == dig_h).all()
                        and roundtrip_all())
+        fast_how = "all blocks decoded back on the device; first/last 128 chunks: restated decoder"
+        if O.have_ref_cli():  # the reference's own LZ4_decompress_safe (oracle/_ref/ref_cli, built from its liblz4.a)
+            rb = O.ref_decompress_chunks(O.COMP_LZ4, CHUNK, f_blk, f_lens)
+            fast_ok = fast_ok and len(rb) == len(src_h) and bool((rb == src_h).all())
+            fast_how += " + the reference's LZ4_decompress_safe (ref_cli)"
+        rs_b, rs_l = O.lz4_fast_chunks(src_h, CHUNK)  # the fast parse is deterministic: byte-equal to its restatement
+        fast_ok = fast_ok and bool((f_lens == rs_l).all() and all((f_blk[i, : rs_l[i]] == rs_b[i, : rs_l[i]]).all()
+                                                                 for i in range(len(sel))))
+        fast_how += "; byte-identical to the restated fast parse"
         fast_ratio = float(lens.sum(dtype=torch.int64).item()) / float(n * CHUNK)
         barrier()
+        eng.prof_enable(True)
+        eng.prof_read()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
         for _ in range(args.steps):
             step_fast()
         f1.record()
         barrier()
+        fk_ms, fk_n = eng.prof_read()
+        eng.prof_enable(False)
         fms = max_over_ranks(f0.elapsed_time(f1))
         fast = {"value": float(n * CHUNK) * world * args.steps / (fms * 1e-3) / 1e9, "unit": "GB/s",
                 "compression_ratio": fast_ratio, "ratio_vs_compat": fast_ratio / ratio,
-                "roundtrip_all_blocks_and_sample_digests_ok": fast_ok}
+                "roundtrip_all_blocks_and_sample_digests_ok": fast_ok, "verified_by": fast_how,
+                "ms_per_step": fms / args.steps, "kernel_ms_per_launch": fk_ms / max(fk_n, 1)}
         step()  # leave compat results in the buffers
         torch.cuda.synchronize()
     except Exception as ex:  # noqa: BLE001
         fast = {"error": str(ex)}
 
     # ---- end to end through the host-buffer C ABI ----
+    # headline: cw_hash_compress_packed (blocks back to back: the device-to-host leg carries the bytes that exist);
+    # beside it the strided call, whose D2H moves whole strides (1.5 x the block bytes)
     e2e = None
     if not args.no_e2e:
         n_e = n
         try:
             import psutil
             avail = psutil.virtual_memory().available
-            while n_e > 16384 and (n_e * (CHUNK + stride + DIGEST + 4)) * max(world, 1) > 0.5 * avail:
+            while n_e > 16384 and (n_e * (CHUNK + stride + DIGEST + 16)) * max(world, 1) > 0.5 * avail:
                 n_e //= 2
         except Exception:
             pass
         h_src = torch.empty(n_e * CHUNK, dtype=torch.uint8).pin_memory()
         h_src.copy_(src[: n_e * CHUNK])
-        h_blocks = torch.empty(n_e * stride, dtype=torch.uint8).pin_memory()
+        h_blocks = torch.empty(n_e * stride, dtype=torch.uint8).pin_memory()  # strided output / packed output (upper bound)
         h_dig = torch.empty(n_e * DIGEST, dtype=torch.uint8).pin_memory()
         h_lens = torch.empty(n_e, dtype=torch.int32).pin_memory()
+        h_off = torch.empty(n_e + 1, dtype=torch.int64).pin_memory()
         torch.cuda.synchronize()
 
-        def e2e_step():
+        def e2e_strided():
             eng.process_block_ptr(cw.HASH_SKEIN512, cw.COMP_LZ4, cw.MODE_COMPAT, h_src.data_ptr(), CHUNK, n_e,
                                   h_dig.data_ptr(), h_blocks.data_ptr(), stride, h_lens.data_ptr())
 
-        e2e_step()
+        def e2e_packed():
+            eng.process_block_packed_ptr(cw.HASH_SKEIN512, cw.COMP_LZ4, cw.MODE_COMPAT, h_src.data_ptr(), CHUNK, n_e,
+                                         h_dig.data_ptr(), h_blocks.data_ptr(), n_e * stride, h_off.data_ptr(), h_lens.data_ptr())
+
+        def timed_e2e(fn):
+            fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                fn()
+            t1 = time.perf_counter()
+            barrier()
+            return max_over_ranks(t1 - t0)
+
+        e2e_strided()
         ok_e2e = bool((h_dig.view(n_e, DIGEST)[:128].numpy() == dig_h[:128]).all()
                       and (h_lens[:128].numpy().astype(np.uint32) == ol[:128]).all())
+        sec_s = timed_e2e(e2e_strided)
+        e2e_packed()
+        offs = h_off.numpy()
+        lens_e = h_lens.numpy().astype(np.int64)
+        ok_e2e = ok_e2e and bool((np.diff(offs) == lens_e).all()) and int(offs[0]) == 0
+        ok_e2e = ok_e2e and bool((h_dig.view(n_e, DIGEST)[:128].numpy() == dig_h[:128]).all())
+        ok_e2e = ok_e2e and all((h_blocks.numpy()[offs[i]: offs[i] + ol[i]] == ob[i, : ol[i]]).all() for i in range(128))
         if not ok_e2e:
             raise SystemExit("bench.py: e2e outputs differ from the device-resident pass")
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        t1 = time.perf_counter()
-        barrier()
-        sec_all = max_over_ranks(t1 - t0)
-        e2e = {"value": float(n_e * CHUNK) * world * args.steps / sec_all / 1e9, "unit": "GB/s",
+        packed_bytes = int(offs[n_e])
+        sec_p = timed_e2e(e2e_packed)
+        gb = float(n_e * CHUNK) * world * args.steps / 1e9
+        e2e = {"value": gb / sec_p, "unit": "GB/s",
                "h2d_bytes_per_step": int(n_e * CHUNK) * world,
-               "d2h_bytes_per_step": int(n_e * (stride + DIGEST + 4)) * world,
-               "chunks_per_gpu": n_e, "timer": "host wall clock around the blocking cw_hash_compress call, max over ranks",
-               "api": "cw_hash_compress (host pinned buffers, strided output)"}
-        del h_src, h_blocks, h_dig, h_lens
+               "d2h_bytes_per_step": int(packed_bytes + n_e * (DIGEST + 4 + 8) + 8) * world,
+               "chunks_per_gpu": n_e, "timer": "host wall clock around the blocking call, max over ranks",
+               "api": "cw_hash_compress_packed (pinned host input; packed blocks + u64 offsets + lens + digests out)",
+               "strided": {"value": gb / sec_s, "unit": "GB/s", "api": "cw_hash_compress (strided output)",
+                           "d2h_bytes_per_step": int(n_e * (stride + DIGEST + 4)) * world}}
+        del h_src, h_blocks, h_dig, h_lens, h_off
 
     ratio_all = sum_over_ranks(comp_bytes) / (float(n * CHUNK) * world)
 
@@ -413,6 +631,7 @@ def main():
             int_peak = ub["int32_alu_plus_fma_tops"]
         except Exception:
             pass
+        int_tops = int_ops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None
         line = {
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -425,15 +644,37 @@ def main():
                                  "all blocks of the shard decoded back on the device == input",
                        "roundtrip_all_blocks": roundtrip_compat, "host_numa_binding_rank0": numa},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "fast_mode": fast,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+            # the fused pass is bounded by the integer pipes, not by HBM; the HBM view of the same launch
+            # (what the kernel moves against the measured copy peak) is kept beside it
+            "roofline": {"bound": "int_pipe", "achieved": int_tops, "peak": int_peak, "unit": "Tops/s (int32)",
+                         "frac": (int_tops / int_peak) if (int_tops and int_peak) else None,
+                         "peak_source": "tools/ubench.cu on this pool's B200: ALU + FMA pipes dual-issued (profiles/ubench_r01.json)",
+                         "algorithmic_ops_per_launch": int_ops,
+                         "ops_counted": "Skein-512 only: 2180 int32 ops per 64-byte block x 129 blocks per chunk (SURVEY.md 8d); "
+                                        "the LZ4 parse adds integer work that has no algorithmic count",
                          "kernel": "cw_fused_kernel<skein512, lz4 compat> (the one kernel of a cw_hash_compress_dev call)",
-                         "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                         "int_pipe": {"int32_ops_per_launch_skein_only": int_ops,
-                                      "achieved_tops": int_ops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None,
-                                      "peak_tops": int_peak,
-                                      "note": "the pass is integer-issue bound, not HBM bound (DESIGN.md)"}},
+                         "kernel_ms_per_launch": k_ms,
+                         "traffic": traffic,
+                         "traffic_source": "static: dram__bytes_read + dram__bytes_write of ONE ncu --set full capture of this "
+                                           "kernel on this shard (profiles/traffic.json), not measured in this run",
+                         "hbm": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                                 "frac": (achieved / peak) if achieved else None, "peak_source": peak_src,
+                                 "algorithmic_bytes_per_launch": alg_bytes}},
         }
+        if fast and "value" in fast and fast.get("kernel_ms_per_launch"):
+            f_ms = fast["kernel_ms_per_launch"]
+            f_bytes = float(n * CHUNK) * (1.0 + fast["compression_ratio"]) + float(n * (DIGEST + 4))
+            f_tops = int_ops / (f_ms * 1e-3) / 1e12
+            fast["roofline"] = {"bound": "int_pipe", "achieved": f_tops, "peak": int_peak, "unit": "Tops/s (int32)",
+                                "frac": f_tops / int_peak if int_peak else None,
+                                "kernel": "cw_fused_kernel<skein512, lz4 fast> (teams of warps per chunk)",
+                                "hbm": {"achieved": f_bytes / (f_ms * 1e-3) / 1e9, "peak": peak,
+                                        "frac": f_bytes / (f_ms * 1e-3) / 1e9 / peak}}
+        if world == 1 and not args.no_configs:
+            try:
+                line["configs"] = run_configs(eng, cw, O, torch, np, dev, stream, peaks, int_peak, max(3, min(args.steps, 5)))
+            except Exception as ex:  # noqa: BLE001
+                line["configs"] = {"error": f"{type(ex).__name__}: {ex}"}
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()
             ncpu = cpu_sample_chunks(threads)
@@ -441,7 +682,20 @@ def main():
             best = min(secs)
             line["cpu_baseline"] = {"value": ncpu * CHUNK / best / 1e9, "unit": "GB/s", "cores": threads, "kind": kind,
                                     "sample": f"{ncpu} chunks x {CHUNK} B prefix of the same synthetic stream, best of 2",
-                                    "compression_ratio": cratio}
+                                    "compression_ratio": cratio, "build": CPU_CHECK.get("build")}
+            # the GPU's compat results over the same prefix against the reference run's own check values: every digest
+            # byte (polynomial check value) and the total compressed size -- covers all chunks of the sample, not 256
+            if CPU_CHECK.get("digest_fnv") and ncpu <= n:
+                g_fnv = fnv_of_bytes(dig[: ncpu * DIGEST].cpu().numpy())
+                g_bytes = int(lens[:ncpu].sum(dtype=torch.int64).item())
+                same = (f"{g_fnv:016x}" == CPU_CHECK["digest_fnv"]) and (CPU_CHECK.get("comp_bytes") in (None, g_bytes))
+                line["config"]["whole_sample_vs_reference_run"] = {
+                    "chunks": ncpu, "digest_check_value_equal": f"{g_fnv:016x}" == CPU_CHECK["digest_fnv"],
+                    "compressed_bytes_equal": CPU_CHECK.get("comp_bytes") == g_bytes, "compressed_bytes": g_bytes}
+                if not same:
+                    raise SystemExit("bench.py: digests / compressed size of the GPU pass differ from the reference run")
+            s1, _, _ = run_cpu_reference(min(ncpu, 8192), 1, 2)
+            line["cpu_baseline"]["one_thread"] = {"value": min(ncpu, 8192) * CHUNK / min(s1) / 1e9, "unit": "GB/s", "cores": 1}
         print(json.dumps(line), flush=True)
     eng.close()
     if dist is not None:

@@ -32,6 +32,14 @@ struct Slot {
     uint32_t *d_lens = nullptr;
     size_t cap_in = 0, cap_out = 0, cap_dig = 0, cap_lens = 0;
     bool busy = false;
+    // packed host output (cw_hash_compress_packed): the slice's blocks back to back, their offsets, the scan scratch,
+    // and the slice's packed size read back into a pinned word once the scan has run
+    uint8_t *d_packed = nullptr;
+    unsigned long long *d_offsets = nullptr, *d_scan = nullptr, *h_total = nullptr;
+    size_t cap_packed = 0, cap_offsets = 0, cap_scan = 0;
+    cudaEvent_t ready = nullptr;  // kernels of the slice done, h_total valid
+    size_t lo = 0, cnt = 0;       // chunks of the slice
+    unsigned long long base = 0;  // where the slice starts in the caller's packed buffer
 };
 
 struct Job {
@@ -292,6 +300,93 @@ int host_pass(cw_ctx *ctx, bool want_hash, bool want_comp, cw_hash_alg halg, cw_
     return rc;
 }
 
+// cw_hash_compress_packed: the pipeline of host_pass with a packed device-to-host leg.  A slice's packed size is only
+// known once its scan has run, so a slice takes two visits: A enqueues copy-in, the fused kernel, the pack kernels and
+// the read-back of the size (8 bytes); B, issued one slice later -- while the next slice's kernels run -- waits for that
+// word and enqueues copies of exactly the bytes that exist.
+int host_pass_packed(cw_ctx *ctx, cw_hash_alg halg, cw_comp_alg calg, cw_mode mode, const void *src, size_t chunk, size_t n,
+                     void *digests, void *packed, size_t packed_cap, uint64_t *offsets, uint32_t *lens)
+{
+    std::lock_guard<std::mutex> hg(ctx->host_mu);
+    CW_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t D = cw_digest_bytes(halg), stride = cw_compress_bound(calg, chunk);
+    static const size_t slice_bytes = [] {
+        const char *e = getenv("CW_SLICE_MB");
+        size_t mb = e ? (size_t)atoi(e) : 0;
+        return mb ? mb << 20 : kSliceBytesDefault;
+    }();
+    size_t per = slice_bytes / chunk;
+    if (per < 1) per = 1;
+    int rc = CW_OK;
+    unsigned long long base = 0;
+    // a finished slice's offsets become offsets into the caller's buffer
+    auto finish = [&](Slot &s) -> int {
+        if (!s.busy) return CW_OK;
+        s.busy = false;
+        cudaError_t e = cudaEventSynchronize(s.done);
+        if (e != cudaSuccess) return fail(ctx, e, "cudaEventSynchronize(slot)");
+        for (size_t i = 0; i < s.cnt; i++) offsets[s.lo + i] += s.base;
+        return CW_OK;
+    };
+    auto stage_b = [&](Slot &s) -> int {
+        cudaError_t e = cudaEventSynchronize(s.ready);
+        if (e != cudaSuccess) return fail(ctx, e, "cudaEventSynchronize(slice)");
+        const unsigned long long total = *s.h_total;
+        if (base + total > packed_cap) {
+            ctx->last_error = "cw_hash_compress_packed: packed buffer too small";
+            return CW_ERR_ARG;
+        }
+        s.base = base;
+        CW_CUDA(ctx, cudaMemcpyAsync((uint8_t *)packed + base, s.d_packed, total, cudaMemcpyDeviceToHost, s.st));
+        CW_CUDA(ctx, cudaMemcpyAsync(offsets + s.lo, s.d_offsets, s.cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, s.st));
+        CW_CUDA(ctx, cudaMemcpyAsync(lens + s.lo, s.d_lens, s.cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.st));
+        CW_CUDA(ctx, cudaMemcpyAsync((uint8_t *)digests + s.lo * D, s.d_dig, s.cnt * D, cudaMemcpyDeviceToHost, s.st));
+        CW_CUDA(ctx, cudaEventRecord(s.done, s.st));
+        s.busy = true;
+        base += total;
+        return CW_OK;
+    };
+    Slot *prev = nullptr;
+    size_t k = 0;
+    for (size_t lo = 0; lo < n && rc == CW_OK; lo += per, k++) {
+        const size_t cnt = (n - lo < per) ? n - lo : per;
+        Slot &s = ctx->slots[k % kSlots];
+        if ((rc = finish(s)) != CW_OK) break;
+        if ((rc = ensure(ctx, (void **)&s.d_in, &s.cap_in, per * chunk)) != CW_OK) break;
+        if ((rc = ensure(ctx, (void **)&s.d_out, &s.cap_out, per * stride)) != CW_OK) break;
+        if ((rc = ensure(ctx, (void **)&s.d_lens, &s.cap_lens, per * sizeof(uint32_t))) != CW_OK) break;
+        if ((rc = ensure(ctx, (void **)&s.d_dig, &s.cap_dig, per * D)) != CW_OK) break;
+        if ((rc = ensure(ctx, (void **)&s.d_packed, &s.cap_packed, per * stride)) != CW_OK) break;
+        if ((rc = ensure(ctx, (void **)&s.d_offsets, &s.cap_offsets, (per + 1) * sizeof(uint64_t))) != CW_OK) break;
+        if ((rc = ensure(ctx, (void **)&s.d_scan, &s.cap_scan, ((per + 1023) / 1024 + 1) * sizeof(uint64_t))) != CW_OK) break;
+        if (!s.h_total) CW_CUDA(ctx, cudaHostAlloc((void **)&s.h_total, sizeof(uint64_t), cudaHostAllocDefault));
+        if (!s.ready) CW_CUDA(ctx, cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
+        s.lo = lo;
+        s.cnt = cnt;
+        CW_CUDA(ctx, cudaMemcpyAsync(s.d_in, (const uint8_t *)src + lo * chunk, cnt * chunk, cudaMemcpyHostToDevice, s.st));
+        if ((rc = do_fused_dev(ctx, halg, calg, mode, s.d_in, chunk, cnt, s.d_dig, s.d_out, stride, s.d_lens, s.st)) != CW_OK) break;
+        CW_CUDA(ctx, cw_launch_pack(s.d_out, stride, s.d_lens, s.d_in, (uint32_t)chunk, cnt, s.d_packed, per * stride, s.d_offsets,
+                                    s.d_scan, s.st));
+        ctx->launches += 3;
+        CW_CUDA(ctx, cudaMemcpyAsync(s.h_total, s.d_offsets + cnt, sizeof(uint64_t), cudaMemcpyDeviceToHost, s.st));
+        CW_CUDA(ctx, cudaEventRecord(s.ready, s.st));
+        if (prev && (rc = stage_b(*prev)) != CW_OK) break;
+        prev = &s;
+    }
+    if (rc == CW_OK && prev) rc = stage_b(*prev);
+    for (int i = 0; i < kSlots; i++) {
+        Slot &s = ctx->slots[i];
+        if (rc == CW_OK) rc = finish(s);
+        else if (s.busy) {  // error path: let the copies into the caller's buffers end before returning
+            cudaEventSynchronize(s.done);
+            s.busy = false;
+        }
+    }
+    if (rc != CW_OK) cudaDeviceSynchronize();  // slices whose visit B never ran
+    if (rc == CW_OK) offsets[n] = base;
+    return rc;
+}
+
 void worker_loop(cw_ctx *ctx)
 {
     for (;;) {
@@ -393,6 +488,11 @@ void cw_shutdown(cw_ctx *ctx)
         if (s.d_out) cudaFree(s.d_out);
         if (s.d_dig) cudaFree(s.d_dig);
         if (s.d_lens) cudaFree(s.d_lens);
+        if (s.d_packed) cudaFree(s.d_packed);
+        if (s.d_offsets) cudaFree(s.d_offsets);
+        if (s.d_scan) cudaFree(s.d_scan);
+        if (s.h_total) cudaFreeHost(s.h_total);
+        if (s.ready) cudaEventDestroy(s.ready);
         if (s.done) cudaEventDestroy(s.done);
         if (s.st) cudaStreamDestroy(s.st);
     }
@@ -483,6 +583,36 @@ int cw_hash(cw_ctx *ctx, cw_hash_alg alg, const void *src, size_t chunk, size_t 
     return host_pass(ctx, true, false, alg, CW_COMP_LZ4, CW_MODE_COMPAT, src, chunk, n, digests, nullptr, 0, nullptr);
 }
 
+int cw_hash_skein(cw_ctx *ctx, unsigned state_bits, unsigned hash_bits, const void *src, size_t chunk, size_t n, void *digests)
+{
+    int rc = check_common(ctx, chunk, n, src);
+    if (rc != CW_OK) return rc;
+    if ((state_bits != 512u && state_bits != 256u) || hash_bits == 0u || hash_bits % 8u || hash_bits > state_bits) return CW_ERR_ARG;
+    if (n && !digests) return CW_ERR_ARG;
+    if (n == 0) return CW_OK;
+    // a KAT-sized convenience path: one allocation, one copy each way, the caller's thread waits.  The chunk kernels of
+    // cw_hash run with the chaining value of the requested digest length and write whole output blocks; the digest is
+    // the head of its block
+    CW_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t D = hash_bits / 8u, B = state_bits / 8u;
+    CwSkeinIV iv;
+    cw_make_skein_iv_bits(&iv, state_bits, hash_bits);
+    const size_t in_bytes = (n * chunk + 255) & ~(size_t)255;
+    uint8_t *d_in = nullptr;
+    CW_CUDA(ctx, cudaMalloc(&d_in, in_bytes + n * B));
+    uint8_t *d_out = d_in + in_bytes;
+    std::vector<uint8_t> blocks(n * B);
+    cudaError_t e = cudaMemcpy(d_in, src, n * chunk, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = cw_launch_hash(state_bits == 512u ? 0 : 3, iv, d_in, (uint32_t)chunk, n, d_out, 0);
+    if (e == cudaSuccess) ctx->launches++;
+    if (e == cudaSuccess) e = cudaMemcpy(blocks.data(), d_out, n * B, cudaMemcpyDeviceToHost);
+    cudaFree(d_in);
+    CW_CUDA(ctx, e);
+    for (size_t i = 0; i < n; i++) memcpy((uint8_t *)digests + i * D, blocks.data() + i * B, D);
+    return CW_OK;
+}
+
 int cw_compress(cw_ctx *ctx, cw_comp_alg alg, cw_mode mode, const void *src, size_t chunk, size_t n, void *dst,
                 size_t stride, uint32_t *lens)
 {
@@ -502,6 +632,20 @@ int cw_hash_compress(cw_ctx *ctx, cw_hash_alg halg, cw_comp_alg calg, cw_mode mo
     if (n && (!dst || !lens || !digests)) return CW_ERR_ARG;
     if (stride < cw_compress_bound(calg, chunk)) return CW_ERR_ARG;
     return host_pass(ctx, true, true, halg, calg, mode, src, chunk, n, digests, dst, stride, lens);
+}
+
+int cw_hash_compress_packed(cw_ctx *ctx, cw_hash_alg halg, cw_comp_alg calg, cw_mode mode, const void *src, size_t chunk,
+                            size_t n, void *digests, void *packed, size_t packed_cap, uint64_t *offsets, uint32_t *lens)
+{
+    int rc = check_common(ctx, chunk, n, src);
+    if (rc != CW_OK) return rc;
+    if ((int)halg < 0 || (int)halg > 2 || (int)calg < 0 || (int)calg > 1 || (int)mode < 0 || (int)mode > 1) return CW_ERR_ARG;
+    if (!offsets || (n && (!packed || !lens || !digests))) return CW_ERR_ARG;
+    if (n == 0) {
+        offsets[0] = 0;
+        return CW_OK;
+    }
+    return host_pass_packed(ctx, halg, calg, mode, src, chunk, n, digests, packed, packed_cap, offsets, lens);
 }
 
 int cw_submit(cw_ctx *ctx, cw_hash_alg halg, cw_comp_alg calg, cw_mode mode, const void *src, size_t chunk, size_t n,

@@ -17,7 +17,7 @@ struct CwSkeinIV {
     uint64_t iv256[4];  // Skein-256, 128-bit output
 };
 
-enum { CW_K_SKEIN512 = 0, CW_K_SKEIN256_128 = 1, CW_K_SHA256 = 2 };
+enum { CW_K_SKEIN512 = 0, CW_K_SKEIN256_128 = 1, CW_K_SHA256 = 2, CW_K_SKEIN256_FULL = 3 /* whole 32-byte output block */ };
 
 #ifndef CW_SKEIN_UNROLL72
 #define CW_SKEIN_UNROLL72 true
@@ -55,6 +55,17 @@ __device__ __forceinline__ void cw_hash_one(const CwSkeinIV &iv, const uint8_t *
 #pragma unroll
             for (int i = 0; i < 16; i++) out[i] = (uint8_t)(X[i >> 3] >> (8 * (i & 7)));
         }
+    } else if constexpr (ALG == CW_K_SKEIN256_FULL) {
+        uint64_t X[4];
+        cw_skein_chunk<4, 32, ALIGNED, true, PREFETCH>(iv.iv256, p, len, X);
+        if (OUT_ALIGNED) {
+            uint4 *o = reinterpret_cast<uint4 *>(out);
+            o[0] = make_uint4((uint32_t)X[0], (uint32_t)(X[0] >> 32), (uint32_t)X[1], (uint32_t)(X[1] >> 32));
+            o[1] = make_uint4((uint32_t)X[2], (uint32_t)(X[2] >> 32), (uint32_t)X[3], (uint32_t)(X[3] >> 32));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; i++) out[i] = (uint8_t)(X[i >> 3] >> (8 * (i & 7)));
+        }
     } else {
         uint32_t H[8];
         cw_sha256_chunk<ALIGNED>(p, len, H);
@@ -72,7 +83,7 @@ __device__ __forceinline__ void cw_hash_one(const CwSkeinIV &iv, const uint8_t *
 template <int ALG>
 __host__ __device__ constexpr int cw_digest_len()
 {
-    return ALG == CW_K_SKEIN512 ? 64 : (ALG == CW_K_SKEIN256_128 ? 16 : 32);
+    return ALG == CW_K_SKEIN512 ? 64 : (ALG == CW_K_SKEIN256_128 ? 16 : 32);  // SHA-256 and the full Skein-256 block: 32
 }
 
 #define CW_HASH_THREADS 64

@@ -15,6 +15,8 @@ struct CwDeviceInfo {
 cudaError_t cw_launch_hash(int alg, const CwSkeinIV &iv, const uint8_t *d_src, uint32_t chunk, uint64_t n,
                            uint8_t *d_digests, cudaStream_t st);
 void cw_make_skein_iv(CwSkeinIV *iv);
+// chaining values for Skein-<state_bits> with a digest of hash_bits; alg 3 of cw_launch_hash = Skein-256, whole 32-byte block
+void cw_make_skein_iv_bits(CwSkeinIV *iv, unsigned state_bits, unsigned hash_bits);
 
 // lz4_kernels.cu
 // work: device u64 zeroed by the caller on `st` before the launch (dynamic chunk queue)

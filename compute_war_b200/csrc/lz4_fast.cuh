@@ -5,7 +5,7 @@
 // compressed size must stay within 1 % of what LZ4_compress_default (HashAndCompress.cpp:349-355) produces.  No
 // parse order is imposed, so nothing of the sequential parser is replayed here (that is compat mode,
 // lz4_warp.cuh).  The parse is defined position-wise, so that a warp can evaluate it 128 positions at a time, and
-// it is a deterministic function of the chunk (scalar restatement: oracle/cw_oracle.c cwo_lz4_fast_compress; the
+// it is a deterministic function of the chunk (the test suite holds a scalar restatement of the rules below; the
 // tests compare the GPU output with it byte for byte):
 //
 //   * the chunk is cut into groups of four windows of 32 consecutive positions, one lane per position.  ALL

@@ -226,13 +226,25 @@ CW_HOSTDEV void cw_skein_load(uint64_t (&w)[WORDS], const uint8_t *p, unsigned a
 #endif
         return;
     }
+    if (avail >= (unsigned)WORDS * 8u) {  // a whole block behind an unaligned pointer: plain byte loads
+#pragma unroll
+        for (int i = 0; i < WORDS; i++) {
+            uint64_t v = 0;
+#pragma unroll
+            for (int k = 7; k >= 0; k--) v = (v << 8) | p[8 * i + k];
+            w[i] = v;
+        }
+        return;
+    }
+    // the last, partial block of a chunk (once per chunk): one short counted loop per word.  (The fully unrolled form
+    // "byte o of the block if o < avail" needs 64 predicates at once; nvcc 12.9 / ptxas produced wrong words from it for
+    // a few tail lengths in some kernels -- found by the ragged-size tests -- so the bound is a loop count here.)
 #pragma unroll
     for (int i = 0; i < WORDS; i++) {
+        const unsigned nb = avail > 8u * i ? (avail - 8u * i < 8u ? avail - 8u * i : 8u) : 0u;
         uint64_t v = 0;
-        for (int k = 7; k >= 0; k--) {
-            unsigned o = 8u * i + k;
-            v = (v << 8) | (o < avail ? p[o] : 0u);
-        }
+#pragma unroll 1
+        for (unsigned k = 0; k < nb; k++) v |= (uint64_t)p[8u * i + k] << (8u * k);
         w[i] = v;
     }
 }

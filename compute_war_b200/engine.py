@@ -60,8 +60,10 @@ def load_library():
     L.cw_compress_bound.argtypes = [C.c_int, sz]
     L.cw_compress_bound.restype = sz
     L.cw_hash.argtypes = [vp, C.c_int, vp, sz, sz, vp]
+    L.cw_hash_skein.argtypes = [vp, C.c_uint, C.c_uint, vp, sz, sz, vp]
     L.cw_compress.argtypes = [vp, C.c_int, C.c_int, vp, sz, sz, vp, sz, vp]
     L.cw_hash_compress.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, sz, sz, vp, vp, sz, vp]
+    L.cw_hash_compress_packed.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, sz, sz, vp, vp, sz, vp, vp]
     L.cw_hash_dev.argtypes = [vp, C.c_int, vp, sz, sz, vp, vp]
     L.cw_compress_dev.argtypes = [vp, C.c_int, C.c_int, vp, sz, sz, vp, sz, vp, vp]
     L.cw_hash_compress_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, sz, sz, vp, vp, sz, vp, vp]
@@ -152,6 +154,14 @@ class Engine:
         self._check(self.L.cw_hash(self.h, hash_alg, s.ctypes.data, chunk, n, out.ctypes.data))
         return out
 
+    def hash_skein(self, state_bits: int, hash_bits: int, src, chunk: int) -> np.ndarray:
+        """Skein-<state_bits> with a digest of hash_bits (Skein_512_Init / Skein_256_Init with any hashBitLen)"""
+        s = _host_u8(src)
+        n = s.size // chunk
+        out = np.zeros((n, hash_bits // 8), np.uint8)
+        self._check(self.L.cw_hash_skein(self.h, state_bits, hash_bits, s.ctypes.data, chunk, n, out.ctypes.data))
+        return out
+
     def do_compression(self, comp_alg: int, src, chunk: int, mode: int = MODE_COMPAT, stride: int | None = None):
         """doCompression per chunk: (blocks[n, stride], lens[n]) with the codec's own return convention"""
         s = _host_u8(src)
@@ -178,6 +188,23 @@ class Engine:
         self._check(self.L.cw_hash_compress(self.h, hash_alg, comp_alg, mode, s.ctypes.data, chunk, n, dig.ctypes.data,
                                             blocks.ctypes.data, stride, lens.ctypes.data))
         return dig, blocks, lens
+
+    def process_block_packed(self, hash_alg: int, comp_alg: int, src, chunk: int, mode: int = MODE_COMPAT, cap: int | None = None):
+        """ProcessBlock with packed output: (digests[n, D], packed bytes, offsets[n + 1] u64, lens[n])"""
+        s = _host_u8(src)
+        n = s.size // chunk
+        cap = n * compress_bound(comp_alg, chunk) if cap is None else cap
+        dig = np.zeros((n, digest_bytes(hash_alg)), np.uint8)
+        packed = np.zeros(max(cap, 1), np.uint8)
+        offsets = np.zeros(n + 1, np.uint64)
+        lens = np.zeros(n, np.uint32)
+        self._check(self.L.cw_hash_compress_packed(self.h, hash_alg, comp_alg, mode, s.ctypes.data, chunk, n, dig.ctypes.data,
+                                                   packed.ctypes.data, cap, offsets.ctypes.data, lens.ctypes.data))
+        return dig, packed[: int(offsets[n])], offsets, lens
+
+    def process_block_packed_ptr(self, hash_alg, comp_alg, mode, src_ptr, chunk, n, dig_ptr, packed_ptr, cap, offsets_ptr, lens_ptr):
+        self._check(self.L.cw_hash_compress_packed(self.h, hash_alg, comp_alg, mode, src_ptr, chunk, n, dig_ptr, packed_ptr, cap,
+                                                   offsets_ptr, lens_ptr))
 
     def process_block_ptr(self, hash_alg, comp_alg, mode, src_ptr, chunk, n, dig_ptr, blocks_ptr, stride, lens_ptr):
         """ProcessBlock on raw HOST pointers (e.g. pinned torch tensors)"""

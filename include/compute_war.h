@@ -88,6 +88,14 @@ int cw_host_unregister(cw_ctx *ctx, void *ptr);
  * HashBlockSkein256 / HashBlockSHA256 (src/hashing_perf/hash.cpp:5-46) */
 int cw_hash(cw_ctx *ctx, cw_hash_alg alg, const void *src, size_t chunk_bytes, size_t n_chunks, void *digests);
 
+/* Skein_512_Init / Skein_256_Init(ctx, hashBitLen) + Update + Final (reference_code/skein/Optimized_64bit/skein.c:226-266,
+ * :31-71, :329-408) for any digest length: state_bits 512 or 256, hash_bits a multiple of 8 up to state_bits.  The two
+ * selectors of cw_hash are the pairs (512, 512) and (256, 128); this entry exists so that every byte-aligned vector of
+ * the reference's KAT files (Skein-512/384, Skein-256/256, Skein-256/224, KAT_MCT/) runs on the GPU.  Host buffers;
+ * digest i (hash_bits / 8 bytes) goes to digests + i * hash_bits / 8. */
+int cw_hash_skein(cw_ctx *ctx, unsigned state_bits, unsigned hash_bits, const void *src, size_t chunk_bytes,
+                  size_t n_chunks, void *digests);
+
 /* doCompression(const char* s, char* d, size_t l): HashAndCompress.cpp:111, lambdas :342-355;
  * experiment.cpp:110 (lzf), :249 (lz4) -- applied to n_chunks chunks at once */
 int cw_compress(cw_ctx *ctx, cw_comp_alg alg, cw_mode mode, const void *src, size_t chunk_bytes, size_t n_chunks,
@@ -98,6 +106,17 @@ int cw_compress(cw_ctx *ctx, cw_comp_alg alg, cw_mode mode, const void *src, siz
 int cw_hash_compress(cw_ctx *ctx, cw_hash_alg halg, cw_comp_alg calg, cw_mode mode, const void *src,
                      size_t chunk_bytes, size_t n_chunks, void *digests, void *dst, size_t dst_stride,
                      uint32_t *lens);
+
+/* ProcessBlock with PACKED output: the blocks of the batch back to back in `packed` (a chunk LZF could not shrink,
+ * lens[i] == 0, is stored raw -- what the reference's caller does with lzf_compress's 0, lzf.h:59-64), offsets[i] =
+ * start of block i, offsets[n_chunks] = total bytes (u64, n_chunks + 1 entries), lens / digests as in
+ * cw_hash_compress.  The reference keeps `2 * readSize` bytes of scratch per work item and throws the blocks away
+ * (HashAndCompress.cpp:233-239,259-260); a storage front-end keeps them, and copying whole strides back costs 1.5 x
+ * the PCIe bytes of the blocks themselves.  packed_cap: capacity of `packed`; n_chunks * cw_compress_bound() always
+ * suffices, the real need is the compressed size.  CW_ERR_ARG if the blocks do not fit. */
+int cw_hash_compress_packed(cw_ctx *ctx, cw_hash_alg halg, cw_comp_alg calg, cw_mode mode, const void *src,
+                            size_t chunk_bytes, size_t n_chunks, void *digests, void *packed, size_t packed_cap,
+                            uint64_t *offsets, uint32_t *lens);
 
 /* ---- device-buffer calls: same contracts, every pointer is device memory on ctx's GPU ----
  * Asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the context's own stream).  This is

@@ -248,9 +248,9 @@ int main(int argc, char **argv)
             for (size_t i = 0; i < n * (size_t)D; i++) dsum = dsum * 1099511628211ull + dig[i];
             printf("{\"impl\": \"reference\", \"kind\": \"reference\", \"hash\": \"%s\", \"comp\": \"%s\", "
                    "\"chunk\": %zu, \"n_chunks\": %zu, \"threads\": %d, \"host_cpus\": %d, \"seconds\": %.6f, "
-                   "\"gbps\": %.6f, \"ratio\": %.6f, \"digest_fnv\": \"%016llx\"}\n",
+                   "\"gbps\": %.6f, \"ratio\": %.6f, \"comp_bytes\": %llu, \"digest_fnv\": \"%016llx\"}\n",
                    argv[2], argv[3], chunk, n, threads, ncpu, sec, (double)(n * chunk) / sec / 1e9,
-                   (double)csum / (double)(n * chunk), (unsigned long long)dsum);
+                   (double)csum / (double)(n * chunk), (unsigned long long)csum, (unsigned long long)dsum);
             fflush(stdout);
         }
         return 0;

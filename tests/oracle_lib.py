@@ -208,6 +208,24 @@ def ref_cli(*args: str) -> str:
     return subprocess.check_output([os.path.join(REF_DIR, "ref_cli"), *args], text=True)
 
 
+_REF_BENCH_EXE = None
+
+
+def ref_cli_bench_exe() -> str:
+    """the driver whose Skein is compiled for x86-64-v3 (oracle/Makefile) if this host runs it, else the portable one"""
+    global _REF_BENCH_EXE
+    if _REF_BENCH_EXE is None:
+        _REF_BENCH_EXE = os.path.join(REF_DIR, "ref_cli")
+        v3 = os.path.join(REF_DIR, "ref_cli_v3")
+        try:
+            if os.access(v3, os.X_OK) and subprocess.run([v3, "bench", "skein512", "lz4", "8192", "64", "1", "0"],
+                                                          capture_output=True, timeout=60).returncode == 0:
+                _REF_BENCH_EXE = v3
+        except Exception:
+            pass
+    return _REF_BENCH_EXE
+
+
 def ref_hash_chunks(alg: int, data, chunk: int) -> np.ndarray:
     d = _as_u8(data)
     with tempfile.TemporaryDirectory() as td:

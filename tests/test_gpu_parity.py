@@ -44,42 +44,71 @@ def test_hash_corpus_sample_matches_reference(eng, golden):
     assert checked > 500
 
 
-@pytest.mark.parametrize("name", ["ShortMsgKAT_512", "LongMsgKAT_512", "ShortMsgKAT_256", "LongMsgKAT_256"])
+@pytest.mark.parametrize("name", ["ShortMsgKAT_512", "LongMsgKAT_512", "ShortMsgKAT_384", "ShortMsgKAT_256", "LongMsgKAT_256",
+                                  "ShortMsgKAT_224"])
 def test_skein_kat_vectors(eng, golden, name):
-    """byte-aligned NIST KAT messages, each hashed as a single chunk.  Skein-512/512 directly; the 256-bit state
-    files pin Skein-256 with a 256-bit digest, which the engine does not expose, so for those the check is
-    oracle(KAT)-pinned Skein-256/128 of the same messages."""
+    """every byte-aligned message of the reference's NIST KAT files (reference_code/skein/KAT_MCT/), each hashed as a
+    single chunk ON THE GPU with the file's own (state, digest) pair: Skein-512/512, Skein-512/384, Skein-256/256 and
+    Skein-256/224 through cw_hash_skein; the 512/512 file also through the cw_hash selector the tools use"""
     k = golden["kat"][name]
     cases = [(b, m, md) for b, m, md in k["cases"] if b % 8 == 0 and b > 0]
     assert len(cases) >= 64
     for bits, msg, md in cases:
         m = np.frombuffer(bytes.fromhex(msg), np.uint8)
-        if k["state"] == 512:
-            got = eng.do_hashing(cw.HASH_SKEIN512, m, len(m))
-            assert got.tobytes().hex() == md, (name, bits)
-        else:
-            got = eng.do_hashing(cw.HASH_SKEIN256_128, m, len(m))
-            assert got.tobytes() == O.skein(256, 128, m.tobytes()), (name, bits)
+        assert eng.hash_skein(k["state"], k["hash"], m, len(m)).tobytes().hex() == md, (name, bits)
+        if (k["state"], k["hash"]) == (512, 512):
+            assert eng.do_hashing(cw.HASH_SKEIN512, m, len(m)).tobytes().hex() == md, (name, bits)
+        if k["state"] == 256:  # the variant the reference's tools run has no KAT of its own: pinned through the oracle
+            assert eng.do_hashing(cw.HASH_SKEIN256_128, m, len(m)).tobytes() == O.skein(256, 128, m.tobytes()), (name, bits)
 
 
-def test_skein_golden_kat_512(eng, golden):
+def test_skein_kat_batched_as_chunks(eng, golden):
+    """the same vectors as batches: all messages of one length form one call (chunk = that length)"""
+    for name in ("ShortMsgKAT_512", "ShortMsgKAT_384", "ShortMsgKAT_256", "ShortMsgKAT_224"):
+        k = golden["kat"][name]
+        by_len = {}
+        for b, m, md in k["cases"]:
+            if b % 8 == 0 and b > 0:
+                by_len.setdefault(b // 8, []).append((m, md))
+        for ln, items in by_len.items():
+            d = np.frombuffer(b"".join(bytes.fromhex(m) for m, _ in items), np.uint8)
+            got = eng.hash_skein(k["state"], k["hash"], d, ln)
+            assert [g.tobytes().hex() for g in got] == [md for _, md in items], (name, ln)
+
+
+def test_skein_golden_kat(eng, golden):
+    """skein_golden_kat.txt: every sequential, un-keyed, byte-aligned case of Skein-256 and Skein-512 whose digest fits
+    one output block (digest <= state), on the GPU"""
     n = 0
     for state, hbits, mbits, msg, res in golden["kat"]["golden"]:
-        if state == 512 and hbits == 512 and mbits % 8 == 0 and mbits > 0:
+        if state in (256, 512) and hbits <= state and hbits % 8 == 0 and mbits % 8 == 0 and mbits > 0:
             m = np.frombuffer(bytes.fromhex(msg), np.uint8)
-            assert eng.do_hashing(cw.HASH_SKEIN512, m, len(m)).tobytes().hex() == res, mbits
+            assert eng.hash_skein(state, hbits, m, len(m)).tobytes().hex() == res, (state, hbits, mbits)
             n += 1
-    assert n >= 30
+    assert n >= 60
 
 
-def test_skein_monte_carlo_512_first_checkpoint(eng, golden):
-    """MonteCarlo_512 j=0: 1000 chained hashes of a 128-byte message (genKAT.c:288-296), through the GPU"""
+def test_skein_monte_carlo_512_all_checkpoints(eng, golden):
+    """MonteCarlo_512, all 100 checkpoints: 100 x 1000 chained hashes of a 128-byte message (genKAT.c:288-296), every
+    one of them a GPU call"""
     k = golden["kat"]["MonteCarlo_512"]
     msg = bytes.fromhex(k["seed"])
-    for _ in range(1000):
-        md = eng.do_hashing(cw.HASH_SKEIN512, np.frombuffer(msg, np.uint8), 128).tobytes()
-        msg = md + msg[:64]
-    assert md.hex() == k["md"][0]
+    for j in range(100):
+        for _ in range(1000):
+            md = eng.do_hashing(cw.HASH_SKEIN512, np.frombuffer(msg, np.uint8), 128).tobytes()
+            msg = md + msg[:64]
+        assert md.hex() == k["md"][j], j
+
+
+def test_skein_monte_carlo_256_first_checkpoints(eng, golden):
+    """MonteCarlo_256 (Skein-256/256), the first 5 checkpoints through cw_hash_skein"""
+    k = golden["kat"]["MonteCarlo_256"]
+    msg = bytes.fromhex(k["seed"])
+    for j in range(5):
+        for _ in range(1000):
+            md = eng.hash_skein(256, 256, np.frombuffer(msg, np.uint8), 128).tobytes()
+            msg = md + msg[:96]
+        assert md.hex() == k["md"][j], j
 
 
 @pytest.mark.parametrize("chunk", [1, 7, 31, 32, 33, 63, 64, 65, 100, 128, 1000, 4096, 4104, 8192, 65536])
@@ -212,6 +241,13 @@ def test_fast_mode_roundtrips_and_ratio(eng, golden, alg):
                 continue
             blocks, lens = eng.do_compression(alg, d, chunk, cw.MODE_FAST)
             assert O.verify_roundtrip(alg, d, chunk, blocks, lens) == 0
+            if O.have_ref_cli():  # the reference's own LZ4_decompress_safe / lzf_decompress (built from its archives)
+                back = O.ref_decompress_chunks(alg, chunk, blocks, lens)
+                assert len(back) == rec["n"] * chunk and (back == d[: len(back)]).all(), (ent["name"], chunk)
+            if alg == O.COMP_LZ4:  # the fast parse is a deterministic function of the chunk: byte-equal to its restatement
+                fb, fl = O.lz4_fast_chunks(d, chunk)
+                assert (lens == fl).all() and all((blocks[i, : fl[i]] == fb[i, : fl[i]]).all() for i in range(len(fl))), \
+                    (ent["name"], chunk)
             mine = sum(int(x) if x else chunk for x in lens)
             theirs = sum(int(x) if x else chunk for x in rec[O.COMP_NAMES[alg] + "_lens"])
             assert mine <= theirs * 1.01, (ent["name"], chunk, mine, theirs)
@@ -410,6 +446,94 @@ def test_packed_output(eng, alg):
         seg = p[want[i]: want[i + 1]]
         assert (seg == (b[i, : lens_h[i]] if lens_h[i] else s_h[i])).all(), i
     assert (p[want[-1]:] == 0).all()  # nothing written past the end
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("halg", [O.HASH_SKEIN512, O.HASH_SKEIN256_128, O.HASH_SHA256])
+def test_process_block_fused_ragged_sizes(eng, golden, halg, mode):
+    """fused pass, both LZ4 modes, chunk sizes whose last hash block has every length 1..64 (and unaligned buffers):
+    digests equal the oracle's, blocks decode back"""
+    blob = golden["blob"]
+    for chunk in list(range(4097, 4097 + 64)) + [13, 100, 8191, 8193, 16400]:
+        n = 5
+        d = blob[3: 3 + n * chunk].copy()
+        dig, blocks, lens = eng.process_block(halg, O.COMP_LZ4, d, chunk, mode)
+        assert (dig == O.hash_chunks(halg, d, chunk)).all(), (chunk, mode)
+        assert O.verify_roundtrip(O.COMP_LZ4, d, chunk, blocks, lens) == 0, (chunk, mode)
+
+
+@pytest.mark.parametrize("halg,calg,mode", [(O.HASH_SKEIN512, O.COMP_LZ4, 0), (O.HASH_SKEIN512, O.COMP_LZ4, 1),
+                                            (O.HASH_SKEIN256_128, O.COMP_LZF, 0), (O.HASH_SHA256, O.COMP_LZ4, 0)])
+def test_packed_host_output(eng, halg, calg, mode):
+    """cw_hash_compress_packed: packed bytes / offsets / lens / digests equal the strided call's, across pipeline slices
+    (72 MiB > one 64 MiB slice), incompressible chunks included (LZF: stored raw); a short buffer is refused"""
+    from compute_war_b200.sharding import packed_offsets
+    chunk, n = 8192, 9216 + 17
+    d = O.synth(chunk, 5, n)
+    dig0, blocks, lens0 = eng.process_block(halg, calg, d, chunk, mode)
+    dig, packed, offsets, lens = eng.process_block_packed(halg, calg, d, chunk, mode)
+    assert (dig == dig0).all() and (lens == lens0).all()
+    want = packed_offsets(lens0, chunk)
+    assert (offsets == want).all() and len(packed) == int(want[-1])
+    dv = d.reshape(n, chunk)
+    for i in list(range(0, 64)) + list(range(8180, 8200)) + list(range(n - 64, n)):  # both sides of the slice boundary
+        seg = packed[int(want[i]): int(want[i + 1])]
+        assert (seg == (blocks[i, : lens0[i]] if lens0[i] else dv[i])).all(), i
+    # all of it: unpack into a strided array and decode on the device
+    if calg == O.COMP_LZ4:
+        stride = cw.compress_bound(calg, chunk)
+        b2 = np.zeros((n, stride), np.uint8)
+        for i in range(n):
+            b2[i, : lens0[i]] = packed[int(want[i]): int(want[i + 1])]
+        assert O.verify_roundtrip(calg, d, chunk, b2, lens0) == 0
+    with pytest.raises(cw.EngineError):
+        eng.process_block_packed(halg, calg, d, chunk, mode, cap=int(want[-1]) - 1)
+    # the context still works after the refusal, and an empty batch yields offsets = [0]
+    dig3, packed3, offsets3, _ = eng.process_block_packed(halg, calg, d[: 100 * chunk], chunk, mode)
+    assert (dig3 == dig0[:100]).all() and (offsets3 == want[:101]).all()
+    assert eng.process_block_packed(halg, calg, d[:0], chunk, mode)[2].tolist() == [0]
+
+
+def test_pack_grow_then_dedup_on_one_context(eng):
+    """dedup, then a pack call that needs more scratch than any before it, then dedup again, on ONE context (ADVICE r01:
+    a stray cudaFree in the pack path once freed the dedup table); run under compute-sanitizer by tools/gpu_memcheck.sh"""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda:0")
+    chunk = 4096
+
+    def dedup(n, seed):
+        src = torch.empty(n * chunk, dtype=torch.uint8, device=dev)
+        eng.synth_dev(src.data_ptr(), chunk, seed, n)
+        src.view(n, chunk)[n // 2:] = src.view(n, chunk)[: n - n // 2]  # second half repeats the first
+        dig = torch.empty(n * 16, dtype=torch.uint8, device=dev)
+        eng.hash_dev(cw.HASH_SKEIN256_128, src.data_ptr(), chunk, n, dig.data_ptr())
+        first = torch.full((n,), -1, dtype=torch.int32, device=dev)
+        uniq = torch.zeros(1, dtype=torch.int64, device=dev)
+        eng.dedup_dev(dig.data_ptr(), 16, n, first.data_ptr(), uniq.data_ptr())
+        eng.sync()
+        want, want_u = O.dedup_first(dig.cpu().numpy().reshape(n, 16))
+        assert (first.cpu().numpy().astype(np.uint32) == want).all() and int(uniq.item()) == want_u
+
+    def pack(n):
+        src = torch.empty(n * chunk, dtype=torch.uint8, device=dev)
+        eng.synth_dev(src.data_ptr(), chunk, 3, n)
+        stride = cw.compress_bound(O.COMP_LZ4, chunk)
+        blocks = torch.zeros(n * stride, dtype=torch.uint8, device=dev)
+        lens = torch.empty(n, dtype=torch.int32, device=dev)
+        eng.compress_dev(O.COMP_LZ4, cw.MODE_COMPAT, src.data_ptr(), chunk, n, blocks.data_ptr(), stride, lens.data_ptr())
+        packed = torch.zeros(n * stride, dtype=torch.uint8, device=dev)
+        offsets = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        eng.pack_dev(blocks.data_ptr(), stride, lens.data_ptr(), src.data_ptr(), chunk, n, packed.data_ptr(), n * stride,
+                     offsets.data_ptr())
+        eng.sync()
+        assert int(offsets[-1].item()) == int(lens.sum(dtype=torch.int64).item())
+
+    dedup(20000, 1)
+    pack(3000)
+    pack(60000)  # grows every scratch of the pack path
+    dedup(20000, 2)
+    dedup(5000, 3)
+    pack(100)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -5,8 +5,10 @@
 // HashAndCompress.cpp:95-98, doHashing :119-134, doCompression :111,342-355, ProcessBlock :231-261,
 // HashOffload HashOffload.h:15-64 + hashing_offload_entry_point HashAndCompress.cpp:160-183.
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <condition_variable>
 #include <deque>
 #include <map>
@@ -55,6 +57,48 @@ struct Job {
     cw_complete_fn cb;
     void *user;
 };
+// ---- small-batch front-end: the reference's callers hand over one small work item at a time from many threads
+// (ProcessBlock per 32 KiB work item from --c-threads workers, HashAndCompress.cpp:160-183,263-272; HashOffload.h:15-64).
+// Work items of equal (hash, codec, mode, chunk size) that arrive while the GPU is busy are gathered in one pinned
+// batch buffer -- every caller copies its own bytes in and, afterwards, its own results out, in parallel -- and one
+// copy in / one launch / one set of copies out serves them all. ----
+constexpr size_t kBatchBytes = 16u << 20;  // input bytes per batch buffer
+constexpr int kBatchBufs = 3;
+constexpr size_t kSmallCall = 4u << 20;    // host-buffer calls up to this many input bytes go through the batcher
+constexpr size_t kBatchMinChunk = 512;     // smaller chunks: direct path (digest / length arrays would dominate)
+
+struct BatchBuf {
+    enum State { FREE, OPEN, SEALED, RUNNING, DONE };
+    uint8_t *h_in = nullptr, *h_out = nullptr, *h_dig = nullptr;
+    uint32_t *h_lens = nullptr;
+    uint8_t *d_in = nullptr, *d_out = nullptr, *d_dig = nullptr;
+    uint32_t *d_lens = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
+    State state = FREE;
+    std::vector<std::pair<Job, size_t>> jobs;  // cw_submit jobs riding in this batch, with their first chunk
+    cw_hash_alg halg = CW_HASH_SKEIN512;
+    cw_comp_alg calg = CW_COMP_LZ4;
+    cw_mode mode = CW_MODE_COMPAT;
+    size_t chunk = 0, stride = 0, D = 0, cap_chunks = 0;
+    size_t chunks = 0;   // chunks reserved so far
+    int copying_in = 0;  // callers still copying their input in
+    int readers = 0;     // callers that still have to copy their results out
+    int rc = 0;
+    uint64_t gen = 0;
+};
+
+struct Batcher {
+    std::mutex mu;
+    std::condition_variable cv_worker, cv_callers;
+    BatchBuf bufs[kBatchBufs];
+    int open = -1;
+    std::thread th;
+    bool started = false, stop = false, failed_alloc = false;
+    std::deque<int> inflight;  // worker-private: launched, not yet complete
+};
+
+
 
 }  // namespace
 
@@ -86,10 +130,13 @@ struct cw_ctx {
     std::mutex q_mu;
     std::condition_variable q_cv, done_cv;
     std::deque<Job> queue;
+    std::deque<int> done_bufs;  // batch buffers whose launch is complete and that carry cw_submit jobs
     std::map<cw_ticket, int> finished;  // status of completed jobs nobody has waited for yet
-    cw_ticket done_upto = 0;            // jobs complete in ticket order (one worker)
+    std::map<cw_ticket, bool> pending;  // submitted, not complete (small jobs travel in groups: no ticket order)
     cw_ticket next_ticket = 1;
     bool stop = false;
+    Batcher bat;
+    std::atomic<uint64_t> batches{0}, batched_calls{0};
 };
 
 namespace {
@@ -387,27 +434,294 @@ int host_pass_packed(cw_ctx *ctx, cw_hash_alg halg, cw_comp_alg calg, cw_mode mo
     return rc;
 }
 
+
+// ---------------- small-batch front-end ----------------
+bool batch_alloc(cw_ctx *ctx, BatchBuf &b)
+{
+    if (b.h_in) return true;
+    const size_t out_bytes = 2 * kBatchBytes + (kBatchBytes / kBatchMinChunk) * 32;  // stride <= chunk + chunk/255 + 16
+    const size_t dig_bytes = (kBatchBytes / kBatchMinChunk) * 64, len_bytes = (kBatchBytes / kBatchMinChunk) * 4;
+    bool ok = cudaHostAlloc((void **)&b.h_in, kBatchBytes, cudaHostAllocDefault) == cudaSuccess &&
+              cudaHostAlloc((void **)&b.h_out, out_bytes, cudaHostAllocDefault) == cudaSuccess &&
+              cudaHostAlloc((void **)&b.h_dig, dig_bytes, cudaHostAllocDefault) == cudaSuccess &&
+              cudaHostAlloc((void **)&b.h_lens, len_bytes, cudaHostAllocDefault) == cudaSuccess &&
+              cudaMalloc(&b.d_in, kBatchBytes) == cudaSuccess && cudaMalloc(&b.d_out, out_bytes) == cudaSuccess &&
+              cudaMalloc(&b.d_dig, dig_bytes) == cudaSuccess && cudaMalloc(&b.d_lens, len_bytes) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&b.st, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) fail(ctx, cudaGetLastError(), "batch buffer allocation");
+    return ok;
+}
+
+void batch_free(BatchBuf &b)
+{
+    if (b.h_in) cudaFreeHost(b.h_in);
+    if (b.h_out) cudaFreeHost(b.h_out);
+    if (b.h_dig) cudaFreeHost(b.h_dig);
+    if (b.h_lens) cudaFreeHost(b.h_lens);
+    if (b.d_in) cudaFree(b.d_in);
+    if (b.d_out) cudaFree(b.d_out);
+    if (b.d_dig) cudaFree(b.d_dig);
+    if (b.d_lens) cudaFree(b.d_lens);
+    if (b.done) cudaEventDestroy(b.done);
+    if (b.st) cudaStreamDestroy(b.st);
+    b = BatchBuf();
+}
+
+// one copy in, one launch, copies out; returns with the work enqueued on the buffer's stream
+int batch_launch(cw_ctx *ctx, BatchBuf &b)
+{
+    CW_CUDA(ctx, cudaMemcpyAsync(b.d_in, b.h_in, b.chunks * b.chunk, cudaMemcpyHostToDevice, b.st));
+    int rc = do_fused_dev(ctx, b.halg, b.calg, b.mode, b.d_in, b.chunk, b.chunks, b.d_dig, b.d_out, b.stride, b.d_lens, b.st);
+    if (rc != CW_OK) return rc;
+    CW_CUDA(ctx, cudaMemcpyAsync(b.h_out, b.d_out, b.chunks * b.stride, cudaMemcpyDeviceToHost, b.st));
+    CW_CUDA(ctx, cudaMemcpyAsync(b.h_lens, b.d_lens, b.chunks * sizeof(uint32_t), cudaMemcpyDeviceToHost, b.st));
+    CW_CUDA(ctx, cudaMemcpyAsync(b.h_dig, b.d_dig, b.chunks * b.D, cudaMemcpyDeviceToHost, b.st));
+    CW_CUDA(ctx, cudaEventRecord(b.done, b.st));
+    ctx->batches++;
+    return CW_OK;
+}
+
+// B.mu held: the launch of buffer i is complete
+void batch_done(cw_ctx *ctx, int i)
+{
+    Batcher &B = ctx->bat;
+    B.bufs[i].state = BatchBuf::DONE;
+    B.cv_callers.notify_all();
+    if (!B.bufs[i].jobs.empty()) {  // cw_submit jobs: the offload thread copies their results out and completes them
+        {
+            std::lock_guard<std::mutex> lk(ctx->q_mu);
+            ctx->done_bufs.push_back(i);
+        }
+        ctx->q_cv.notify_one();
+    }
+}
+
+void batch_worker(cw_ctx *ctx)
+{
+    Batcher &B = ctx->bat;
+    cudaSetDevice(ctx->device);
+    std::unique_lock<std::mutex> lk(B.mu);
+    for (;;) {
+        // a buffer is ready when it is sealed (full, or of another kind than the next caller) or simply holds what arrived
+        // while the GPU was busy -- an idle worker takes whatever there is -- and nobody is still copying into it
+        int ready = -1;
+        for (int i = 0; i < kBatchBufs && ready < 0; i++) {
+            BatchBuf &b = B.bufs[i];
+            if (b.copying_in == 0 && b.chunks > 0 && (b.state == BatchBuf::SEALED || b.state == BatchBuf::OPEN)) ready = i;
+        }
+        if (ready >= 0) {
+            BatchBuf &b = B.bufs[ready];
+            if (B.open == ready) B.open = -1;
+            b.state = BatchBuf::RUNNING;
+            lk.unlock();
+            const int rc = batch_launch(ctx, b);
+            lk.lock();
+            b.rc = rc;
+            if (rc == CW_OK) B.inflight.push_back(ready);
+            else {
+                cudaStreamSynchronize(b.st);
+                batch_done(ctx, ready);
+            }
+            continue;
+        }
+        if (!B.inflight.empty()) {  // nothing to launch: finish the oldest launch
+            const int i = B.inflight.front();
+            B.inflight.pop_front();
+            BatchBuf &b = B.bufs[i];
+            lk.unlock();
+            const cudaError_t e = cudaEventSynchronize(b.done);
+            lk.lock();
+            if (e != cudaSuccess) b.rc = fail(ctx, e, "cudaEventSynchronize(batch)");
+            batch_done(ctx, i);
+            continue;
+        }
+        if (B.stop) return;
+        B.cv_worker.wait(lk);
+    }
+}
+
+// reserve room for n chunks in a batch buffer of this kind; returns the buffer (its generation in *gen, first chunk in
+// *first) with copying_in and readers raised, or nullptr if the batcher cannot be used.  B.mu held by the caller.
+BatchBuf *batch_reserve(cw_ctx *ctx, std::unique_lock<std::mutex> &lk, cw_hash_alg halg, cw_comp_alg calg, cw_mode mode,
+                        size_t chunk, size_t n, size_t *first)
+{
+    Batcher &B = ctx->bat;
+    if (B.failed_alloc) return nullptr;
+    if (!B.started) {
+        B.started = true;
+        B.th = std::thread(batch_worker, ctx);
+    }
+    const size_t stride = cw_compress_bound(calg, chunk);
+    for (;;) {
+        if (B.open >= 0) {
+            BatchBuf &b = B.bufs[B.open];
+            if (b.state == BatchBuf::OPEN && b.halg == halg && b.calg == calg && b.mode == mode && b.chunk == chunk &&
+                b.chunks + n <= b.cap_chunks) {
+                *first = b.chunks;
+                b.chunks += n;
+                b.copying_in++;
+                b.readers++;
+                return &b;
+            }
+            b.state = BatchBuf::SEALED;  // full, or another kind of work: off it goes
+            B.open = -1;
+            B.cv_worker.notify_one();
+        }
+        int f = -1;
+        for (int i = 0; i < kBatchBufs && f < 0; i++)
+            if (B.bufs[i].state == BatchBuf::FREE) f = i;
+        if (f < 0) {
+            B.cv_callers.wait(lk);
+            continue;
+        }
+        BatchBuf &b = B.bufs[f];
+        if (!batch_alloc(ctx, b)) {
+            B.failed_alloc = true;
+            return nullptr;
+        }
+        b.state = BatchBuf::OPEN;
+        b.halg = halg;
+        b.calg = calg;
+        b.mode = mode;
+        b.chunk = chunk;
+        b.stride = stride;
+        b.D = cw_digest_bytes(halg);
+        b.cap_chunks = kBatchBytes / chunk;
+        b.chunks = 0;
+        b.rc = CW_OK;
+        B.open = f;  // the reservation itself happens in the branch above
+    }
+}
+
+void batch_copy_out(const BatchBuf &b, size_t first, size_t n, void *digests, void *dst, size_t stride, uint32_t *lens)
+{
+    memcpy(digests, b.h_dig + first * b.D, n * b.D);
+    memcpy(lens, b.h_lens + first, n * sizeof(uint32_t));
+    for (size_t i = 0; i < n; i++)  // only the bytes that exist (LZF: 0 = "store raw", nothing to copy)
+        memcpy((uint8_t *)dst + i * stride, b.h_out + (first + i) * b.stride, b.h_lens[first + i]);
+}
+
+void batch_release(cw_ctx *ctx, BatchBuf *b)
+{
+    Batcher &B = ctx->bat;
+    std::lock_guard<std::mutex> lk(B.mu);
+    if (--b->readers == 0) {
+        b->state = BatchBuf::FREE;
+        b->jobs.clear();
+        b->chunks = 0;
+        b->gen++;
+        B.cv_callers.notify_all();
+    }
+}
+
+// a blocking small call: join the open batch, wait for it, take the results.  Returns CW_ERR_UNSUPPORTED if the
+// batcher is not available (the caller then uses the direct pipeline).
+int batch_call(cw_ctx *ctx, cw_hash_alg halg, cw_comp_alg calg, cw_mode mode, const void *src, size_t chunk, size_t n,
+               void *digests, void *dst, size_t stride, uint32_t *lens)
+{
+    Batcher &B = ctx->bat;
+    size_t first = 0;
+    BatchBuf *b;
+    uint64_t gen;
+    {
+        std::unique_lock<std::mutex> lk(B.mu);
+        b = batch_reserve(ctx, lk, halg, calg, mode, chunk, n, &first);
+        if (!b) return CW_ERR_UNSUPPORTED;
+        gen = b->gen;
+    }
+    memcpy(b->h_in + first * chunk, src, n * chunk);
+    int rc;
+    {
+        std::unique_lock<std::mutex> lk(B.mu);
+        b->copying_in--;
+        B.cv_worker.notify_one();
+        B.cv_callers.wait(lk, [&] { return b->gen == gen && b->state == BatchBuf::DONE; });
+        rc = b->rc;
+    }
+    if (rc == CW_OK) batch_copy_out(*b, first, n, digests, dst, stride, lens);
+    batch_release(ctx, b);
+    ctx->batched_calls++;
+    return rc;
+}
+
+bool batchable(size_t chunk, size_t n)
+{
+    static const bool off = getenv("CW_NO_BATCHER") != nullptr;  // A/B knob for the profiling scripts
+    return !off && chunk >= kBatchMinChunk && n > 0 && n * chunk <= kSmallCall;
+}
+
+void complete_job(cw_ctx *ctx, const Job &j, int rc)
+{
+    {
+        // the status is visible before the callback runs, so the callback itself may call cw_wait; a job with a
+        // callback keeps no entry (its status was delivered), so callback-only callers do not grow the map
+        std::lock_guard<std::mutex> lk(ctx->q_mu);
+        if (!j.cb) ctx->finished[j.ticket] = rc;
+        ctx->pending.erase(j.ticket);
+    }
+    ctx->done_cv.notify_all();
+    if (j.cb) j.cb(j.ticket, rc, j.user);
+}
+
+// cw_submit of a small job: the submitting thread copies the input into the open batch (in parallel with other
+// submitters) and returns; the job rides in that batch.  false: the batcher is not available.
+bool batch_submit(cw_ctx *ctx, const Job &j)
+{
+    Batcher &B = ctx->bat;
+    size_t first = 0;
+    BatchBuf *b;
+    {
+        std::unique_lock<std::mutex> lk(B.mu);
+        b = batch_reserve(ctx, lk, j.halg, j.calg, j.mode, j.chunk, j.n, &first);
+        if (!b) return false;
+        if (!b->jobs.empty()) b->readers--;  // the submitted jobs of a batch count as one reader: the offload thread
+        b->jobs.emplace_back(j, first);
+    }
+    memcpy(b->h_in + first * j.chunk, j.src, j.n * j.chunk);
+    {
+        std::lock_guard<std::mutex> lk(B.mu);
+        b->copying_in--;
+    }
+    B.cv_worker.notify_one();
+    return true;
+}
+
+// offload thread: a batch that carries submitted jobs is complete
+void finish_batch_jobs(cw_ctx *ctx, int i)
+{
+    BatchBuf &b = ctx->bat.bufs[i];
+    for (auto &jf : b.jobs) {
+        if (b.rc == CW_OK) batch_copy_out(b, jf.second, jf.first.n, jf.first.digests, jf.first.dst, jf.first.stride, jf.first.lens);
+        complete_job(ctx, jf.first, b.rc);
+    }
+    ctx->batched_calls += b.jobs.size();
+    batch_release(ctx, &b);
+}
+
 void worker_loop(cw_ctx *ctx)
 {
     for (;;) {
         Job j;
+        int done_buf = -1;
         {
             std::unique_lock<std::mutex> lk(ctx->q_mu);
-            ctx->q_cv.wait(lk, [&] { return ctx->stop || !ctx->queue.empty(); });
-            if (ctx->queue.empty()) return;  // stop requested and drained
-            j = ctx->queue.front();
-            ctx->queue.pop_front();
+            ctx->q_cv.wait(lk, [&] { return ctx->stop || !ctx->queue.empty() || !ctx->done_bufs.empty(); });
+            if (!ctx->done_bufs.empty()) {
+                done_buf = ctx->done_bufs.front();
+                ctx->done_bufs.pop_front();
+            } else if (!ctx->queue.empty()) {
+                j = ctx->queue.front();
+                ctx->queue.pop_front();
+            } else if (ctx->pending.empty())
+                return;  // stop requested and everything delivered
+            else {
+                ctx->q_cv.wait_for(lk, std::chrono::milliseconds(1));  // jobs still riding in batches
+                continue;
+            }
         }
-        int rc = host_pass(ctx, true, true, j.halg, j.calg, j.mode, j.src, j.chunk, j.n, j.digests, j.dst, j.stride, j.lens);
-        {
-            // the status is visible before the callback runs, so the callback itself may call cw_wait; a job with a
-            // callback keeps no entry (its status was delivered), so callback-only callers do not grow the map
-            std::lock_guard<std::mutex> lk(ctx->q_mu);
-            if (!j.cb) ctx->finished[j.ticket] = rc;
-            ctx->done_upto = j.ticket;
-        }
-        ctx->done_cv.notify_all();
-        if (j.cb) j.cb(j.ticket, rc, j.user);
+        if (done_buf >= 0) finish_batch_jobs(ctx, done_buf);
+        else complete_job(ctx, j, host_pass(ctx, true, true, j.halg, j.calg, j.mode, j.src, j.chunk, j.n, j.digests, j.dst, j.stride, j.lens));
     }
 }
 
@@ -481,8 +795,17 @@ void cw_shutdown(cw_ctx *ctx)
         ctx->q_cv.notify_all();
         ctx->worker.join();
     }
+    if (ctx->bat.started) {
+        {
+            std::lock_guard<std::mutex> lk(ctx->bat.mu);
+            ctx->bat.stop = true;
+        }
+        ctx->bat.cv_worker.notify_all();
+        ctx->bat.th.join();
+    }
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    for (auto &b : ctx->bat.bufs) batch_free(b);
     for (auto &s : ctx->slots) {
         if (s.d_in) cudaFree(s.d_in);
         if (s.d_out) cudaFree(s.d_out);
@@ -506,6 +829,12 @@ void cw_shutdown(cw_ctx *ctx)
         if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+void cw_batch_stats(const cw_ctx *ctx, uint64_t *batches, uint64_t *calls)
+{
+    if (batches) *batches = ctx ? ctx->batches.load() : 0;
+    if (calls) *calls = ctx ? ctx->batched_calls.load() : 0;
 }
 
 const char *cw_last_error(const cw_ctx *ctx) { return ctx ? ctx->last_error.c_str() : g_init_error.c_str(); }
@@ -631,6 +960,10 @@ int cw_hash_compress(cw_ctx *ctx, cw_hash_alg halg, cw_comp_alg calg, cw_mode mo
     if ((int)halg < 0 || (int)halg > 2 || (int)calg < 0 || (int)calg > 1 || (int)mode < 0 || (int)mode > 1) return CW_ERR_ARG;
     if (n && (!dst || !lens || !digests)) return CW_ERR_ARG;
     if (stride < cw_compress_bound(calg, chunk)) return CW_ERR_ARG;
+    if (batchable(chunk, n)) {  // small work items from many threads share batches (HashAndCompress.cpp:263-272)
+        rc = batch_call(ctx, halg, calg, mode, src, chunk, n, digests, dst, stride, lens);
+        if (rc != CW_ERR_UNSUPPORTED) return rc;
+    }
     return host_pass(ctx, true, true, halg, calg, mode, src, chunk, n, digests, dst, stride, lens);
 }
 
@@ -657,10 +990,16 @@ int cw_submit(cw_ctx *ctx, cw_hash_alg halg, cw_comp_alg calg, cw_mode mode, con
     if ((int)halg < 0 || (int)halg > 2 || (int)calg < 0 || (int)calg > 1 || (int)mode < 0 || (int)mode > 1) return CW_ERR_ARG;
     if (n && (!dst || !lens || !digests)) return CW_ERR_ARG;
     if (stride < cw_compress_bound(calg, chunk)) return CW_ERR_ARG;
-    std::lock_guard<std::mutex> lk(ctx->q_mu);
+    std::unique_lock<std::mutex> lk(ctx->q_mu);
     if (!ctx->worker.joinable()) ctx->worker = std::thread(worker_loop, ctx);
     Job j{ctx->next_ticket++, halg, calg, mode, src, chunk, n, digests, dst, stride, lens, cb, user};
     *ticket = j.ticket;
+    ctx->pending[j.ticket] = true;
+    if (batchable(chunk, n)) {
+        lk.unlock();
+        if (batch_submit(ctx, j)) return CW_OK;
+        lk.lock();
+    }
     ctx->queue.push_back(j);
     ctx->q_cv.notify_one();
     return CW_OK;
@@ -671,7 +1010,7 @@ int cw_wait(cw_ctx *ctx, cw_ticket ticket)
     if (!ctx) return CW_ERR_ARG;
     std::unique_lock<std::mutex> lk(ctx->q_mu);
     if (ticket == 0 || ticket >= ctx->next_ticket) return CW_ERR_ARG;
-    ctx->done_cv.wait(lk, [&] { return ctx->done_upto >= ticket; });
+    ctx->done_cv.wait(lk, [&] { return ctx->pending.find(ticket) == ctx->pending.end(); });
     auto it = ctx->finished.find(ticket);
     if (it == ctx->finished.end()) return CW_ERR_ARG;  // already waited for, or its status went to the completion callback
     const int rc = it->second;

@@ -80,6 +80,8 @@ def load_library():
     L.cw_submit.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, sz, sz, vp, vp, sz, vp, vp, vp, C.POINTER(u64)]
     L.cw_wait.argtypes = [vp, u64]
     L.cw_synth_dev.argtypes = [vp, vp, sz, u64, sz, u64, vp]
+    L.cw_batch_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    L.cw_batch_stats.restype = None
     L.cw_launch_count.argtypes = [vp]
     L.cw_launch_count.restype = u64
     L.cw_prof_enable.argtypes = [vp, C.c_int]
@@ -287,6 +289,12 @@ class Engine:
         self._check(self.L.cw_sync(self.h, stream or None))
 
     # ---- introspection ----
+    def batch_stats(self):
+        """(launches made for small host-buffer calls, calls they served)"""
+        b, c = C.c_uint64(0), C.c_uint64(0)
+        self.L.cw_batch_stats(self.h, C.byref(b), C.byref(c))
+        return int(b.value), int(c.value)
+
     def launch_count(self) -> int:
         return int(self.L.cw_launch_count(self.h))
 

@@ -186,6 +186,11 @@ int cw_synth_dev(cw_ctx *ctx, void *d_dst, size_t chunk_bytes, uint64_t first_ch
 /* kernels launched by this context since creation (bench.py's gpu_launches = difference around the
  * timed region) */
 uint64_t cw_launch_count(const cw_ctx *ctx);
+/* small-batch front-end: host-buffer calls (cw_hash_compress, cw_submit) of up to 4 MiB that arrive from several
+ * threads -- the reference's --c-threads workers each hand over one readBlockFactor x 4 KiB work item at a time
+ * (HashAndCompress.cpp:160-183,263-272) -- are gathered into shared batches of one copy in / one launch / one set of
+ * copies out.  batches = launches made for such calls, calls = calls served by them. */
+void cw_batch_stats(const cw_ctx *ctx, uint64_t *batches, uint64_t *calls);
 /* name + duration of the dominant kernel: the library records CUDA events around the kernel launches of
  * the *_dev calls when profiling is on; cw_prof_read returns the accumulated milliseconds and launches */
 int cw_prof_enable(cw_ctx *ctx, int on);

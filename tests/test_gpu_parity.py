@@ -338,6 +338,63 @@ def test_concurrent_callers_threads_and_contexts(eng):
         assert all((blocks[i, : ol[i]] == ob[i, : ol[i]]).all() for i in range(0, n, 7))
 
 
+def test_small_work_items_from_many_threads_share_batches(eng):
+    """the reference's calling pattern (HashAndCompress.cpp:160-183,263-272): 14 worker threads, each handing over one
+    32 KiB work item (8 x 4 KiB) at a time.  Results equal the oracle's; the calls were served by far fewer launches;
+    other kinds of work interleaved from other threads do not mix"""
+    import threading
+    chunk, per, items, T = 4096, 8, 120, 14
+    data = [O.synth(chunk, 1000 * t, per * items) for t in range(T)]
+    out = [None] * T
+    b0, c0 = eng.batch_stats()
+
+    def worker(t):
+        res = []
+        kind = (O.HASH_SKEIN256_128, O.COMP_LZ4, 0) if t % 3 else (O.HASH_SKEIN512, O.COMP_LZF, 0)
+        for i in range(items):
+            d = data[t][i * per * chunk:(i + 1) * per * chunk]
+            res.append(eng.process_block(kind[0], kind[1], d, chunk, kind[2]))
+        out[t] = (kind, res)
+
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(T)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    b1, c1 = eng.batch_stats()
+    assert c1 - c0 == T * items and (b1 - b0) < (c1 - c0)
+    for t in range(T):
+        (halg, calg, _), res = out[t]
+        want_d = O.hash_chunks(halg, data[t], chunk)
+        want_b, want_l = O.compress_chunks(calg, data[t], chunk)
+        for i, (dig, blocks, lens) in enumerate(res):
+            sl = slice(i * per, (i + 1) * per)
+            assert (dig == want_d[sl]).all() and (lens == want_l[sl]).all(), (t, i)
+            for k in range(per):
+                assert (blocks[k, : lens[k]] == want_b[i * per + k, : lens[k]]).all(), (t, i, k)
+
+
+def test_queued_small_jobs_travel_together(eng):
+    """cw_submit: many small jobs queued at once complete (any order), with the oracle's results, in few launches"""
+    chunk, per, jobs = 4096, 8, 300
+    d = O.synth(chunk, 555, per * jobs)
+    stride = cw.compress_bound(O.COMP_LZ4, chunk)
+    dig = np.zeros((jobs * per, 16), np.uint8)
+    blocks = np.zeros((jobs * per, stride), np.uint8)
+    lens = np.zeros(jobs * per, np.uint32)
+    b0, c0 = eng.batch_stats()
+    tickets = []
+    for i in range(jobs):
+        o = i * per
+        tickets.append(eng.submit(O.HASH_SKEIN256_128, O.COMP_LZ4, 0, d[o * chunk:].ctypes.data, chunk, per, dig[o:].ctypes.data,
+                                  blocks[o:].ctypes.data, stride, lens[o:].ctypes.data))
+    for tk in reversed(tickets):
+        eng.wait(tk)
+    b1, c1 = eng.batch_stats()
+    assert c1 - c0 == jobs and (b1 - b0) <= jobs // 4
+    want_b, want_l = O.compress_chunks(O.COMP_LZ4, d, chunk)
+    assert (dig == O.hash_chunks(O.HASH_SKEIN256_128, d, chunk)).all() and (lens == want_l).all()
+    assert all((blocks[i, : lens[i]] == want_b[i, : lens[i]]).all() for i in range(jobs * per))
+
+
 def test_device_pointer_api_and_synth(eng):
     torch = pytest.importorskip("torch")
     chunk, n = 8192, 4096
@@ -651,9 +708,59 @@ def test_host_tool_end_to_end(eng, tmp_path):
     assert lines[16].startswith("Average std dev: ") and abs(float(lines[16].split(": ")[1]) - o_tot) < 1e-3 * o_tot
     run("--gpu-offload", "1", "--c-threads", "5")
     run("--no-pin")  # pageable host buffers, like the reference's malloc'd ones
+    # the reference's own calling pattern: 14 worker threads, one call per work item of 8 blocks
+    r = subprocess.run([exe, "-H", "skein", "-C", "lzf", "-k", str(chunk), "--work-items", "-c", "14", "-r", "8", "--no-pin",
+                        "--dump", str(tmp_path / "wi"), str(f)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert np.fromfile(str(tmp_path / "wi.digests"), np.uint8).tobytes() == want_dig.tobytes()
+    assert open(str(tmp_path / "wi.blocks"), "rb").read() == want_blocks
+    m = re.search(r"(\d+) calls served by (\d+) launches", r.stderr)
+    assert m and int(m.group(1)) >= n // 8 and int(m.group(2)) < int(m.group(1))
+    # the same items, HashOffload style: started asynchronously, many in flight per worker
+    r = subprocess.run([exe, "-H", "skein", "-C", "lzf", "-k", str(chunk), "--work-items", "--gpu-offload", "1", "-c", "14", "-r", "8",
+                        "--no-pin", "--dump", str(tmp_path / "wo"), str(f)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert np.fromfile(str(tmp_path / "wo.digests"), np.uint8).tobytes() == want_dig.tobytes()
+    assert open(str(tmp_path / "wo.blocks"), "rb").read() == want_blocks
     torch = pytest.importorskip("torch")
     if torch.cuda.device_count() >= 2:
         run("--devices", "2")
+
+
+def test_host_tool_prints_the_reference_tools_log_lines(eng, tmp_path):
+    """--experiment / --hash-perf: the per-block lines of the reference's `experiment` and hashing_perf tools
+    (experiment.cpp:114,122,253,260; hash.cpp:18-23,38-43), read the way its notebooks read them
+    (notebooks/compression-comparison.ipynb cell 1, hash-perf.ipynb cells 3-4)"""
+    import os
+    import subprocess
+    pd = pytest.importorskip("pandas")
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "compute_war_b200", "hashandcompress")
+    if not os.path.exists(exe):
+        pytest.skip("host tool not built")
+    chunk, n = 4096, 500
+    d = O.synth(chunk, 4242, n)
+    f = tmp_path / "blocks.bin"
+    f.write_bytes(d.tobytes() + b"partial block")
+    r = subprocess.run([exe, "--experiment", "-C", "both", str(f)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    log = tmp_path / "exp.out"
+    log.write_text(r.stdout)
+    df = pd.read_csv(str(log), sep="|", header=None)
+    df.columns = ["alg", "comp_size", "compress_us", "decompress_us", "file", "block"]
+    assert len(df) == 2 * n and list(df.alg[:2]) == ["lzf", "lz4"] and int(df.block.min()) == 1 and int(df.block.max()) == n
+    for name, alg in (("lz4", O.COMP_LZ4), ("lzf", O.COMP_LZF)):
+        sub = df[df.alg == name].sort_values("block")
+        assert (sub.comp_size.to_numpy() == O.compress_chunks(alg, d, chunk)[1]).all()  # lzf: 0 where it did not fit, as the reference prints
+        assert (sub.compress_us > 0).all() and (sub.decompress_us > 0).all() and (sub.file == str(f)).all()
+    r = subprocess.run([exe, "--hash-perf", str(f)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    log = tmp_path / "hash_perf_sb.1"
+    log.write_text(r.stdout)
+    sb = pd.read_csv(str(log), sep="|", header=None).drop(4, axis=1)
+    sb.columns = "FilePath|BlockIndex|Algo|TimeElapsedUS".split("|")
+    assert len(sb) == 2 * n and list(sb.BlockIndex) == list(range(2 * n))
+    g = sb.groupby("Algo").TimeElapsedUS.mean()
+    assert g["Skein256"] > 0 and g["Sha256"] > 0 and set(sb.Algo) == {"Skein256", "Sha256"}
 
 
 def test_decompress_rejects_malformed_blocks(eng):

@@ -201,7 +201,7 @@ static cudaError_t launch_one(const CwDeviceInfo &dev, int max_dyn_smem, const C
     const int hw = fused_hash_warps(cw_c_fast(CALG));
     if (cw_c_fast(CALG)) {
         // teams of nteam warps, one slot per team; the kernel's `emitters` argument carries the team size
-        int nteam = cw_lz4f_team_size();
+        int nteam = cw_lz4f_team_size(chunk);
         const uint32_t fslot = cw_slot_bytes<CALG>(chunk, (uint32_t)nteam);
         int teams = max_dyn_smem / (int)fslot;
         if (teams < 1) return cudaErrorInvalidValue;

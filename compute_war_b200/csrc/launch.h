@@ -23,7 +23,7 @@ void cw_make_skein_iv_bits(CwSkeinIV *iv, unsigned state_bits, unsigned hash_bit
 cudaError_t cw_launch_lz4(const CwDeviceInfo &dev, bool fast, const uint8_t *d_src, uint32_t chunk, uint64_t n, uint8_t *d_dst,
                           uint64_t stride, uint32_t *d_lens, unsigned long long *work, cudaStream_t st);
 cudaError_t cw_lz4_configure(const CwDeviceInfo &dev);
-int cw_lz4f_team_size();  // warps per chunk in fast mode (CW_LZ4F_TEAM, default 2)
+int cw_lz4f_team_size(uint32_t chunk);  // warps per chunk in fast mode (CW_LZ4F_TEAM; default 2, 4 for chunks read in place)
 
 // synth.cu
 cudaError_t cw_launch_synth(uint8_t *d_dst, uint32_t chunk, uint64_t first_chunk, uint64_t n, uint64_t seed,

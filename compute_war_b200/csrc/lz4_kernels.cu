@@ -75,16 +75,18 @@ __global__ void __launch_bounds__(CW_LZ4F_MAX_WARPS * 32, 1)
                                                 n_chunks, work, dst, stride, lens);
 }
 
-int cw_lz4f_team_size()
+// warps per chunk: 2 while shared memory holds 13+ chunks per SM (26 warps issue 75 % of the slots); chunks that are read
+// in place (> 16 KiB) leave room for only 6 tables, so 4 warps share each of them (profiles/r02_lz4_fast_teams.txt)
+int cw_lz4f_team_size(uint32_t chunk)
 {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("CW_LZ4F_TEAM");  // tuning knob for the profiling scripts
-        v = e ? atoi(e) : CW_LZ4F_TEAM_DEFAULT;
-        if (v < 1) v = 1;
-        if (v > 4) v = 4;
+        v = e ? atoi(e) : 0;
+        if (v > CW_LZ4F_MAX_TEAM) v = CW_LZ4F_MAX_TEAM;
     }
-    return v;
+    if (v > 0) return v;
+    return chunk > CW_LZ4_DIRECT_ABOVE ? 4 : CW_LZ4F_TEAM_DEFAULT;
 }
 
 static int g_lz4_max_smem = 0, g_lz4f_max_smem = 0;
@@ -119,7 +121,7 @@ cudaError_t cw_launch_lz4(const CwDeviceInfo &dev, bool fast, const uint8_t *d_s
     if (fast) {
         // 12 / 13 / 14 table bits by chunk size (lz4_fast.cuh); teams of warps, no emitters
         const int hl = cw_lz4f_hashlog(chunk);
-        int nteam = cw_lz4f_team_size();
+        int nteam = cw_lz4f_team_size(chunk);
         const uint32_t fslot = cw_lz4f_slot_bytes(chunk, hl, direct, (uint32_t)nteam);
         int teams = g_lz4f_max_smem / (int)fslot;
         if (teams < 1) return cudaErrorInvalidValue;

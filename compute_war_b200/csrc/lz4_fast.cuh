@@ -49,7 +49,9 @@
 #pragma once
 #include "lz4_warp.cuh"
 
-#define CW_LZ4F_SW 4  // windows per group
+#ifndef CW_LZ4F_SW
+#define CW_LZ4F_SW 4  // windows per group (the output does not depend on it)
+#endif
 #ifndef CW_LZ4F_DOUBLINGS
 #define CW_LZ4F_DOUBLINGS 2  // rounds of pointer doubling before the walk: chains of 4 choices per step of the walk
 #endif

@@ -58,7 +58,9 @@ __global__ void __launch_bounds__((CW_LZ4_MAX_PARSERS + CW_LZ4_MAX_EMITTERS) * 3
 
 // fast mode (lz4_fast.cuh): teams of `nteam` warps, one chunk per team at a time; every team stages, parses and emits
 // on its own.  As many teams as slots fit into the SM's shared memory (and hardware barriers: 15).
+#ifndef CW_LZ4F_MAX_WARPS
 #define CW_LZ4F_MAX_WARPS 26  // 832 threads: ptxas may use 78 registers
+#endif
 #define CW_LZ4F_MAX_TEAMS 15
 #ifndef CW_LZ4F_TEAM_DEFAULT
 #define CW_LZ4F_TEAM_DEFAULT 2

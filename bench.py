@@ -294,22 +294,29 @@ def run_configs(eng, cw, O, torch, np, dev, stream, peaks, int_peak, steps: int)
         else:
             ok = O.verify_roundtrip(calg, samp, chunk, blk_h, lens_h) == 0
             how = "first chunks decode back (restated decoder)"
+            if calg == cw.COMP_LZF:  # length 0 = kept raw (lzf.h:59-64): the decoders take such a chunk from its block
+                blk_h = blk_h.copy()
+                for i in np.nonzero(lens_h == 0)[0]:
+                    blk_h[i, :chunk] = samp[i * chunk: (i + 1) * chunk]
             if O.have_ref_cli():
                 back = O.ref_decompress_chunks(calg, chunk, blk_h, lens_h)
                 ok = ok and len(back) == len(samp) and bool((back == samp).all())
                 how = "first chunks restored by the reference's own decompressor (ref_cli)"
-            if calg == cw.COMP_LZ4:
-                fb, fl = O.lz4_fast_chunks(samp, chunk)
-                ok = ok and bool((lens_h == fl).all() and all((blk_h[i, : fl[i]] == fb[i, : fl[i]]).all() for i in range(k)))
-                how += " and byte-identical to the restated fast parse"
+            fb, fl = O.lz4_fast_chunks(samp, chunk) if calg == cw.COMP_LZ4 else O.lzf_fast_chunks(samp, chunk)
+            ok = ok and bool((lens_h == fl).all() and all((blk_h[i, : fl[i]] == fb[i, : fl[i]]).all() for i in range(k)))
+            how += " and byte-identical to the restated fast parse"
         if halg is not None:
             ok = ok and bool((dig.view(n, D)[:k].cpu().numpy() == O.hash_chunks(halg, samp, chunk)).all())
         # all blocks of the set decode back on the device
         back = torch.empty(n * chunk, dtype=torch.uint8, device=dev)
         bl = torch.empty(n, dtype=torch.int32, device=dev)
+        if calg == cw.COMP_LZF:  # chunks that did not shrink (length 0) are kept raw: put them where the decoder looks
+            raw = (lens == 0).nonzero().flatten()
+            if raw.numel():
+                blocks.view(n, stride)[raw, :chunk] = src.view(n, chunk)[raw]
         eng.decompress_dev(calg, blocks.data_ptr(), stride, lens.data_ptr(), chunk, n, back.data_ptr(), bl.data_ptr(), stream)
         torch.cuda.synchronize()
-        rt = bool((bl == chunk).all().item()) and bool(torch.equal(back, src)) if calg == cw.COMP_LZ4 else None
+        rt = bool((bl == chunk).all().item()) and bool(torch.equal(back, src))
         lh = lens.cpu().numpy().astype(np.int64)
         ratio = float(np.where(lh == 0, chunk, lh).sum()) / (n * chunk)
         ref_ratio_sample = float(np.where(ol == 0, chunk, ol.astype(np.int64)).sum()) / (k * chunk)
@@ -353,7 +360,7 @@ def run_configs(eng, cw, O, torch, np, dev, stream, peaks, int_peak, steps: int)
     # configs[3]: fused hc_sklz4 / hc_sklzf / hc_shlz4 at 8 KiB, real corpus tiled and the synthetic mix
     d, reps, per = corpus(("canterbury", "canterbury-large"), 8192, GiB // 4)
     syn8 = O.synth(8192, 0, 32768)
-    for halg, calg, modes in ((cw.HASH_SKEIN512, cw.COMP_LZ4, (0, 1)), (cw.HASH_SKEIN512, cw.COMP_LZF, (0,)),
+    for halg, calg, modes in ((cw.HASH_SKEIN512, cw.COMP_LZ4, (0, 1)), (cw.HASH_SKEIN512, cw.COMP_LZF, (0, 1)),
                               (cw.HASH_SHA256, cw.COMP_LZ4, (0, 1))):
         tag = "hc_" + {"skein512": "sk", "sha256": "sh"}[HN[halg]] + CN[calg]
         for mode in modes:

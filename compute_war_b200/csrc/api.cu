@@ -244,8 +244,10 @@ int do_compress_dev(cw_ctx *ctx, cw_comp_alg alg, cw_mode mode, const void *d_sr
         const WorkSlot w = next_work(ctx);
         CW_CUDA(ctx, cudaMemsetAsync(w.p, 0, sizeof *w.p, st));
         ProfScope ps(ctx, st);
-        CW_CUDA(ctx, cw_launch_lzf(ctx->dev, (const uint8_t *)d_src, (uint32_t)chunk, n, (uint8_t *)d_dst, stride, d_lens,
-                                   w.p, st));
+        if (mode == CW_MODE_FAST)
+            CW_CUDA(ctx, cw_launch_lzf_fast(ctx->dev, (const uint8_t *)d_src, (uint32_t)chunk, n, (uint8_t *)d_dst, stride, d_lens, w.p, st));
+        else
+            CW_CUDA(ctx, cw_launch_lzf(ctx->dev, (const uint8_t *)d_src, (uint32_t)chunk, n, (uint8_t *)d_dst, stride, d_lens, w.p, st));
         work_done(ctx, w, st);
         ctx->launches++;
         return CW_OK;

@@ -112,8 +112,21 @@ __device__ __forceinline__ void cw_lz4_emitter_role(unsigned e, unsigned emitter
 // slot of a team: [chunk | pad | table | CwLz4fTeam | nteam x CwLz4fScratch] (DIRECT: no chunk, it is read where it lies).
 __host__ __device__ constexpr uint32_t cw_lz4f_slot_bytes(uint32_t chunk, int hashlog, bool direct, uint32_t nteam)
 {
-    return (direct ? 0u : cw_lz4_chunk_pad(chunk)) + (2u << hashlog) + (uint32_t)sizeof(CwLz4fTeam) +
-           nteam * (uint32_t)sizeof(CwLz4fScratch);
+    return ((direct ? 0u : cw_lz4_chunk_pad(chunk)) + (2u << hashlog) + (uint32_t)sizeof(CwLz4fTeam) +
+            nteam * (uint32_t)sizeof(CwLz4fScratch) + 15u) & ~15u;  // slots stay 16-byte aligned for the bulk copy
+}
+// Which team a compress warp belongs to when `warps` warps share `teams` slots: the first warps % teams teams get one
+// warp more than the others (13 slots of 8 KiB chunks and 32 warps: six teams of 3, seven of 2), so that the register
+// file, not the number of slots, decides how many warps an SM runs.
+struct CwLz4fPlace {
+    unsigned team, rank, nteam;
+};
+__host__ __device__ __forceinline__ CwLz4fPlace cw_lz4f_place(unsigned warp, unsigned teams, unsigned warps)
+{
+    const unsigned base = warps / teams, extra = warps - base * teams, cut = extra * (base + 1u);
+    if (warp < cut) return {warp / (base + 1u), warp % (base + 1u), base + 1u};
+    const unsigned w = warp - cut;
+    return {extra + w / base, w % base, base};
 }
 // barrier of the warps of one team (hardware barrier `id`, 1..15); a team of one warp needs none
 __device__ __forceinline__ void cw_lz4f_team_sync(unsigned id, unsigned nteam)
@@ -122,7 +135,8 @@ __device__ __forceinline__ void cw_lz4f_team_sync(unsigned id, unsigned nteam)
     else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nteam * 32u) : "memory");
 }
 // rank: this warp's index inside its team; bar_id: the team's hardware barrier; bar: the team's mbarrier
-template <int HASHLOG, bool ALIGNED, bool DIRECT>
+// CODEC: CW_F_LZ4 / CW_F_LZF (an LZF block may take chunk - 1 bytes, like the reference's lzf_compress(s, l, d, l - 1) call)
+template <int HASHLOG, bool ALIGNED, bool DIRECT, int CODEC = CW_F_LZ4>
 __device__ __forceinline__ void cw_lz4f_team_role(uint8_t *s, uint64_t *bar, unsigned rank, unsigned nteam, unsigned bar_id,
                                                   const uint8_t *__restrict__ src, uint32_t chunk, uint64_t n_chunks,
                                                   unsigned long long *work, uint8_t *__restrict__ dst, uint64_t stride,
@@ -175,7 +189,8 @@ __device__ __forceinline__ void cw_lz4f_team_role(uint8_t *s, uint64_t *bar, uns
             }
         }
         const uint32_t len =
-            cw_lz4f_team_chunk<HASHLOG, DIRECT>(DIRECT ? src + g * chunk : s, chunk, table, team, scr, dst + g * stride, rank, nteam, seen);
+            cw_lz4f_team_chunk<CODEC, HASHLOG, DIRECT>(DIRECT ? src + g * chunk : s, chunk, table, team, scr, dst + g * stride, rank, nteam,
+                                                       seen, CODEC == CW_F_LZF ? chunk - 1u : 0xffffffffu);
         if (len != CW_LZ4_NONE && lane == 0) lens[g] = len;
         cw_lz4f_team_sync(bar_id, nteam);  // every warp is done with the slot before it is refilled
     }

@@ -12,18 +12,21 @@
 // host-only build of the per-chunk algorithms (tests/simt/): scalar code compiles as is, warp code runs on
 // the fibre-based warp emulator
 #define CW_DEV static inline
+#define CW_DEV_NI static
 #define CW_HOSTDEV static inline
 #if defined(CW_EMULATE)
 #include "warp_emu.h"  // provides cw_lane(), cw_ballot(), cw_shfl(), cw_match_any(), cw_syncwarp(), ...
 #endif
 #else
 #define CW_DEV __device__ __forceinline__
+#define CW_DEV_NI __device__
 #define CW_HOSTDEV __host__ __device__ __forceinline__
 #define CW_FULL 0xffffffffu
 CW_DEV unsigned cw_lane() { return threadIdx.x & 31u; }
 CW_DEV unsigned cw_ballot(bool p) { return __ballot_sync(CW_FULL, p); }
 CW_DEV uint32_t cw_shfl(uint32_t v, unsigned src) { return __shfl_sync(CW_FULL, v, src); }
 CW_DEV unsigned cw_match_any(uint32_t v) { return __match_any_sync(CW_FULL, v); }
+CW_DEV uint32_t cw_reduce_or(uint32_t v) { return __reduce_or_sync(CW_FULL, v); }  // REDUX.OR
 CW_DEV void cw_syncwarp() { __syncwarp(); }
 CW_DEV int cw_ffs(uint32_t v) { return __ffs(v); }       // 1-based, 0 if none
 CW_DEV int cw_clz(uint32_t v) { return __clz(v); }

@@ -33,8 +33,10 @@
 #define CW_FUSED_MAX_COMP_WARPS 14
 #define CW_FUSED_MAX_THREADS ((CW_FUSED_HASH_WARPS_MAX + CW_FUSED_MAX_COMP_WARPS + 3) * 32)  // + emitters
 // fast mode: teams of warps per chunk (lz4_fast.cuh), no emitters: 26 compress warps + 2 hash warps = 896 threads, which
-// leaves ptxas 72 registers -- the hash role then runs without the next-block prefetch of skein.cuh (16 registers)
-#define CW_FUSED_FAST_COMP_WARPS 26
+// leaves ptxas 72 registers -- the hash role then runs the single-call-site Skein loop without the next-block prefetch
+#ifndef CW_FUSED_FAST_COMP_WARPS
+#define CW_FUSED_FAST_COMP_WARPS 26  // 30 (1024 threads, 64 registers) measured 10 % slower at 8 KiB: the hash rounds want the registers
+#endif
 #define CW_FUSED_FAST_THREADS ((CW_FUSED_HASH_WARPS_MAX + CW_FUSED_FAST_COMP_WARPS) * 32)
 
 // measured on the synthetic mix (profiles/r01_tune_emitters_hashwarps.txt): the 9-parser compat kernel is best
@@ -53,12 +55,17 @@ static int fused_hash_warps(bool fast)
 // compressor variants of the fused kernel: LZ4 compat (the reference's parse, 13-bit table, chunk staged) / LZF /
 // LZ4 fast (window-parallel parse of lz4_fast.cuh) with a 12-bit and a 13-bit table / the two LZ4 modes for chunks
 // > 16 KiB, which are read where they lie (DIRECT; fast mode then uses a 14-bit table)
-enum { CW_C_LZ4 = 0, CW_C_LZF = 1, CW_C_LZ4_FAST = 2, CW_C_LZ4_FAST13 = 3, CW_C_LZ4_DIRECT = 4, CW_C_LZ4_FAST_DIRECT = 5 };
-__host__ __device__ constexpr bool cw_c_direct(int c) { return c == CW_C_LZ4_DIRECT || c == CW_C_LZ4_FAST_DIRECT; }
-__host__ __device__ constexpr bool cw_c_fast(int c) { return c == CW_C_LZ4_FAST || c == CW_C_LZ4_FAST13 || c == CW_C_LZ4_FAST_DIRECT; }
+// ... and the LZF flavour of the fast parse with 13 / 14 table bits, staged or read in place
+enum {
+    CW_C_LZ4 = 0, CW_C_LZF = 1, CW_C_LZ4_FAST = 2, CW_C_LZ4_FAST13 = 3, CW_C_LZ4_DIRECT = 4, CW_C_LZ4_FAST_DIRECT = 5,
+    CW_C_LZF_FAST13 = 6, CW_C_LZF_FAST14 = 7, CW_C_LZF_FAST_DIRECT = 8
+};
+__host__ __device__ constexpr bool cw_c_direct(int c) { return c == CW_C_LZ4_DIRECT || c == CW_C_LZ4_FAST_DIRECT || c == CW_C_LZF_FAST_DIRECT; }
+__host__ __device__ constexpr bool cw_c_fast(int c) { return c == CW_C_LZ4_FAST || c == CW_C_LZ4_FAST13 || c == CW_C_LZ4_FAST_DIRECT || c >= CW_C_LZF_FAST13; }
+__host__ __device__ constexpr int cw_c_codec(int c) { return c >= CW_C_LZF_FAST13 ? CW_F_LZF : CW_F_LZ4; }
 __host__ __device__ constexpr int cw_c_hashlog(int c)
 {
-    return c == CW_C_LZ4_FAST ? 12 : c == CW_C_LZ4_FAST_DIRECT ? 14 : 13;
+    return c == CW_C_LZ4_FAST ? 12 : (c == CW_C_LZ4_FAST_DIRECT || c == CW_C_LZF_FAST14 || c == CW_C_LZF_FAST_DIRECT) ? 14 : 13;
 }
 
 #define CW_FUSED_EMITTERS_DEFAULT 3  // emitter warps per CTA
@@ -118,13 +125,13 @@ __global__ void __launch_bounds__(cw_c_fast(CALG) ? CW_FUSED_FAST_THREADS : CW_F
     __shared__ uint64_t bars[32];
     const unsigned warp = roles.logical[threadIdx.x >> 5], lane = threadIdx.x & 31u;
     if constexpr (cw_c_fast(CALG)) {
-        // fast mode: `emitters` carries the team size; a team of warps stages, parses and emits a chunk on its own
+        // fast mode: `emitters` carries the number of teams; a team of warps stages, parses and emits a chunk on its own
         // (lz4_fast.cuh), no queues, no emitter warps
         if (warp < parsers) {
-            const unsigned nteam = emitters, t = warp / nteam;
-            cw_lz4f_team_role<cw_c_hashlog(CALG), ALIGNED, cw_c_direct(CALG)>(smem + (size_t)t * slot_bytes, &bars[t], warp - t * nteam,
-                                                                              nteam, 1u + t, src, chunk, n_chunks, &work[0], dst,
-                                                                              stride, lens);
+            const CwLz4fPlace pl = cw_lz4f_place(warp, emitters, parsers);
+            cw_lz4f_team_role<cw_c_hashlog(CALG), ALIGNED, cw_c_direct(CALG), cw_c_codec(CALG)>(
+                smem + (size_t)pl.team * slot_bytes, &bars[pl.team], pl.rank, pl.nteam, 1u + pl.team, src, chunk, n_chunks, &work[0], dst,
+                stride, lens);
             if (!CW_FUSED_TAIL_HELP) return;
         }
     } else {
@@ -172,7 +179,7 @@ __global__ void __launch_bounds__(cw_c_fast(CALG) ? CW_FUSED_FAST_THREADS : CW_F
         }
         __syncwarp();
         const unsigned long long idx = first + lane;
-        if (idx < n_chunks) cw_hash_one<HALG, ALIGNED, ALIGNED, !cw_c_fast(CALG)>(iv, src + idx * chunk, chunk, digests + idx * D);
+        if (idx < n_chunks) cw_hash_one<HALG, ALIGNED, ALIGNED, !cw_c_fast(CALG), cw_c_fast(CALG)>(iv, src + idx * chunk, chunk, digests + idx * D);
     }
 }
 
@@ -200,18 +207,20 @@ static cudaError_t launch_one(const CwDeviceInfo &dev, int max_dyn_smem, const C
     auto kern = cw_fused_kernel<HALG, CALG, ALIGNED>;
     const int hw = fused_hash_warps(cw_c_fast(CALG));
     if (cw_c_fast(CALG)) {
-        // teams of nteam warps, one slot per team; the kernel's `emitters` argument carries the team size
-        int nteam = cw_lz4f_team_size(chunk);
-        const uint32_t fslot = cw_slot_bytes<CALG>(chunk, (uint32_t)nteam);
-        int teams = max_dyn_smem / (int)fslot;
-        if (teams < 1) return cudaErrorInvalidValue;
-        if (nteam > 1 && teams > 15) teams = 15;  // one hardware barrier per team
-        if (teams * nteam > CW_FUSED_FAST_COMP_WARPS) teams = CW_FUSED_FAST_COMP_WARPS / nteam;
+        // one slot per team; the kernel's `emitters` argument carries the number of teams (cw_lz4f_place spreads the warps)
+        int teams = 0, warps = 0;
+        uint32_t fslot = cw_slot_bytes<CALG>(chunk, CW_LZ4F_MAX_TEAM);
+        for (int it = 0; it < 2; it++) {
+            const int slots = max_dyn_smem / (int)fslot;
+            if (slots < 1) return cudaErrorInvalidValue;
+            cw_lz4f_shape(slots, CW_FUSED_FAST_COMP_WARPS, &teams, &warps);
+            fslot = cw_slot_bytes<CALG>(chunk, (uint32_t)((warps + teams - 1) / teams));
+        }
         uint64_t fctas = (n + (uint64_t)teams - 1) / (uint64_t)teams;
         if (fctas > (uint64_t)dev.sm_count) fctas = (uint64_t)dev.sm_count;
-        kern<<<(unsigned)fctas, (teams * nteam + hw) * 32, (size_t)teams * fslot, st>>>(
-            iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, fslot, (uint32_t)(teams * nteam), (uint32_t)nteam,
-            make_role_map(teams * nteam, 0, hw, nullptr, nullptr));
+        kern<<<(unsigned)fctas, (warps + hw) * 32, (size_t)teams * fslot, st>>>(
+            iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, fslot, (uint32_t)warps, (uint32_t)teams,
+            make_role_map(warps, 0, hw, nullptr, nullptr));
         return cudaGetLastError();
     }
     const uint32_t per = cw_slot_bytes<CALG>(chunk);  // slot + queue
@@ -252,7 +261,7 @@ cudaError_t cw_fused_configure(const CwDeviceInfo &dev)
     if (e == cudaSuccess) e = configure_one<H, C, true>(m);
 #define CW_CFG_H(H)                                                                                                    \
     CW_CFG(H, CW_C_LZ4) CW_CFG(H, CW_C_LZF) CW_CFG(H, CW_C_LZ4_FAST) CW_CFG(H, CW_C_LZ4_FAST13) CW_CFG_D(H, CW_C_LZ4_DIRECT) \
-        CW_CFG_D(H, CW_C_LZ4_FAST_DIRECT)
+        CW_CFG_D(H, CW_C_LZ4_FAST_DIRECT) CW_CFG(H, CW_C_LZF_FAST13) CW_CFG(H, CW_C_LZF_FAST14) CW_CFG_D(H, CW_C_LZF_FAST_DIRECT)
     CW_CFG_H(CW_K_SKEIN512)
     CW_CFG_H(CW_K_SKEIN256_128)
     CW_CFG_H(CW_K_SHA256)
@@ -277,6 +286,9 @@ static cudaError_t launch_h(int calg, bool aligned, const CwDeviceInfo &dev, con
     case CW_C_LZF: CW_BOTH(CW_C_LZF);
     case CW_C_LZ4_DIRECT: return launch_one<HALG, CW_C_LZ4_DIRECT, true>(CW_ARGS);
     case CW_C_LZ4_FAST_DIRECT: return launch_one<HALG, CW_C_LZ4_FAST_DIRECT, true>(CW_ARGS);
+    case CW_C_LZF_FAST13: CW_BOTH(CW_C_LZF_FAST13);
+    case CW_C_LZF_FAST14: CW_BOTH(CW_C_LZF_FAST14);
+    case CW_C_LZF_FAST_DIRECT: return launch_one<HALG, CW_C_LZF_FAST_DIRECT, true>(CW_ARGS);
     }
 #undef CW_BOTH
 #undef CW_ARGS
@@ -300,8 +312,19 @@ cudaError_t cw_launch_fused(const CwDeviceInfo &dev, int halg, int calg, bool fa
             if (e != cudaSuccess) return e;
             return cw_launch_hash(halg, iv, d_src, chunk, n, d_digests, st);
         }
-    } else if (calg == CW_C_LZ4 && fast)  // fast mode of LZF is the compat kernel
+    } else if (calg == CW_C_LZ4 && fast)
         calg = cw_lz4f_hashlog(chunk) == 12 ? CW_C_LZ4_FAST : CW_C_LZ4_FAST13;
+    else if (calg == CW_C_LZF && fast) {
+        if (chunk > 16384u) {
+            if (aligned) calg = CW_C_LZF_FAST_DIRECT;
+            else {
+                cudaError_t e = cw_launch_lzf_fast(dev, d_src, chunk, n, d_dst, stride, d_lens, &work[0], st);
+                if (e != cudaSuccess) return e;
+                return cw_launch_hash(halg, iv, d_src, chunk, n, d_digests, st);
+            }
+        } else
+            calg = cw_lzff_hashlog(chunk) == 13 ? CW_C_LZF_FAST13 : CW_C_LZF_FAST14;
+    }
     switch (halg) {
     case CW_K_SKEIN512: return launch_h<CW_K_SKEIN512>(calg, aligned, dev, iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, st);
     case CW_K_SKEIN256_128: return launch_h<CW_K_SKEIN256_128>(calg, aligned, dev, iv, d_src, chunk, n, d_digests, d_dst, stride, d_lens, work, st);

@@ -28,13 +28,15 @@ enum { CW_K_SKEIN512 = 0, CW_K_SKEIN256_128 = 1, CW_K_SHA256 = 2, CW_K_SKEIN256_
 
 // digest of chunk `p` (len bytes) written to `out` (D bytes); OUT_ALIGNED: out is 16-byte aligned
 // PREFETCH: Skein loads the next block before it processes the current one (16 more registers)
-template <int ALG, bool ALIGNED, bool OUT_ALIGNED, bool PREFETCH = CW_SKEIN_PREFETCH>
+// COMPACT: one call site of the Skein block function (skein.cuh; no prefetch) -- the fused kernels, for their code size
+template <int ALG, bool ALIGNED, bool OUT_ALIGNED, bool PREFETCH = CW_SKEIN_PREFETCH, bool COMPACT = false>
 __device__ __forceinline__ void cw_hash_one(const CwSkeinIV &iv, const uint8_t *__restrict__ p, uint32_t len,
                                             uint8_t *__restrict__ out)
 {
     if constexpr (ALG == CW_K_SKEIN512) {
         uint64_t X[8];
-        cw_skein_chunk<8, 64, ALIGNED, CW_SKEIN_UNROLL72, PREFETCH>(iv.iv512, p, len, X);
+        if constexpr (COMPACT) cw_skein_chunk_compact<8, ALIGNED, CW_SKEIN_UNROLL72>(iv.iv512, p, len, X);
+        else cw_skein_chunk<8, 64, ALIGNED, CW_SKEIN_UNROLL72, PREFETCH>(iv.iv512, p, len, X);
         if (OUT_ALIGNED) {
             uint4 *o = reinterpret_cast<uint4 *>(out);
 #pragma unroll
@@ -47,7 +49,8 @@ __device__ __forceinline__ void cw_hash_one(const CwSkeinIV &iv, const uint8_t *
         }
     } else if constexpr (ALG == CW_K_SKEIN256_128) {
         uint64_t X[4];
-        cw_skein_chunk<4, 16, ALIGNED, true, PREFETCH>(iv.iv256, p, len, X);
+        if constexpr (COMPACT) cw_skein_chunk_compact<4, ALIGNED, true>(iv.iv256, p, len, X);
+        else cw_skein_chunk<4, 16, ALIGNED, true, PREFETCH>(iv.iv256, p, len, X);
         if (OUT_ALIGNED) {
             *reinterpret_cast<uint4 *>(out) =
                 make_uint4((uint32_t)X[0], (uint32_t)(X[0] >> 32), (uint32_t)X[1], (uint32_t)(X[1] >> 32));

@@ -23,7 +23,8 @@ void cw_make_skein_iv_bits(CwSkeinIV *iv, unsigned state_bits, unsigned hash_bit
 cudaError_t cw_launch_lz4(const CwDeviceInfo &dev, bool fast, const uint8_t *d_src, uint32_t chunk, uint64_t n, uint8_t *d_dst,
                           uint64_t stride, uint32_t *d_lens, unsigned long long *work, cudaStream_t st);
 cudaError_t cw_lz4_configure(const CwDeviceInfo &dev);
-int cw_lz4f_team_size(uint32_t chunk);  // warps per chunk in fast mode (CW_LZ4F_TEAM; default 2, 4 for chunks read in place)
+// fast mode: teams (<= slots) and compress warps (<= max_warps) of one CTA (CW_LZ4F_TEAM forces a team size)
+void cw_lz4f_shape(int slots, int max_warps, int *teams, int *warps);
 
 // synth.cu
 cudaError_t cw_launch_synth(uint8_t *d_dst, uint32_t chunk, uint64_t first_chunk, uint64_t n, uint64_t seed,
@@ -33,6 +34,9 @@ cudaError_t cw_launch_synth(uint8_t *d_dst, uint32_t chunk, uint64_t first_chunk
 cudaError_t cw_launch_lzf(const CwDeviceInfo &dev, const uint8_t *d_src, uint32_t chunk, uint64_t n, uint8_t *d_dst,
                           uint64_t stride, uint32_t *d_lens, unsigned long long *work, cudaStream_t st);
 cudaError_t cw_lzf_configure(const CwDeviceInfo &dev);
+// lz4_kernels.cu: LZF fast mode runs the team kernel of lz4_fast.cuh
+cudaError_t cw_launch_lzf_fast(const CwDeviceInfo &dev, const uint8_t *d_src, uint32_t chunk, uint64_t n, uint8_t *d_dst,
+                               uint64_t stride, uint32_t *d_lens, unsigned long long *work, cudaStream_t st);
 
 // fused_kernels.cu -- ProcessBlock: digest + compressed block of every chunk in one pass
 // work: two device u64 counters zeroed by the caller

@@ -22,24 +22,29 @@
 // What the warp does NOT do is measure every verified position's match: neighbouring positions of one match have
 // neighbouring candidates, so the masks
 //     OK   (position verified),  SAME (position x and x + 1 verified with candidates c and c + 1)
-// and a per-lane count CNT (how many of the bytes x + 4 .. x + 7 equal c + 4 .. c + 7) already hold the exact end of
+// and a per-position count CNT (how many of the bytes x + 4 .. x + 7 equal c + 4 .. c + 7) already hold the exact end of
 // almost every match: it is the first position r at or after the start whose SAME bit is clear, plus 4 + CNT[r].
-// Only when CNT[r] is 4 (the bytes go on although the neighbour chose another candidate), and for matches that
-// outgrow a window, does the warp extend the match itself (32 bytes, then 128 per step).
+// Every position works out, from those masks alone, where its own match ends (E) and which verified position the greedy
+// parse would choose after it (N), and leaves both in a 16-bit entry of a per-warp table in shared memory.  The greedy
+// walk over a group is then ONE shared-memory load per chosen match.  Only when CNT[r] is 4 (the bytes go on although
+// the neighbour chose another candidate: an "open" match), when a chain of neighbours is longer than 32 positions, or
+// when no verified position lies within 32 positions of a match end does the walk leave that fast path: the warp
+// extends the match itself (32 bytes, then 128 per step) and looks the next position up in the OK masks.
 //
-// Emission happens in the same warp as the parse, once per group: the chosen matches are compacted into one lane each (backward
+// Emission happens in the same warp as the parse, once per group: the chosen matches are handed to one lane each (backward
 // extension, sizes, prefix sum, token / lengths / offset), and the literal bytes are then written position-wise --
 // a lane looks up the sequence its position belongs to and stores its own byte -- so a group costs the same number
 // of instructions whether it holds two sequences or twenty.  Literals that precede the group (a sequence is only
 // written once its match is known) are copied by the whole warp.
 //
-// A chunk is a dependent chain of ~10^5 instructions, a warp issues one of them every 6-7 cycles, and shared memory
-// holds only 13 chunks of 8 KiB per SM, so one warp per chunk leaves most issue slots idle.  A team of NW warps
+// A chunk is a dependent chain of several 10^4 instructions, a warp issues one of them every 6-7 cycles, and shared
+// memory holds only 13 chunks of 8 KiB per SM, so one warp per chunk leaves most issue slots idle.  A team of NW warps
 // therefore shares a chunk: warp r takes groups r, r + NW, ... and only three short sections of a group are ordered
 // by tokens in shared memory (CwLz4fTeam): the table look-ups / inserts (group g needs the inserts of g - 1), the
 // greedy walk (needs the position the walk of g - 1 ended at) and the output offset (one addition).  Everything
-// else of group g + 1 -- fetch, hash, verification, masks, sizes, stores -- overlaps with group g in the other warp.
-// Nothing is copied between the warps: a group's values stay in the registers of the warp that owns it.
+// else of group g + 1 -- fetch, hash, verification, masks, E / N entries, sizes, stores -- overlaps with group g in the
+// other warp.  Nothing is copied between the warps: a group's values stay in the registers and the scratch of the warp
+// that owns it.
 //
 // End rules of the block format: a match starts at or before n - 12 and ends at or before
 // n - 5; chunks shorter than 13 bytes are one literal run.
@@ -49,23 +54,32 @@
 #pragma once
 #include "lz4_warp.cuh"
 
-#ifndef CW_LZ4F_SW
-#define CW_LZ4F_SW 4  // windows per group (the output does not depend on it)
-#endif
-#ifndef CW_LZ4F_DOUBLINGS
-#define CW_LZ4F_DOUBLINGS 2  // rounds of pointer doubling before the walk: chains of 4 choices per step of the walk
-#endif
+#define CW_LZ4F_SW 4  // windows per group: 128 positions, which is what the 8-bit fields of the E / N entries hold
 
 // hash table size for a chunk size: chosen on the reference's corpora with tools/lz4_fast_model.c so that the worst
 // file stays below 1.01 x the reference's size (4 KiB 1.006, 8 KiB 1.002 with 12 bits; 16 KiB 0.998 with 13;
 // 64 KiB 0.990 with 14 -- 13 bits would give 1.012 on world192.txt)
 CW_HOSTDEV int cw_lz4f_hashlog(uint32_t chunk) { return chunk <= 8192u ? 12 : chunk <= 16384u ? 13 : 14; }
+// LZF flavour (3-byte keys collide more): 4 KiB 1.003 / worst file 1.007 with 13 bits; 8 KiB 1.002 / 1.006, 16 KiB 0.999 / 1.007,
+// 64 KiB 0.996 / 1.008 with 14 (tools/lzf_fast_model.c against lzf_compress)
+CW_HOSTDEV int cw_lzff_hashlog(uint32_t chunk) { return chunk <= 4096u ? 13 : 14; }
 
-// per-warp scratch in shared memory: the chosen matches of a group, then the literal map of its sequences
-union CwLz4fScratch {
-    uint32_t rec[32][2];  // {start | end << 16, candidate}
-    uint32_t map[32][2];  // {output offset of literal x, minus x; first literal | end of literals << 16}
+// per-warp scratch in shared memory (312 bytes)
+struct CwLz4fScratch {
+    union {
+        uint16_t pos[128];    // per position of the group.  First the continuation count CNT; then N | E << 8: the verified
+                              // position the parse chooses after this one's match and the end of that match, both relative to
+                              // the group (N: CW_LZ4F_* codes below).  An open match leaves its extended end (absolute) in the
+                              // entry of the neighbour x ^ 1 (minus 1), which lies inside the match and is never looked at
+        uint32_t map[32][2];  // afterwards: {output offset of literal x, minus x; first literal | end of literals << 16}
+    };
+    uint32_t okw[6];  // OK masks of the four windows, two zero words behind them
+    uint8_t rec[32];  // the chosen matches of the group (their positions), in order
 };
+static_assert(sizeof(CwLz4fScratch) % 8 == 0, "the literal map is read with 64-bit loads");
+#define CW_LZ4F_LEAVE 128u  // N >= 128: nothing more to choose in this group
+#define CW_LZ4F_OPEN 254u   // N: the match goes on beyond E, the warp extends it
+#define CW_LZ4F_FAR 255u    // N: no verified position within 32 positions of E, the walk looks it up in the OK masks
 
 // aligned 32-bit word i of the chunk (DIRECT: words at or beyond nw read as 0)
 template <bool DIRECT>
@@ -108,7 +122,7 @@ CW_DEV uint32_t cw_lz4f_extend(const uint8_t *s, uint32_t e, uint32_t d, uint32_
 // suspended by the hardware instead of polling shared memory -- a polling team mate takes the issue slots the working
 // warp needs) and a plain counter on the warp emulator.  The kernels initialise them once; every warp keeps the number
 // of arrivals it has consumed (`seen`, the same for its three tokens).
-#define CW_LZ4F_MAX_TEAM 4
+#define CW_LZ4F_MAX_TEAM 6
 struct CwLz4fTeam {
     uint64_t tok_table[CW_LZ4F_MAX_TEAM];  // the table inserts of the group before are done
     uint64_t tok_walk[CW_LZ4F_MAX_TEAM];   // its greedy walk is done; ip = where the parse stands
@@ -165,6 +179,59 @@ CW_DEV void cw_lz4f_tok_post(uint64_t *tok, unsigned lane)
 }
 #endif
 
+// whole-warp copy of len literal bytes s[src..] -> out[dst..] (long runs: literals in front of a group, the end of the chunk).
+// Same stores as cw_lz4_copy_warp, kept as ONE out-of-line loop nest: the inlined, unrolled copies were a quarter of the
+// kernel's code, and the fused kernel's instruction cache also has to hold the hash rounds.
+#if defined(__CUDACC__)
+#define CW_NOINLINE __noinline__
+#else
+#define CW_NOINLINE
+#endif
+template <bool DIRECT>
+CW_NOINLINE CW_DEV_NI void cw_lz4f_copy(uint8_t *out, uint32_t dst, const uint8_t *s, uint32_t src, uint32_t len, uint32_t nw)
+{
+    const unsigned lane = cw_lane();
+    uint32_t head = (4u - (uint32_t)(reinterpret_cast<uintptr_t>(out + dst) & 3u)) & 3u;
+    if (len < 64u) head = len;  // short runs: bytes only
+    const uint32_t words = (len - head) >> 2;
+    if (lane < head || len < 64u) {
+#pragma unroll 1
+        for (uint32_t x = lane; x < head; x += 32u) out[dst + x] = cw_lz4_src8<DIRECT>(s, src + x);
+    }
+    uint32_t *o32 = reinterpret_cast<uint32_t *>(out + dst + head);
+#pragma unroll 1
+    for (uint32_t w = lane; w < words; w += 32u) o32[w] = cw_lz4_src32<DIRECT>(s, src + head + 4u * w, nw);
+    const uint32_t done = head + 4u * words;
+    if (lane < len - done) out[dst + done + lane] = cw_lz4_src8<DIRECT>(s, src + done + lane);
+}
+
+#define CW_F_LZ4 0
+#define CW_F_LZF 1
+// LZF literal runs: the first `cnt` literals of a run of `run` bytes s[src..] whose area (a header byte in front of every
+// 32 literals, lzf.h) starts at out[w].  Whole warp, out of line like cw_lz4f_copy.
+template <bool DIRECT>
+CW_NOINLINE CW_DEV_NI void cw_lzff_put_literals(uint8_t *out, uint32_t w, const uint8_t *s, uint32_t src, uint32_t run, uint32_t cnt)
+{
+#pragma unroll 1
+    for (uint32_t k = cw_lane(); k < cnt; k += 32u) {
+        const uint32_t o = w + k + (k >> 5);
+        out[o + 1u] = cw_lz4_src8<DIRECT>(s, src + k);
+        if ((k & 31u) == 0u) out[o] = (uint8_t)(cw_umin(32u, run - k) - 1u);
+    }
+}
+
+// first verified position of the group at or after rel (< 128), from the OK masks in shared memory; 128: none
+CW_DEV uint32_t cw_lz4f_scan(const uint32_t *okw, uint32_t rel)
+{
+    uint32_t j = rel >> 5;
+    uint32_t m = okw[j] & (0xffffffffu << (rel & 31u));
+    while (!m) {
+        if (++j >= (uint32_t)CW_LZ4F_SW) return 128u;
+        m = okw[j];
+    }
+    return 32u * j + cw_lz4f_ctz(m);
+}
+
 // Compress chunk s[0..n) (n <= 65536) into out, as warp `rank` of a team of `nteam` warps that all call this function
 // with the same arguments.  s: 4-byte aligned; not DIRECT: CW_LZ4_PAD readable bytes behind the chunk.  table: zeroed
 // u16[1 << HASHLOG]; team: tokens initialised, ip = 1, op = 0, visible to every warp of the team before the first one
@@ -172,55 +239,65 @@ CW_DEV void cw_lz4f_tok_post(uint64_t *tok, unsigned lane)
 // warp's own scratch.  Returns the block length in the warp that finishes the chunk (same value in every lane) and CW_LZ4_NONE in
 // the others.
 CW_HOSTDEV uint32_t cw_lz4f_groups(uint32_t n) { return n >= 13u ? (n - 12u) / (32u * CW_LZ4F_SW) + 1u : 0u; }
-template <int HASHLOG, bool DIRECT>
+CW_HOSTDEV uint32_t cw_lzff_groups(uint32_t n) { return n >= 8u ? (n - 7u) / 96u + 1u : 0u; }
+// CODEC: CW_F_LZ4 or CW_F_LZF (the LZF flavour of the same parse: 3-byte keys, lzf.h block format, see the end of this file).
+// LZF: `cap` = the most the block may take (the reference's call passes chunk - 1); 0 is returned when it does not fit.
+template <int CODEC, int HASHLOG, bool DIRECT>
 CW_DEV uint32_t cw_lz4f_team_chunk(const uint8_t *s, uint32_t n, uint16_t *table, CwLz4fTeam *team, CwLz4fScratch *scr,
-                                   uint8_t *out, uint32_t rank, uint32_t nteam, uint32_t &seen)
+                                   uint8_t *out, uint32_t rank, uint32_t nteam, uint32_t &seen, uint32_t cap = 0xffffffffu)
 {
+    constexpr bool LZF = CODEC == CW_F_LZF;
+    constexpr uint32_t KB = LZF ? 3u : 4u;  // bytes of a key = the shortest match
+    // windows per group: a group hands every chosen match to a lane of its own, and 32 matches of KB bytes fill 4 (3) windows.
+    // (Positions and codes in the E / N entries stay as for 128 positions; an LZF group simply has no fourth window.)
+    constexpr int SWN = LZF ? 3 : CW_LZ4F_SW;
+    constexpr uint32_t G = 32u * SWN;
     const uint32_t next = rank + 1u == nteam ? 0u : rank + 1u;  // owner of the group after mine
     const uint32_t nw = n >> 2;
     const unsigned lane = cw_lane();
     const uint32_t lt = (1u << lane) - 1u;  // window positions below mine
     const uint32_t *sw = reinterpret_cast<const uint32_t *>(s);
-    const unsigned sh = (lane & 3u) * 8u;  // my position's byte offset inside its aligned word, in bits
-    const uint32_t NONE = 0xfff00000u;     // "no verified candidate": never one below a real candidate
+    const unsigned sh = (lane & 3u) * 8u;           // my position's byte offset inside its aligned word, in bits
+    const unsigned sh2 = ((lane + 2u) & 3u) * 8u;   // the same for the position two bytes back
+    const bool hi2 = (lane & 3u) >= 2u;             // ... which starts in the same aligned word as mine
+    const uint32_t NONE = 0xfff00000u;              // "no verified candidate": never one below a real candidate
     uint32_t anchor = 0, op = 0;
 
-    if (n >= 13u) {
-        const uint32_t last = n - 12u;       // last position a match may start at
-        const uint32_t matchlimit = n - 5u;  // matches never cover the last 5 bytes
-        const uint32_t groups = cw_lz4f_groups(n);
+    if (n >= (LZF ? 8u : 13u)) {
+        // LZ4: a match starts at or before n - 12 and never covers the last 5 bytes.  LZF has no such rules; a match may
+        // start where the 7 bytes the parse looks at (key + continuation count) lie inside the chunk, and run to its end
+        const uint32_t last = LZF ? n - 7u : n - 12u;
+        const uint32_t matchlimit = LZF ? n : n - 5u;
+        const uint32_t groups = LZF ? cw_lzff_groups(n) : cw_lz4f_groups(n);
         uint32_t ip = 1u;  // next position the greedy parse looks at (position 0 has no source)
         for (uint32_t g = rank; g < groups; g += nteam) {
-            const uint32_t sbase = g * (32u * CW_LZ4F_SW);  // first position of the group
-            uint32_t v[CW_LZ4F_SW], c[CW_LZ4F_SW], h[CW_LZ4F_SW], own4[CW_LZ4F_SW], cnt[CW_LZ4F_SW], myend[CW_LZ4F_SW];
-            uint32_t okm[CW_LZ4F_SW + 1], psm[CW_LZ4F_SW + 1], same[CW_LZ4F_SW + 1], sel[CW_LZ4F_SW];
-            bool live[CW_LZ4F_SW], valid[CW_LZ4F_SW], per2[CW_LZ4F_SW];
-            // ---- phase 1: my own bytes in every window of the group (independent loads) ----
+            const uint32_t sbase = g * G;  // first position of the group
+            uint32_t v[CW_LZ4F_SW], c[CW_LZ4F_SW], h[CW_LZ4F_SW], own4[CW_LZ4F_SW];
+            uint32_t okm[CW_LZ4F_SW], nsame[CW_LZ4F_SW + 1];
+            bool valid[CW_LZ4F_SW], per2[CW_LZ4F_SW];
+            // ---- phase 1: my own bytes in every window of the group (independent loads).  Positions beyond the last
+            //      match start are fetched like the others (the chunk is padded / words beyond it read as 0) and are
+            //      simply never valid ----
+            const uint32_t wi0 = (sbase >> 2) + (lane >> 2);
 #pragma unroll
-            for (int j = 0; j < CW_LZ4F_SW; j++) {
-                const uint32_t wbase = sbase + 32u * j, p = wbase + lane;
-                live[j] = wbase <= last;  // windows beyond the last match start hold literals only
-                valid[j] = live[j] && p <= last && p != 0u;
-                v[j] = h[j] = own4[j] = c[j] = cnt[j] = 0u;
-                per2[j] = false;
-                myend[j] = 0u;
-                sel[j] = 0u;
-                if (live[j]) {
-                    const uint32_t wi = (wbase >> 2) + (lane >> 2);
-                    const uint32_t w0 = cw_lz4f_word<DIRECT>(sw, wi, nw), w1 = cw_lz4f_word<DIRECT>(sw, wi + 1u, nw);
-                    v[j] = cw_funnel_r(w0, w1, sh);
-                    own4[j] = cw_funnel_r(w1, cw_lz4f_word<DIRECT>(sw, wi + 2u, nw), sh);  // bytes p + 4 .. p + 7
-                    // the 4 bytes two positions back (run / period-2 candidate)
-                    per2[j] = p >= 2u && cw_lz4_src32<DIRECT>(s, p >= 2u ? p - 2u : 0u, nw) == v[j];
-                    h[j] = cw_lz4_hash<HASHLOG>(v[j]);
-                }
+            for (int j = 0; j < SWN; j++) {
+                const uint32_t p = sbase + 32u * j + lane, wi = wi0 + 8u * j;
+                const uint32_t wm = cw_lz4f_word<DIRECT>(sw, (j == 0 && wi == 0u) ? 0u : wi - 1u, nw);
+                const uint32_t w0 = cw_lz4f_word<DIRECT>(sw, wi, nw), w1 = cw_lz4f_word<DIRECT>(sw, wi + 1u, nw);
+                const uint32_t w2 = cw_lz4f_word<DIRECT>(sw, wi + 2u, nw);
+                v[j] = cw_funnel_r(w0, w1, sh);
+                own4[j] = cw_funnel_r(w1, w2, sh);  // bytes p + 4 .. p + 7
+                valid[j] = p - 1u < last;           // 1 <= p <= last
+                // the 4 bytes two positions back (run / period-2 candidate)
+                const uint32_t d2 = cw_funnel_r(hi2 ? w0 : wm, hi2 ? w1 : w0, sh2) ^ v[j];
+                per2[j] = (LZF ? (d2 & 0xffffffu) == 0u : d2 == 0u) && (j != 0 || p >= 2u);
+                h[j] = cw_lz4_hash<HASHLOG>(LZF ? v[j] & 0xffffffu : v[j]);
             }
             // ---- phase 2a (ordered: after the inserts of group g - 1): look-up and insert, window by window (a window
             //      sees the inserts of the windows before it) ----
             if (g) cw_lz4f_tok_wait(&team->tok_table[rank], seen + 1u, lane);
 #pragma unroll
-            for (int j = 0; j < CW_LZ4F_SW; j++) {
-                if (!live[j]) continue;
+            for (int j = 0; j < SWN; j++) {
                 const uint32_t p = sbase + 32u * j + lane;
                 uint32_t cj = table[h[j]];
                 cw_syncwarp();  // every lane has read the old entry before any lane stores
@@ -235,103 +312,106 @@ CW_DEV uint32_t cw_lz4f_team_chunk(const uint8_t *s, uint32_t n, uint16_t *table
                     w = table[h[j]];
                 }
                 if (valid[j] && w < p) cj = w;  // an earlier position of this window: more recent than the old entry
+                if (per2[j]) cj = p - 2u;
                 c[j] = cj;
             }
             if (g + 1u < groups) cw_lz4f_tok_post(&team->tok_table[next], lane);
-            // ---- phase 2b: candidate verification and the OK / CONT / chain masks ----
-            uint32_t c_last = NONE;  // lane 31's verified candidate in the window before
-            okm[CW_LZ4F_SW] = psm[CW_LZ4F_SW] = 0u;
+            // ---- phase 2b: candidate verification, continuation counts and the OK / SAME masks ----
+            uint32_t rotprev = NONE;  // lane 0: lane 31's verified candidate in the window before
+            uint32_t psm[CW_LZ4F_SW + 1];
 #pragma unroll
-            for (int j = 0; j < CW_LZ4F_SW; j++) {
-                okm[j] = psm[j] = 0u;
-                if (!live[j]) {
-                    c_last = NONE;
-                    continue;
-                }
-                const uint32_t p = sbase + 32u * j + lane;
-                uint32_t cj = c[j];
-                if (per2[j]) cj = p - 2u;
-                const bool ok = valid[j] && cw_lz4_src32<DIRECT>(s, valid[j] ? cj : 0u, nw) == v[j];
-                if (ok) {  // how many of the next 4 bytes go on matching (4: at least that many)
-                    const uint32_t x = cw_lz4_src32<DIRECT>(s, cj + 4u, nw) ^ own4[j];
-                    cnt[j] = x ? cw_lz4f_ctz(x) >> 3 : 4u;
-                }
-                c[j] = cj;
+            for (int j = 0; j < SWN; j++) {
+                const uint32_t cj = c[j], a = cj >> 2;
+                const unsigned shc = (cj & 3u) * 8u;
+                const uint32_t a0 = cw_lz4f_word<DIRECT>(sw, a, nw), a1 = cw_lz4f_word<DIRECT>(sw, a + 1u, nw);
+                const uint32_t a2 = cw_lz4f_word<DIRECT>(sw, a + 2u, nw);
+                // the 8 bytes at the candidate against my 8: the key decides, the rest is the continuation count
+                // (how many of the bytes behind the key go on matching; 4: at least that many)
+                const uint32_t x0 = cw_funnel_r(a0, a1, shc) ^ v[j], x = cw_funnel_r(a1, a2, shc) ^ own4[j];
+                bool ok;
+                uint32_t cntv = x ? cw_lz4f_ctz(x) >> 3 : 4u;
+                if (LZF) {
+                    const uint32_t m0 = x0 ? cw_lz4f_ctz(x0) >> 3 : 4u;
+                    ok = valid[j] && m0 >= 3u;
+                    if (n > 8192u) ok = ok && sbase + 32u * j + lane - cj <= 8192u;  // lzf.h: offsets end at 8192
+                    cntv = m0 == 4u ? cw_umin(1u + cntv, 4u) : 0u;
+                } else
+                    ok = valid[j] && x0 == 0u;
+                scr->pos[32 * j + lane] = (uint16_t)cntv;
                 const uint32_t cc = ok ? cj : NONE;
-                uint32_t prevc = cw_shfl(cc, (lane + 31u) & 31u);
-                if (lane == 0u) prevc = c_last;
-                c_last = cw_shfl(cc, 31u);
+                const uint32_t rot = cw_shfl(cc, (lane + 31u) & 31u);
+                const uint32_t prevc = lane == 0u ? rotprev : rot;
+                rotprev = rot;
                 okm[j] = cw_ballot(ok);
                 psm[j] = cw_ballot(ok && prevc + 1u == cj);  // my match continues the one of the position before me
             }
-            // SAME[j] bit x: positions x and x + 1 of window j belong to one match
+            psm[SWN] = 0u;
+            // nsame[j] bit x: positions x and x + 1 of window j do NOT belong to one match
 #pragma unroll
-            for (int j = 0; j < CW_LZ4F_SW; j++) same[j] = (psm[j] >> 1) | ((psm[j + 1] & 1u) << 31);
-            same[CW_LZ4F_SW] = 0u;
-            // ---- phase 3 (ordered: after the walk of group g - 1): greedy walk over the group ----
-            // Every verified lane knows from the masks where its own match ends (exactly, unless it is "open") and which
-            // lane the greedy parse would choose after it; rounds of pointer doubling give every lane the chain of the next
-            // 2^rounds choices that starts at it (a window holds at most 8 matches).  A step of the walk itself is then one
-            // pair of shuffles, plus one whole-warp extension if the chain stops at an open match.
-            uint32_t pk[CW_LZ4F_SW], R[CW_LZ4F_SW];
+            for (int j = 0; j < SWN; j++) nsame[j] = ~((psm[j] >> 1) | ((psm[j + 1] & 1u) << 31));
+            nsame[SWN] = 0xffffffffu;
+            const uint32_t okany = okm[0] | okm[1] | okm[2] | (SWN == 4 ? okm[3] : 0u);
+            if (lane < 6u) scr->okw[lane] = lane == 0u ? okm[0] : lane == 1u ? okm[1] : lane == 2u ? okm[2] : (SWN == 4 && lane == 3u) ? okm[3] : 0u;
+            cw_syncwarp();  // counts and masks are in the scratch
+            // ---- phase 3a: every position's entry: E = where its match ends, N = what the parse chooses after it ----
+            if (okany) {
+                uint32_t ent[CW_LZ4F_SW];
 #pragma unroll
-            for (int j = 0; j < CW_LZ4F_SW; j++) {
-                pk[j] = R[j] = 0u;
-                if (!okm[j]) continue;
-                const uint32_t ns = cw_funnel_r(~same[j], ~same[j + 1], lane);  // bit k: the chain breaks after lane + k
-                const uint32_t dr = ns ? cw_lz4f_ctz(ns) : 32u;
-                // the bytes behind the last position of my chain: 0-3 more of them match, or the match is "open"
-                const uint32_t r = lane + dr;
-                const uint32_t ca = cw_shfl(cnt[j], r & 31u), cb = cw_shfl(j + 1 < CW_LZ4F_SW ? cnt[j + 1] : 0u, r & 31u);
-                const uint32_t cr = r < 32u ? ca : cb;
-                const bool opn = !ns || cr == 4u;
-                const uint32_t endr = r + 4u + (opn ? 0u : cr);  // end of my match, relative to the window (a lower bound if open)
-                myend[j] = sbase + 32u * j + endr;
-                uint32_t J = 32u;  // next chosen lane after my match; 32: the chain leaves the window or stops at an open match
-                if (!opn && endr < 32u) {
-                    const uint32_t m = okm[j] & (0xffffffffu << endr);
-                    if (m) J = cw_lz4f_ctz(m);
+                for (int j = 0; j < SWN; j++) {
+                    const uint32_t ns = cw_funnel_r(nsame[j], nsame[j + 1], lane);  // bit k: the chain breaks after lane + k
+                    const uint32_t dr = ns ? cw_lz4f_ctz(ns) : 32u;
+                    const uint32_t r = 32u * j + lane + dr;  // last position of my chain (dr = 32: it goes on)
+                    const uint32_t cr = scr->pos[r];
+                    const bool opn = dr == 32u || cr == 4u;
+                    const uint32_t E = r + KB + (cr & 3u);  // end of my match (a lower bound if open)
+                    const uint32_t lo = scr->okw[E >> 5], hi = scr->okw[(E >> 5) + 1u];
+                    const uint32_t t = cw_funnel_r(lo, hi, E & 31u);  // verified positions from E on
+                    uint32_t N = t ? E + cw_lz4f_ctz(t) : CW_LZ4F_FAR;
+                    if (E >= G) N = CW_LZ4F_LEAVE;
+                    if (opn) N = CW_LZ4F_OPEN;
+                    ent[j] = N | (E << 8);  // N <= 255: E <= 135, and a verified position lies at most 31 behind it
                 }
-                uint32_t Rj = 1u << lane;                                // lanes chosen on the chain that starts at me
-                uint32_t pkj = J | (endr << 8) | (opn ? 1u << 16 : 0u);  // chain: next lane | end | ends in an open match
+                cw_syncwarp();  // every lane has read the counts
 #pragma unroll
-                for (int k = 0; k < CW_LZ4F_DOUBLINGS; k++) {
-                    const uint32_t nx = pkj & 0xffu;
-                    const uint32_t pk2 = cw_shfl(pkj, nx & 31u), R2 = cw_shfl(Rj, nx & 31u);
-                    if (nx < 32u) {
-                        Rj |= R2;
-                        pkj = pk2;
-                    }
-                }
-                pk[j] = pkj;
-                R[j] = Rj;
+                for (int j = 0; j < SWN; j++) scr->pos[32 * j + lane] = (uint16_t)ent[j];
             }
+            // ---- phase 3b (ordered: after the walk of group g - 1): greedy walk over the group ----
             if (g) cw_lz4f_tok_wait(&team->tok_walk[rank], seen + 1u, lane);
             ip = cw_ld_vol(&team->ip);
-            cw_syncwarp();  // every lane has read it before lane 0 writes the new value
+            cw_syncwarp();  // every lane has read it before lane 0 writes the new value (and the entries are in place)
             anchor = ip == 1u ? 0u : ip;  // the parse stands at the end of the last match (nothing chosen yet: 1 / 0)
-            uint32_t tot = 0;
+            uint32_t tot = 0, x = 128u;
+            if (okany) {
+                const uint32_t rel = ip > sbase ? ip - sbase : 0u;
+                if (rel < 128u) x = cw_lz4f_scan(scr->okw, rel);
+            }
+            if (x < 128u) {
+                // the fast path is the inner loop: one load per chosen match (every lane reads the same entry and stores the
+                // same record byte, so nothing in it is predicated on the lane)
+                for (;;) {
+                    uint32_t t;
+                    do {
+                        t = scr->pos[x];
+                        scr->rec[tot++] = (uint8_t)x;
+                        x = t & 255u;
+                    } while (x < 128u);
+                    ip = sbase + (t >> 8);
+                    if (x < 254u) break;  // nothing more to choose in this group
+                    if (x == CW_LZ4F_OPEN) {  // the warp extends the match
+                        const uint32_t xs = scr->rec[tot - 1u];
+                        uint32_t cnd = 0;
 #pragma unroll
-            for (int j = 0; j < CW_LZ4F_SW; j++) {
-                const uint32_t base = sbase + 32u * j;
-                if (!okm[j] || ip >= base + 32u) continue;
-                uint32_t rel = ip > base ? ip - base : 0u;
-                while (rel < 32u) {
-                    const uint32_t m = okm[j] & (0xffffffffu << rel);
-                    if (!m) break;
-                    const unsigned f = cw_lz4f_ctz(m);
-                    const uint32_t pkf = cw_shfl(pk[j], f), Rf = cw_shfl(R[j], f);
-                    sel[j] |= Rf;
-                    tot += (uint32_t)cw_popc(Rf);
-                    uint32_t e = base + ((pkf >> 8) & 0xffu);
-                    if ((pkf >> 16) & 1u) {  // the chain stopped at an open match (its highest lane): the warp extends it
-                        const unsigned fo = 31u - (unsigned)cw_clz(Rf);
-                        const uint32_t cnd = cw_shfl(c[j], fo);
-                        e = cw_lz4f_extend<DIRECT>(s, e, base + fo - cnd, matchlimit, nw, lane);
-                        if (lane == fo) myend[j] = e;
+                        for (int j = 0; j < SWN; j++) {
+                            const uint32_t q = cw_shfl(c[j], xs & 31u);
+                            if ((xs >> 5) == (uint32_t)j) cnd = q;
+                        }
+                        ip = cw_lz4f_extend<DIRECT>(s, ip, sbase + xs - cnd, matchlimit, nw, lane);
+                        if (lane == 0u) scr->pos[xs ^ 1u] = (uint16_t)(ip - 1u);  // (an LZF match may end at 65536)
                     }
-                    ip = e;
-                    rel = e - base;
+                    const uint32_t r2 = ip - sbase;
+                    if (r2 >= 128u) break;
+                    x = cw_lz4f_scan(scr->okw, r2);
+                    if (x >= 128u) break;
                 }
             }
             if (lane == 0u) cw_st_vol(&team->ip, ip);
@@ -344,28 +424,26 @@ CW_DEV uint32_t cw_lz4f_team_chunk(const uint8_t *s, uint32_t n, uint16_t *table
                 }
                 op = cw_ld_vol(&team->op);
                 if (g + 1u < groups) cw_lz4f_tok_post(&team->tok_emit[next], lane);
+                cw_syncwarp();  // the scratch is read before the next group's counts overwrite it
                 continue;
             }
+            cw_syncwarp();  // the walk's records are in the scratch
             // one lane per chosen match, in position order
-            uint32_t cum = 0;
-#pragma unroll
-            for (int j = 0; j < CW_LZ4F_SW; j++) {
-                if (!sel[j]) continue;
-                if ((sel[j] >> lane) & 1u) {
-                    const uint32_t k = cum + (uint32_t)cw_popc(sel[j] & lt);
-                    scr->rec[k][0] = (sbase + 32u * j + lane) | (myend[j] << 16);
-                    scr->rec[k][1] = c[j];
-                }
-                cum += (uint32_t)cw_popc(sel[j]);
-            }
-            cw_syncwarp();
             const bool mine = lane < tot;
-            uint32_t P = 0, E = 0, C = 0;
+            uint32_t P = 0, E = 0, C = 0, xr = 0;
             if (mine) {
-                const uint32_t r0 = scr->rec[lane][0];
-                C = scr->rec[lane][1];
-                P = r0 & 0xffffu;
-                E = r0 >> 16;
+                xr = scr->rec[lane];
+                const uint32_t t = scr->pos[xr];
+                P = sbase + xr;
+                E = (t & 255u) == CW_LZ4F_OPEN ? (uint32_t)scr->pos[xr ^ 1u] + 1u : sbase + (t >> 8);
+            }
+            uint32_t sel[CW_LZ4F_SW];  // the chosen positions of every window
+#pragma unroll
+            for (int j = 0; j < SWN; j++) {
+                const uint32_t q = cw_shfl(c[j], xr & 31u);  // my match's candidate sits in the lane that owns the position
+                const bool here = mine && (xr >> 5) == (uint32_t)j;
+                if (here) C = q;
+                sel[j] = cw_reduce_or(here ? 1u << (xr & 31u) : 0u);
             }
             const uint32_t prevE = cw_shfl(E, (lane + 31u) & 31u);
             const uint32_t A = lane == 0u ? anchor : prevE;  // first literal of my sequence
@@ -375,61 +453,159 @@ CW_DEV uint32_t cw_lz4f_team_chunk(const uint8_t *s, uint32_t n, uint16_t *table
                 const uint32_t maxb = cw_umin(P - A, C);
                 while (back < maxb && cw_lz4_src8<DIRECT>(s, P - 1u - back) == cw_lz4_src8<DIRECT>(s, C - 1u - back)) back++;
             }
-            const uint32_t lit = P - back - A, mcode = E - P - 4u + back;
-            const uint32_t le = cw_lz4_ext_bytes(lit);
-            const uint32_t sz = mine ? 3u + le + lit + cw_lz4_ext_bytes(mcode) : 0u;
-            uint32_t inc = sz;  // inclusive prefix sum over the lanes
-#pragma unroll
-            for (uint32_t d = 1; d < 32u; d <<= 1) {
-                const uint32_t t = cw_shfl(inc, lane >= d ? lane - d : lane);
-                if (lane >= d) inc += t;
-            }
-            const uint32_t total = cw_shfl(inc, 31u);
-            // (ordered: after the allotment of group g - 1) this group's place in the block
-            if (g) {
-                cw_lz4f_tok_wait(&team->tok_emit[rank], seen + 1u, lane);
-                seen++;
-            }
-            op = cw_ld_vol(&team->op);
-            cw_syncwarp();  // every lane has read it before lane 0 writes the new value
-            if (lane == 0u) cw_st_vol(&team->op, op + total);
-            if (g + 1u < groups) cw_lz4f_tok_post(&team->tok_emit[next], lane);
-            const uint32_t start = op + inc - sz;
-            cw_syncwarp();  // the records are read: the scratch now takes the literal map
-            if (mine) {
-                uint32_t w = start;
-                out[w++] = (uint8_t)((cw_umin(lit, 15u) << 4) | cw_umin(mcode, 15u));
-                if (lit >= 15u) w = cw_lz4_put_ext1(out, w, lit - 15u);
-                scr->map[lane][0] = w - A;  // literal x of my sequence goes to out[w - A + x]
-                scr->map[lane][1] = A | ((P - back) << 16);
-                w += lit;
-                const uint32_t off = P - C;
-                out[w] = (uint8_t)off;
-                out[w + 1u] = (uint8_t)(off >> 8);
-                if (mcode >= 15u) cw_lz4_put_ext1(out, w + 2u, mcode - 15u);
-            }
-            op += total;
-            cw_syncwarp();
-            // literals in front of the group (they belong to its first sequence): copied by the whole warp
-            if (anchor < sbase) {
-                const uint32_t m0 = scr->map[0][0], fend = scr->map[0][1] >> 16;
-                const uint32_t stop = cw_umin(sbase, fend);
-                if (stop > anchor) cw_lz4_copy_warp<DIRECT>(out, m0 + anchor, s, anchor, stop - anchor, nw, lane);
-            }
-            // literals inside the group: every position looks up its sequence and stores its own byte
-            cum = 0;
-#pragma unroll
-            for (int j = 0; j < CW_LZ4F_SW; j++) {
-                if (!live[j]) continue;
-                const uint32_t x = sbase + 32u * j + lane;
-                const uint32_t idx = cum + (uint32_t)cw_popc(sel[j] & lt);
-                if (idx < tot) {
-                    const uint32_t m0 = scr->map[idx][0], m1 = scr->map[idx][1];
-                    if (x >= (m1 & 0xffffu) && x < (m1 >> 16)) out[m0 + x] = (uint8_t)v[j];
+            if constexpr (LZF) {
+                // ---- lzf.h block format: literal runs of at most 32 bytes behind a header byte (length - 1); a match is
+                //      (length - 2) << 5 | offset >> 8, [length - 9], offset & 255 with offset = distance - 1, at most 264
+                //      bytes long: longer matches are written as several tokens of the same distance ----
+                const uint32_t Pb = P - back, lit = Pb - A, mlen = E - Pb;
+                const uint32_t lsz = lit + ((lit + 31u) >> 5);
+                uint32_t msz = 0;
+                if (mine) {
+                    uint32_t l = mlen;
+#pragma unroll 1
+                    while (l > 264u) {
+                        l -= l - 264u < 3u ? 262u : 264u;  // never leave a rest shorter than a match
+                        msz += 3u;
+                    }
+                    msz += l - 2u < 7u ? 2u : 3u;
                 }
-                cum += (uint32_t)cw_popc(sel[j]);
+                const uint32_t sz = mine ? lsz + msz : 0u;
+                uint32_t inc = sz;  // inclusive prefix sum over the lanes
+#pragma unroll
+                for (uint32_t d = 1; d < 32u; d <<= 1) {
+                    const uint32_t t = cw_shfl(inc, lane >= d ? lane - d : lane);
+                    if (lane >= d) inc += t;
+                }
+                const uint32_t total = cw_shfl(inc, 31u);
+                // (ordered: after the allotment of group g - 1) this group's place in the block
+                if (g) {
+                    cw_lz4f_tok_wait(&team->tok_emit[rank], seen + 1u, lane);
+                    seen++;
+                }
+                op = cw_ld_vol(&team->op);
+                cw_syncwarp();  // every lane has read it before lane 0 writes the new value
+                if (lane == 0u) cw_st_vol(&team->op, op + total);
+                if (g + 1u < groups) cw_lz4f_tok_post(&team->tok_emit[next], lane);
+                // a block that outgrows `cap` is dropped (the caller stores the chunk raw): from the first group that does
+                // not fit nothing is written any more -- the offsets only grow -- and the chunk's length comes out as 0
+                const bool fits = op + total <= cap;
+                const uint32_t start = op + inc - sz;
+                cw_syncwarp();  // the entries are read: the scratch now takes the literal map
+                if (mine) {
+                    scr->map[lane][0] = start;  // literal k of my run goes to out[start + 1 + k + k / 32]
+                    scr->map[lane][1] = A | (Pb << 16);
+                    if (fits) {
+                        uint32_t w = start + lsz, l = mlen;
+                        const uint32_t off = P - C - 1u;
+#pragma unroll 1
+                        while (l > 264u) {
+                            const uint32_t take = l - 264u < 3u ? 262u : 264u;
+                            out[w] = (uint8_t)((7u << 5) | (off >> 8));
+                            out[w + 1u] = (uint8_t)(take - 9u);
+                            out[w + 2u] = (uint8_t)off;
+                            w += 3u;
+                            l -= take;
+                        }
+                        if (l - 2u < 7u) {
+                            out[w] = (uint8_t)(((l - 2u) << 5) | (off >> 8));
+                            out[w + 1u] = (uint8_t)off;
+                        } else {
+                            out[w] = (uint8_t)((7u << 5) | (off >> 8));
+                            out[w + 1u] = (uint8_t)(l - 9u);
+                            out[w + 2u] = (uint8_t)off;
+                        }
+                    }
+                }
+                op += total;
+                cw_syncwarp();
+                if (fits) {
+                    // literals in front of the group (they belong to its first sequence): copied by the whole warp
+                    if (anchor < sbase) {
+                        const uint32_t m0 = scr->map[0][0], fend = scr->map[0][1] >> 16;
+                        const uint32_t stop = cw_umin(sbase, fend);
+                        if (stop > anchor) cw_lzff_put_literals<DIRECT>(out, m0, s, anchor, fend - anchor, stop - anchor);
+                    }
+                    // literals inside the group: every position looks up its run and stores its own byte (and the run header
+                    // in front of every 32nd)
+                    uint32_t cum = 0;
+#pragma unroll
+                    for (int j = 0; j < SWN; j++) {
+                        const uint32_t x = sbase + 32u * j + lane;
+                        const uint32_t idx = cum + (uint32_t)cw_popc(sel[j] & lt);
+                        if (idx < tot) {
+                            const uint32_t m0 = scr->map[idx][0], m1 = scr->map[idx][1];
+                            const uint32_t k = x - (m1 & 0xffffu), run = (m1 >> 16) - (m1 & 0xffffu);
+                            if (k < run) {  // (k wraps for positions below the run)
+                                const uint32_t w = m0 + k + (k >> 5);
+                                out[w + 1u] = (uint8_t)v[j];
+                                if ((k & 31u) == 0u) out[w] = (uint8_t)(cw_umin(32u, run - k) - 1u);
+                            }
+                        }
+                        cum += (uint32_t)cw_popc(sel[j]);
+                    }
+                }
+                cw_syncwarp();  // the map is read before the next group's counts overwrite the scratch
+            } else {
+                const uint32_t lit = P - back - A, mcode = E - P - 4u + back;
+                const uint32_t le = cw_lz4_ext_bytes(lit);
+                const uint32_t sz = mine ? 3u + le + lit + cw_lz4_ext_bytes(mcode) : 0u;
+                uint32_t inc = sz;  // inclusive prefix sum over the lanes
+    #pragma unroll
+                for (uint32_t d = 1; d < 32u; d <<= 1) {
+                    const uint32_t t = cw_shfl(inc, lane >= d ? lane - d : lane);
+                    if (lane >= d) inc += t;
+                }
+                const uint32_t total = cw_shfl(inc, 31u);
+                // (ordered: after the allotment of group g - 1) this group's place in the block
+                if (g) {
+                    cw_lz4f_tok_wait(&team->tok_emit[rank], seen + 1u, lane);
+                    seen++;
+                }
+                op = cw_ld_vol(&team->op);
+                cw_syncwarp();  // every lane has read it before lane 0 writes the new value
+                if (lane == 0u) cw_st_vol(&team->op, op + total);
+                if (g + 1u < groups) cw_lz4f_tok_post(&team->tok_emit[next], lane);
+                const uint32_t start = op + inc - sz;
+                cw_syncwarp();  // the entries are read: the scratch now takes the literal map
+                if (mine) {
+                    uint32_t w = start;
+                    out[w++] = (uint8_t)((cw_umin(lit, 15u) << 4) | cw_umin(mcode, 15u));
+                    if (lit >= 15u) w = cw_lz4_put_ext1(out, w, lit - 15u);
+                    scr->map[lane][0] = w - A;  // literal x of my sequence goes to out[w - A + x]
+                    scr->map[lane][1] = A | ((P - back) << 16);
+                    w += lit;
+                    const uint32_t off = P - C;
+                    out[w] = (uint8_t)off;
+                    out[w + 1u] = (uint8_t)(off >> 8);
+                    if (mcode >= 15u) cw_lz4_put_ext1(out, w + 2u, mcode - 15u);
+                }
+                op += total;
+                cw_syncwarp();
+                // literals in front of the group (they belong to its first sequence): copied by the whole warp
+                if (anchor < sbase) {
+                    const uint32_t m0 = scr->map[0][0], fend = scr->map[0][1] >> 16;
+                    const uint32_t stop = cw_umin(sbase, fend);
+                    if (stop > anchor) {
+                        if (stop - anchor <= 32u) {  // the usual case: a few bytes between the last match and the group
+                            if (lane < stop - anchor) out[m0 + anchor + lane] = cw_lz4_src8<DIRECT>(s, anchor + lane);
+                        } else
+                            cw_lz4f_copy<DIRECT>(out, m0 + anchor, s, anchor, stop - anchor, nw);
+                    }
+                }
+                // literals inside the group: every position looks up its sequence and stores its own byte
+                uint32_t cum = 0;
+    #pragma unroll
+                for (int j = 0; j < SWN; j++) {
+                    const uint32_t x = sbase + 32u * j + lane;
+                    const uint32_t idx = cum + (uint32_t)cw_popc(sel[j] & lt);
+                    if (idx < tot) {
+                        const uint32_t m0 = scr->map[idx][0], m1 = scr->map[idx][1];
+                        if (x >= (m1 & 0xffffu) && x < (m1 >> 16)) out[m0 + x] = (uint8_t)v[j];
+                    }
+                    cum += (uint32_t)cw_popc(sel[j]);
+                }
+                cw_syncwarp();  // the map is read before the next group's counts overwrite the scratch
             }
-            cw_syncwarp();  // the map is read before the next group's matches overwrite the scratch
         }
         if ((groups - 1u) % nteam != rank) return CW_LZ4_NONE;  // another warp owns the last group and finishes the chunk
         anchor = ip == 1u ? 0u : ip;
@@ -437,11 +613,18 @@ CW_DEV uint32_t cw_lz4f_team_chunk(const uint8_t *s, uint32_t n, uint16_t *table
         return CW_LZ4_NONE;
     // ---- end of chunk: the final literal run [anchor, n) ----
     const uint32_t lit = n - anchor;
-    const uint32_t qe = op + 1u + cw_lz4_ext_bytes(lit);
-    if (lane == 0u) {
-        out[op] = (uint8_t)(cw_umin(lit, 15u) << 4);
-        if (lit >= 15u) cw_lz4_put_ext1(out, op + 1u, lit - 15u);
+    if constexpr (LZF) {
+        const uint32_t total = op + lit + ((lit + 31u) >> 5);
+        if (total > cap) return 0u;  // did not shrink: the caller keeps the chunk as it is (lzf.h:59-64)
+        cw_lzff_put_literals<DIRECT>(out, op, s, anchor, lit, lit);
+        return total;
+    } else {
+        const uint32_t qe = op + 1u + cw_lz4_ext_bytes(lit);
+        if (lane == 0u) {
+            out[op] = (uint8_t)(cw_umin(lit, 15u) << 4);
+            if (lit >= 15u) cw_lz4_put_ext1(out, op + 1u, lit - 15u);
+        }
+        cw_lz4f_copy<DIRECT>(out, qe, s, anchor, lit, nw);
+        return qe + lit;
     }
-    cw_lz4_copy_warp<DIRECT>(out, qe, s, anchor, lit, nw, lane);
-    return qe + lit;
 }

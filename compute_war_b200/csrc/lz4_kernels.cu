@@ -59,36 +59,43 @@ __global__ void __launch_bounds__((CW_LZ4_MAX_PARSERS + CW_LZ4_MAX_EMITTERS) * 3
 // fast mode (lz4_fast.cuh): teams of `nteam` warps, one chunk per team at a time; every team stages, parses and emits
 // on its own.  As many teams as slots fit into the SM's shared memory (and hardware barriers: 15).
 #ifndef CW_LZ4F_MAX_WARPS
-#define CW_LZ4F_MAX_WARPS 26  // 832 threads: ptxas may use 78 registers
+#define CW_LZ4F_MAX_WARPS 32  // 1024 threads: ptxas may use 64 registers (the kernel needs 62, no spills)
 #endif
 #define CW_LZ4F_MAX_TEAMS 15
-#ifndef CW_LZ4F_TEAM_DEFAULT
-#define CW_LZ4F_TEAM_DEFAULT 2
-#endif
-template <int HASHLOG, bool ALIGNED, bool DIRECT>
+template <int HASHLOG, bool ALIGNED, bool DIRECT, int CODEC = CW_F_LZ4>
 __global__ void __launch_bounds__(CW_LZ4F_MAX_WARPS * 32, 1)
     cw_lz4f_kernel(const uint8_t *__restrict__ src, uint32_t chunk, uint64_t n_chunks, uint8_t *__restrict__ dst, uint64_t stride,
-                   uint32_t *__restrict__ lens, unsigned long long *work, uint32_t slot_bytes, uint32_t nteam)
+                   uint32_t *__restrict__ lens, unsigned long long *work, uint32_t slot_bytes, uint32_t teams)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bars[CW_LZ4F_MAX_WARPS];
-    const unsigned warp = threadIdx.x >> 5, t = warp / nteam;
-    cw_lz4f_team_role<HASHLOG, ALIGNED, DIRECT>(smem + (size_t)t * slot_bytes, &bars[t], warp - t * nteam, nteam, 1u + t, src, chunk,
-                                                n_chunks, work, dst, stride, lens);
+    __shared__ uint64_t bars[CW_LZ4F_MAX_TEAMS];
+    const CwLz4fPlace pl = cw_lz4f_place(threadIdx.x >> 5, teams, blockDim.x >> 5);
+    cw_lz4f_team_role<HASHLOG, ALIGNED, DIRECT, CODEC>(smem + (size_t)pl.team * slot_bytes, &bars[pl.team], pl.rank, pl.nteam,
+                                                       1u + pl.team, src, chunk, n_chunks, work, dst, stride, lens);
 }
 
-// warps per chunk: 2 while shared memory holds 13+ chunks per SM (26 warps issue 75 % of the slots); chunks that are read
-// in place (> 16 KiB) leave room for only 6 tables, so 4 warps share each of them (profiles/r02_lz4_fast_teams.txt)
-int cw_lz4f_team_size(uint32_t chunk)
+// Teams and warps of a fast-mode CTA.  Shared memory decides how many chunks an SM holds (`slots`: 13 at 8 KiB, 6 tables
+// for chunks read in place), the register file how many warps it runs (`max_warps`); the warps are spread over the
+// slots as evenly as they go (cw_lz4f_place).  CW_LZ4F_TEAM = n forces n warps per chunk (profiling scripts).
+void cw_lz4f_shape(int slots, int max_warps, int *teams, int *warps)
 {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("CW_LZ4F_TEAM");  // tuning knob for the profiling scripts
-        v = e ? atoi(e) : 0;
-        if (v > CW_LZ4F_MAX_TEAM) v = CW_LZ4F_MAX_TEAM;
+    static int forced = -1;
+    if (forced < 0) {
+        const char *e = getenv("CW_LZ4F_TEAM");
+        forced = e ? atoi(e) : 0;
+        if (forced > CW_LZ4F_MAX_TEAM) forced = CW_LZ4F_MAX_TEAM;
     }
-    if (v > 0) return v;
-    return chunk > CW_LZ4_DIRECT_ABOVE ? 4 : CW_LZ4F_TEAM_DEFAULT;
+    int t = slots < CW_LZ4F_MAX_TEAMS ? slots : CW_LZ4F_MAX_TEAMS;  // one hardware barrier per team
+    if (t > max_warps) t = max_warps;
+    int w;
+    if (forced > 0) {
+        if (t * forced > max_warps) t = max_warps / forced;
+        w = t * forced;
+    } else {
+        w = t * CW_LZ4F_MAX_TEAM < max_warps ? t * CW_LZ4F_MAX_TEAM : max_warps;
+    }
+    *teams = t;
+    *warps = w;
 }
 
 static int g_lz4_max_smem = 0, g_lz4f_max_smem = 0;
@@ -112,6 +119,11 @@ cudaError_t cw_lz4_configure(const CwDeviceInfo &dev)
     CW_CFG(12, true, false) CW_CFG(12, false, false) CW_CFG(13, true, false) CW_CFG(13, false, false)
     CW_CFG(14, true, true) CW_CFG(14, false, false)
 #undef CW_CFG
+#define CW_CFG(HL, AL, DI)                                                                                                         \
+    if ((e = cudaFuncSetAttribute(cw_lz4f_kernel<HL, AL, DI, CW_F_LZF>, cudaFuncAttributeMaxDynamicSharedMemorySize, mf)) != cudaSuccess) \
+        return e;
+    CW_CFG(13, true, false) CW_CFG(13, false, false) CW_CFG(14, true, false) CW_CFG(14, false, false) CW_CFG(14, true, true)
+#undef CW_CFG
     return cudaSuccess;
 }
 
@@ -123,21 +135,20 @@ cudaError_t cw_launch_lz4(const CwDeviceInfo &dev, bool fast, const uint8_t *d_s
     if (fast) {
         // 12 / 13 / 14 table bits by chunk size (lz4_fast.cuh); teams of warps, no emitters
         const int hl = cw_lz4f_hashlog(chunk);
-        int nteam = cw_lz4f_team_size(chunk);
-        const uint32_t fslot = cw_lz4f_slot_bytes(chunk, hl, direct, (uint32_t)nteam);
-        int teams = g_lz4f_max_smem / (int)fslot;
-        if (teams < 1) return cudaErrorInvalidValue;
-        if (nteam > 1 && teams > CW_LZ4F_MAX_TEAMS) teams = CW_LZ4F_MAX_TEAMS;
-        if (teams * nteam > CW_LZ4F_MAX_WARPS) teams = CW_LZ4F_MAX_WARPS / nteam;
-        if (const char *e = getenv("CW_LZ4_PARSERS")) {  // tuning knob for the profiling scripts
-            const int v = atoi(e);
-            if (v > 0 && v < teams) teams = v;
+        // a slot is sized for the largest team it may get; the slot count follows from that, then the final shape
+        int teams = 0, warps = 0;
+        uint32_t fslot = cw_lz4f_slot_bytes(chunk, hl, direct, CW_LZ4F_MAX_TEAM);
+        for (int it = 0; it < 2; it++) {
+            const int slots = g_lz4f_max_smem / (int)fslot;
+            if (slots < 1) return cudaErrorInvalidValue;
+            cw_lz4f_shape(slots, CW_LZ4F_MAX_WARPS, &teams, &warps);
+            fslot = cw_lz4f_slot_bytes(chunk, hl, direct, (uint32_t)((warps + teams - 1) / teams));
         }
         uint64_t fctas = (n + (uint64_t)teams - 1) / (uint64_t)teams;
         if (fctas > (uint64_t)dev.sm_count) fctas = (uint64_t)dev.sm_count;
-#define CW_GOF(HL, AL, DI)                                                                                                    \
-    cw_lz4f_kernel<HL, AL, DI><<<(unsigned)fctas, teams * nteam * 32, (size_t)teams * fslot, st>>>(d_src, chunk, n, d_dst, stride, \
-                                                                                                 d_lens, work, fslot, (uint32_t)nteam)
+#define CW_GOF(HL, AL, DI)                                                                                               \
+    cw_lz4f_kernel<HL, AL, DI><<<(unsigned)fctas, warps * 32, (size_t)teams * fslot, st>>>(d_src, chunk, n, d_dst, stride, \
+                                                                                          d_lens, work, fslot, (uint32_t)teams)
         if (hl == 12) {
             if (aligned) CW_GOF(12, true, false);
             else CW_GOF(12, false, false);
@@ -184,5 +195,36 @@ cudaError_t cw_launch_lz4(const CwDeviceInfo &dev, bool fast, const uint8_t *d_s
     else if (aligned) CW_GO(13, true, false);
     else CW_GO(13, false, false);
 #undef CW_GO
+    return cudaGetLastError();
+}
+
+// LZF fast mode: the same team kernel with the LZF flavour of the parse (lz4_fast.cuh); 13 table bits up to 4 KiB chunks,
+// 14 above (cw_lzff_hashlog: chosen like the LZ4 ones, tools/lzf_fast_model.c)
+cudaError_t cw_launch_lzf_fast(const CwDeviceInfo &dev, const uint8_t *d_src, uint32_t chunk, uint64_t n, uint8_t *d_dst,
+                               uint64_t stride, uint32_t *d_lens, unsigned long long *work, cudaStream_t st)
+{
+    const bool aligned = ((chunk & 15u) == 0) && ((reinterpret_cast<uintptr_t>(d_src) & 15u) == 0);
+    const bool direct = aligned && chunk > CW_LZ4_DIRECT_ABOVE;
+    const int hl = cw_lzff_hashlog(chunk);
+    int teams = 0, warps = 0;
+    uint32_t fslot = cw_lz4f_slot_bytes(chunk, hl, direct, CW_LZ4F_MAX_TEAM);
+    for (int it = 0; it < 2; it++) {
+        const int slots = g_lz4f_max_smem / (int)fslot;
+        if (slots < 1) return cudaErrorInvalidValue;
+        cw_lz4f_shape(slots, CW_LZ4F_MAX_WARPS, &teams, &warps);
+        fslot = cw_lz4f_slot_bytes(chunk, hl, direct, (uint32_t)((warps + teams - 1) / teams));
+    }
+    uint64_t fctas = (n + (uint64_t)teams - 1) / (uint64_t)teams;
+    if (fctas > (uint64_t)dev.sm_count) fctas = (uint64_t)dev.sm_count;
+#define CW_GOF(HL, AL, DI)                                                                                                   \
+    cw_lz4f_kernel<HL, AL, DI, CW_F_LZF><<<(unsigned)fctas, warps * 32, (size_t)teams * fslot, st>>>(d_src, chunk, n, d_dst, stride, \
+                                                                                                    d_lens, work, fslot, (uint32_t)teams)
+    if (hl == 13) {
+        if (aligned) CW_GOF(13, true, false);
+        else CW_GOF(13, false, false);
+    } else if (direct) CW_GOF(14, true, true);
+    else if (aligned) CW_GOF(14, true, false);
+    else CW_GOF(14, false, false);
+#undef CW_GOF
     return cudaGetLastError();
 }

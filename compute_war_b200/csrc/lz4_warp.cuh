@@ -99,6 +99,7 @@ CW_DEV uint32_t cw_lz4_step(int32_t j) { return j <= 0 ? 1u : (63u + (uint32_t)j
 // 255-run length extension of a literal / match length, written by ONE lane: bytes for value r (>= 0)
 CW_DEV uint32_t cw_lz4_put_ext1(uint8_t *out, uint32_t op, uint32_t r)
 {
+#pragma unroll 1
     while (r >= 255u) {
         out[op++] = 255u;
         r -= 255u;

@@ -249,6 +249,42 @@ CW_HOSTDEV void cw_skein_load(uint64_t (&w)[WORDS], const uint8_t *p, unsigned a
     }
 }
 
+// The same digest with ONE call site of the block function: message blocks, the final block and the output block go
+// through one loop.  The fused kernels use this form -- three inlined copies of the 72 rounds are 33 KB of SASS, and the
+// instruction cache of an SM whose other warps run the compressor holds 32 KB.
+template <int WORDS, bool ALIGNED, bool UNROLL72>
+CW_HOSTDEV void cw_skein_chunk_compact(const uint64_t (&IV)[WORDS], const uint8_t *p, uint32_t len, uint64_t (&X)[WORDS])
+{
+    constexpr uint32_t B = WORDS * 8;
+    uint64_t w[WORDS];
+#pragma unroll
+    for (int i = 0; i < WORDS; i++) X[i] = IV[i];
+    uint64_t T1 = CW_SKEIN_T1_FIRST | CW_SKEIN_T1_MSG;
+    uint32_t off = 0;
+    bool out_block = false;
+#pragma unroll 1
+    for (;;) {
+        uint64_t T0;
+        if (!out_block) {  // the next 1..B message bytes (an empty message is one zero block); the last block is FINAL
+            const uint32_t rest = len - off, nb = rest > B ? B : rest;
+            cw_skein_load<WORDS, ALIGNED>(w, p + off, nb);
+            off += nb;
+            T0 = off;
+            if (off == len) T1 |= CW_SKEIN_T1_FINAL;
+        } else {  // output block: counter 0 under the final chaining value (skein.c:393-399)
+#pragma unroll
+            for (int i = 0; i < WORDS; i++) w[i] = 0;
+            T0 = 8;
+            T1 = CW_SKEIN_T1_FIRST | CW_SKEIN_T1_FINAL | CW_SKEIN_T1_OUT;
+        }
+        if constexpr (WORDS == 8) cw_tf512_block<UNROLL72>(X, w, T0, T1);
+        else cw_tf256_block(X, w, T0, T1);
+        if (out_block) break;
+        T1 = CW_SKEIN_T1_MSG;
+        out_block = off == len;
+    }
+}
+
 // Hash one chunk of `len` bytes.  IV = cw_skein_iv(...) computed once on the host.  out receives
 // OUT_BYTES (<= 8*WORDS) digest bytes, little-endian words (Skein_Put64_LSB_First, skein_port.h:57).
 // PREFETCH: the next block's words are loaded before the current block is processed.  The lone hash warp of the fused

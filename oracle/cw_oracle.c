@@ -430,6 +430,97 @@ int cwo_lz4_fast_compress(const uint8_t *src, int n_, uint8_t *dst, int cap, int
     return (int)op;
 }
 
+/* ------------------------------------------------------------------------------------------- */
+/* LZF "fast mode" of THIS engine (the LZF flavour of compute_war_b200/csrc/lz4_fast.cuh) -- NOT a reference         */
+/* algorithm.  The reference side is lzf_decompress (lzf.h:98-100, experiment.cpp:118) and the size of               */
+/* lzf_compress(s, l, d, l - 1) (HashAndCompress.cpp:342-348); like the LZ4 one the parse is a deterministic         */
+/* function of the chunk, restated here in scalar form:                                                              */
+/*   3-byte keys; windows of 32 positions, every position 1 .. n - 7 looked up and inserted (lowest position of a    */
+/*   window owns a slot; in-window candidate = the owner if below the position); a position whose 3 bytes equal      */
+/*   those two back takes p - 2; candidates further than 8192 back do not count (lzf.h offsets); greedy choice of    */
+/*   the first verified position at or after the end of the previous match; full forward extension (to the end of    */
+/*   the chunk), backward extension; lzf.h block format with matches longer than 264 bytes written as several        */
+/*   tokens of one distance; 0 when the block would take more than `cap` bytes.                                      */
+/* ------------------------------------------------------------------------------------------- */
+int cwo_lzf_fast_hashlog(size_t chunk) { return chunk <= 4096 ? 13 : 14; }
+
+static uint32_t lzff_put_lits(uint8_t *dst, uint32_t op, const uint8_t *src, uint32_t from, uint32_t lit)
+{
+    for (uint32_t k = 0; k < lit; k++) {
+        if ((k & 31u) == 0) dst[op++] = (uint8_t)((lit - k < 32u ? lit - k : 32u) - 1u);
+        dst[op++] = src[from + k];
+    }
+    return op;
+}
+
+int cwo_lzf_fast_compress(const uint8_t *src, int n_, uint8_t *dst, int cap, int hashlog)
+{
+    enum { W = 32 };
+    static __thread uint16_t table[1 << 14];
+    static __thread uint8_t buf[65536 + 65536 / 32 + 64];
+    const uint32_t n = (uint32_t)n_;
+    uint32_t op = 0, anchor = 0, ip = 1;
+    if (n_ < 0 || n > 65536u || hashlog < 1 || hashlog > 14) return 0;
+    memset(table, 0, sizeof(uint16_t) << hashlog);
+    if (n >= 8) {
+        const uint32_t last = n - 7;
+        for (uint32_t base = 0; base <= last; base += W) {
+            uint32_t cand[W], v[W], h[W];
+            int ok[W];
+            for (int l = 0; l < W; l++) {
+                const uint32_t p = base + l;
+                ok[l] = 0;
+                if (p > last) continue;
+                v[l] = rd32(src + p) & 0xffffffu;
+                h[l] = (v[l] * 2654435761u) >> (32 - hashlog);
+                cand[l] = table[h[l]];
+            }
+            for (int l = W - 1; l >= 0; l--) /* the lowest position of the window owns the slot */
+                if (base + l <= last && base + l != 0) table[h[l]] = (uint16_t)(base + l);
+            for (int l = 0; l < W; l++) {
+                const uint32_t p = base + l;
+                if (p > last || p == 0) continue;
+                const uint32_t w = table[h[l]];
+                if (w < p) cand[l] = w;
+                if (p >= 2 && (rd32(src + p - 2) & 0xffffffu) == v[l]) cand[l] = p - 2;
+                ok[l] = (rd32(src + cand[l]) & 0xffffffu) == v[l] && p - cand[l] <= 8192u;
+            }
+            for (int l = ip > base ? (int)(ip - base) : 0; l < W; l++) {
+                if (!ok[l]) continue;
+                uint32_t cur = base + l, c = cand[l], e = cur + 3, ce = c + 3;
+                while (e < n && src[e] == src[ce]) e++, ce++;
+                while (cur > anchor && c > 0 && src[cur - 1] == src[c - 1]) cur--, c--;
+                op = lzff_put_lits(buf, op, src, anchor, cur - anchor);
+                {
+                    uint32_t len = e - cur;
+                    const uint32_t off = cur - c - 1;
+                    while (len > 264) {
+                        const uint32_t take = len - 264 < 3 ? 262 : 264;
+                        buf[op++] = (uint8_t)((7u << 5) | (off >> 8));
+                        buf[op++] = (uint8_t)(take - 9);
+                        buf[op++] = (uint8_t)off;
+                        len -= take;
+                    }
+                    if (len - 2 < 7) {
+                        buf[op++] = (uint8_t)(((len - 2) << 5) | (off >> 8));
+                        buf[op++] = (uint8_t)off;
+                    } else {
+                        buf[op++] = (uint8_t)((7u << 5) | (off >> 8));
+                        buf[op++] = (uint8_t)(len - 9);
+                        buf[op++] = (uint8_t)off;
+                    }
+                }
+                anchor = ip = e;
+                l = (int)(e - base) - 1;
+            }
+        }
+    }
+    op = lzff_put_lits(buf, op, src, anchor, n - anchor);
+    if (cap < 0 || op > (uint32_t)cap) return 0;
+    memcpy(dst, buf, op);
+    return (int)op;
+}
+
 int cwo_lz4_decompress(const uint8_t *src, int n, uint8_t *dst, int cap)
 {
     const uint8_t *ip = src, *const iend = src + n;

@@ -45,6 +45,10 @@ int cwo_lz4_compress(const uint8_t *src, int n, uint8_t *dst, int dst_cap);
  * cwo_lz4_fast_hashlog(chunk) = what the kernels pick.  Returns bytes written, 0 if dst_cap < bound. */
 int cwo_lz4_fast_hashlog(size_t chunk);
 int cwo_lz4_fast_compress(const uint8_t *src, int n, uint8_t *dst, int dst_cap, int hashlog);
+/* the LZF flavour of the same parse; returns bytes written, 0 when the block would take more than dst_cap bytes (the
+ * engine passes n - 1 like the reference's lzf_compress call) */
+int cwo_lzf_fast_hashlog(size_t chunk);
+int cwo_lzf_fast_compress(const uint8_t *src, int n, uint8_t *dst, int dst_cap, int hashlog);
 /* LZ4 block decoder, bounds-checked; returns decoded size or <0 on malformed input
  * (role of LZ4_decompress_safe, experiment.cpp:256). */
 int cwo_lz4_decompress(const uint8_t *src, int n, uint8_t *dst, int dst_cap);

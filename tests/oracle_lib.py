@@ -54,6 +54,10 @@ def lib():
         L.cwo_lz4_fast_compress.restype = C.c_int
         L.cwo_lz4_fast_hashlog.argtypes = [C.c_size_t]
         L.cwo_lz4_fast_hashlog.restype = C.c_int
+        L.cwo_lzf_fast_compress.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        L.cwo_lzf_fast_compress.restype = C.c_int
+        L.cwo_lzf_fast_hashlog.argtypes = [C.c_size_t]
+        L.cwo_lzf_fast_hashlog.restype = C.c_int
         L.cwo_lz4_decompress.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.cwo_lz4_decompress.restype = C.c_int
         L.cwo_lzf_compress.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint]
@@ -131,6 +135,21 @@ def lz4_fast_chunks(data, chunk: int, stride: int | None = None, hashlog: int = 
     for i in range(n):
         lens[i] = lib().cwo_lz4_fast_compress(d[i * chunk:].ctypes.data_as(C.c_void_p), chunk,
                                               blocks[i].ctypes.data_as(C.c_void_p), stride, hashlog)
+    return blocks, lens
+
+
+def lzf_fast_chunks(data, chunk: int, stride: int | None = None, hashlog: int = 0):
+    """the ENGINE's fast-mode LZF parse restated on the CPU (not a reference algorithm): (blocks[n, stride], lens[n]);
+    lens 0 = the block would not fit in chunk - 1 bytes (the chunk is kept raw)"""
+    d = _as_u8(data)
+    n = len(d) // chunk
+    stride = stride or compress_bound(COMP_LZF, chunk)
+    hashlog = hashlog or int(lib().cwo_lzf_fast_hashlog(chunk))
+    blocks = np.zeros((n, stride), np.uint8)
+    lens = np.zeros(n, np.uint32)
+    for i in range(n):
+        lens[i] = lib().cwo_lzf_fast_compress(d[i * chunk:].ctypes.data_as(C.c_void_p), chunk,
+                                              blocks[i].ctypes.data_as(C.c_void_p), chunk - 1, hashlog)
     return blocks, lens
 
 

@@ -91,25 +91,41 @@ struct Lz4fJob {
     CwLz4fScratch *scr;  // one per warp
     uint8_t *out;
     uint32_t len;
-    int hashlog, direct, nteam;
+    int hashlog, direct, nteam, codec;
 };
 static void lz4f_body(void *a, int warp)
 {
     Lz4fJob *j = (Lz4fJob *)a;
     uint32_t r, seen = 0;
     const uint32_t rank = (uint32_t)warp, nt = (uint32_t)j->nteam;
-    if (j->direct) {
-        if (j->hashlog == 14) r = cw_lz4f_team_chunk<14, true>(j->s, j->n, j->table, j->team, j->scr + warp, j->out, rank, nt, seen);
-        else r = cw_lz4f_team_chunk<13, true>(j->s, j->n, j->table, j->team, j->scr + warp, j->out, rank, nt, seen);
-    } else if (j->hashlog == 12) r = cw_lz4f_team_chunk<12, false>(j->s, j->n, j->table, j->team, j->scr + warp, j->out, rank, nt, seen);
-    else if (j->hashlog == 13) r = cw_lz4f_team_chunk<13, false>(j->s, j->n, j->table, j->team, j->scr + warp, j->out, rank, nt, seen);
-    else r = cw_lz4f_team_chunk<14, false>(j->s, j->n, j->table, j->team, j->scr + warp, j->out, rank, nt, seen);
+    if (j->codec == CW_F_LZF) {  // the LZF flavour: a block may take n - 1 bytes
+        const uint32_t cap = j->n ? j->n - 1u : 0u;
+        if (j->direct) r = cw_lz4f_team_chunk<CW_F_LZF, 14, true>(j->s, j->n, j->table, j->team, j->scr + warp, j->out, rank, nt, seen, cap);
+        else if (j->hashlog == 13) r = cw_lz4f_team_chunk<CW_F_LZF, 13, false>(j->s, j->n, j->table, j->team, j->scr + warp, j->out, rank, nt, seen, cap);
+        else r = cw_lz4f_team_chunk<CW_F_LZF, 14, false>(j->s, j->n, j->table, j->team, j->scr + warp, j->out, rank, nt, seen, cap);
+    } else if (j->direct) {
+        if (j->hashlog == 14) r = cw_lz4f_team_chunk<CW_F_LZ4, 14, true>(j->s, j->n, j->table, j->team, j->scr + warp, j->out, rank, nt, seen);
+        else r = cw_lz4f_team_chunk<CW_F_LZ4, 13, true>(j->s, j->n, j->table, j->team, j->scr + warp, j->out, rank, nt, seen);
+    } else if (j->hashlog == 12) r = cw_lz4f_team_chunk<CW_F_LZ4, 12, false>(j->s, j->n, j->table, j->team, j->scr + warp, j->out, rank, nt, seen);
+    else if (j->hashlog == 13) r = cw_lz4f_team_chunk<CW_F_LZ4, 13, false>(j->s, j->n, j->table, j->team, j->scr + warp, j->out, rank, nt, seen);
+    else r = cw_lz4f_team_chunk<CW_F_LZ4, 14, false>(j->s, j->n, j->table, j->team, j->scr + warp, j->out, rank, nt, seen);
     if (r != CW_LZ4_NONE && cw_lane() == 0) j->len = r;
 }
 // hashlog 0 = what the kernels pick for the chunk size; nteam = warps per chunk
+static uint32_t emu_fast(int codec, const uint8_t *src, uint32_t n, uint8_t *out, int hashlog, int direct, int nteam);
 extern "C" uint32_t emu_lz4_fast(const uint8_t *src, uint32_t n, uint8_t *out, int hashlog, int direct, int nteam)
 {
-    if (!hashlog) hashlog = cw_lz4f_hashlog(n);
+    return emu_fast(CW_F_LZ4, src, n, out, hashlog, direct, nteam);
+}
+// LZF flavour: hashlog 13 or 14 (0 = what the kernels pick); direct runs the 14-bit in-place variant
+extern "C" uint32_t emu_lzf_fast(const uint8_t *src, uint32_t n, uint8_t *out, int hashlog, int direct, int nteam)
+{
+    return emu_fast(CW_F_LZF, src, n, out, hashlog, direct, nteam);
+}
+static uint32_t emu_fast(int codec, const uint8_t *src, uint32_t n, uint8_t *out, int hashlog, int direct, int nteam)
+{
+    if (!hashlog) hashlog = codec == CW_F_LZF ? cw_lzff_hashlog(n) : cw_lz4f_hashlog(n);
+    if (codec == CW_F_LZF && direct) hashlog = 14;
     if (nteam < 1) nteam = 1;
     std::vector<uint16_t> table(1u << hashlog, 0);
     std::vector<CwLz4fScratch> scr(nteam);
@@ -120,7 +136,7 @@ extern "C" uint32_t emu_lz4_fast(const uint8_t *src, uint32_t n, uint8_t *out, i
     if (!direct) {
         std::vector<uint32_t> staged((n + CW_LZ4_PAD + 3) / 4 + 4, 0);
         memcpy(staged.data(), src, n);
-        Lz4fJob j{(const uint8_t *)staged.data(), n, table.data(), &team, scr.data(), out, 0xffffffffu, hashlog, 0, nteam};
+        Lz4fJob j{(const uint8_t *)staged.data(), n, table.data(), &team, scr.data(), out, 0xffffffffu, hashlog, 0, nteam, codec};
         cwemu::run_block(nteam, lz4f_body, &j);
         return j.len;
     }
@@ -129,7 +145,7 @@ extern "C" uint32_t emu_lz4_fast(const uint8_t *src, uint32_t n, uint8_t *out, i
     mprotect(map + span, page, PROT_NONE);
     uint8_t *exact = map + span - n;
     memcpy(exact, src, n);
-    Lz4fJob j{(const uint8_t *)exact, n, table.data(), &team, scr.data(), out, 0xffffffffu, hashlog, 1, nteam};
+    Lz4fJob j{(const uint8_t *)exact, n, table.data(), &team, scr.data(), out, 0xffffffffu, hashlog, 1, nteam, codec};
     cwemu::run_block(nteam, lz4f_body, &j);
     munmap(map, span + page);
     return j.len;

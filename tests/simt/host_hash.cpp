@@ -9,8 +9,11 @@ extern "C" void host_skein512(const uint8_t *p, uint32_t len, uint8_t *out, int 
 {
     uint64_t IV[8], X[8];
     cw_skein_iv<8>(IV, 512);
-    // unroll72: 0 = 3 x 24-round body, 1 = 72 rounds unrolled, 2 / 3 = the same two with the next-block prefetch loop
-    if (unroll72 == 1) cw_skein_chunk<8, 64, false, true>(IV, p, len, X);
+    // unroll72: 0 = 3 x 24-round body, 1 = 72 rounds unrolled, 2 / 3 = the same two with the next-block prefetch loop,
+    // 4 / 5 = the same two in the single-call-site form of the fused kernels
+    if (unroll72 == 4) cw_skein_chunk_compact<8, false, false>(IV, p, len, X);
+    else if (unroll72 == 5) cw_skein_chunk_compact<8, false, true>(IV, p, len, X);
+    else if (unroll72 == 1) cw_skein_chunk<8, 64, false, true>(IV, p, len, X);
     else if (unroll72 == 0) cw_skein_chunk<8, 64, false, false>(IV, p, len, X);
     else if (unroll72 == 3) cw_skein_chunk<8, 64, false, true, true>(IV, p, len, X);
     else cw_skein_chunk<8, 64, false, false, true>(IV, p, len, X);
@@ -20,7 +23,8 @@ extern "C" void host_skein256_128(const uint8_t *p, uint32_t len, uint8_t *out, 
 {
     uint64_t IV[4], X[4];
     cw_skein_iv<4>(IV, 128);
-    if (prefetch) cw_skein_chunk<4, 16, false, true, true>(IV, p, len, X);
+    if (prefetch == 2) cw_skein_chunk_compact<4, false, true>(IV, p, len, X);
+    else if (prefetch) cw_skein_chunk<4, 16, false, true, true>(IV, p, len, X);
     else cw_skein_chunk<4, 16, false, true>(IV, p, len, X);
     memcpy(out, X, 16);
 }

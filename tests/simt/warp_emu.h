@@ -90,6 +90,13 @@ static inline unsigned cw_match_any(uint32_t v)
     for (int i = 0; i < 32; i++) m |= (unsigned)(s[i] == v) << i;
     return m;
 }
+static inline uint32_t cw_reduce_or(uint32_t v)
+{
+    const uint32_t *s = cwemu::collective(v);
+    uint32_t m = 0;
+    for (int i = 0; i < 32; i++) m |= s[i];
+    return m;
+}
 static inline void cw_syncwarp() { (void)cwemu::collective(0); }
 static inline int cw_ffs(uint32_t v) { return v ? __builtin_ctz(v) + 1 : 0; }
 static inline int cw_clz(uint32_t v) { return v ? __builtin_clz(v) : 32; }

@@ -244,10 +244,10 @@ def test_fast_mode_roundtrips_and_ratio(eng, golden, alg):
             if O.have_ref_cli():  # the reference's own LZ4_decompress_safe / lzf_decompress (built from its archives)
                 back = O.ref_decompress_chunks(alg, chunk, blocks, lens)
                 assert len(back) == rec["n"] * chunk and (back == d[: len(back)]).all(), (ent["name"], chunk)
-            if alg == O.COMP_LZ4:  # the fast parse is a deterministic function of the chunk: byte-equal to its restatement
-                fb, fl = O.lz4_fast_chunks(d, chunk)
-                assert (lens == fl).all() and all((blocks[i, : fl[i]] == fb[i, : fl[i]]).all() for i in range(len(fl))), \
-                    (ent["name"], chunk)
+            # the fast parse is a deterministic function of the chunk: byte-equal to its scalar restatement in the oracle
+            fb, fl = O.lz4_fast_chunks(d, chunk) if alg == O.COMP_LZ4 else O.lzf_fast_chunks(d, chunk)
+            assert (lens == fl).all() and all((blocks[i, : fl[i]] == fb[i, : fl[i]]).all() for i in range(len(fl))), \
+                (ent["name"], chunk)
             mine = sum(int(x) if x else chunk for x in lens)
             theirs = sum(int(x) if x else chunk for x in rec[O.COMP_NAMES[alg] + "_lens"])
             assert mine <= theirs * 1.01, (ent["name"], chunk, mine, theirs)
@@ -519,8 +519,27 @@ def test_process_block_fused_ragged_sizes(eng, golden, halg, mode):
         assert O.verify_roundtrip(O.COMP_LZ4, d, chunk, blocks, lens) == 0, (chunk, mode)
 
 
+@pytest.mark.parametrize("halg", [O.HASH_SKEIN512, O.HASH_SKEIN256_128, O.HASH_SHA256])
+@pytest.mark.parametrize("calg", [O.COMP_LZ4, O.COMP_LZF])
+def test_process_block_fused_fast_equals_separate(eng, golden, halg, calg):
+    """fast mode of the fused pass (hc_sklz4 / hc_sklzf / hc_shlz4 ...): digests equal the oracle's, blocks equal the restated
+    fast parse byte for byte (= what the stand-alone fast kernel writes) and decode back; staged chunks, chunks read in place
+    (64 KiB), ragged sizes, incompressible chunks (LZF: length 0)"""
+    blob = golden["blob"]
+    for chunk in (4096, 8192, 16384, 65536, 5000, 20001):
+        n = 24 if chunk <= 8192 else 6
+        d = np.concatenate([blob[11: 11 + n * chunk], O.synth(chunk, 3, n)])
+        dig, blocks, lens = eng.process_block(halg, calg, d, chunk, cw.MODE_FAST)
+        assert (dig == O.hash_chunks(halg, d, chunk)).all(), chunk
+        fb, fl = O.lz4_fast_chunks(d, chunk) if calg == O.COMP_LZ4 else O.lzf_fast_chunks(d, chunk)
+        assert (lens == fl).all(), (chunk, lens, fl)
+        assert all((blocks[i, : fl[i]] == fb[i, : fl[i]]).all() for i in range(len(fl))), chunk
+        assert O.verify_roundtrip(calg, d, chunk, blocks, lens) == 0, chunk
+
+
 @pytest.mark.parametrize("halg,calg,mode", [(O.HASH_SKEIN512, O.COMP_LZ4, 0), (O.HASH_SKEIN512, O.COMP_LZ4, 1),
-                                            (O.HASH_SKEIN256_128, O.COMP_LZF, 0), (O.HASH_SHA256, O.COMP_LZ4, 0)])
+                                            (O.HASH_SKEIN256_128, O.COMP_LZF, 0), (O.HASH_SKEIN512, O.COMP_LZF, 1),
+                                            (O.HASH_SHA256, O.COMP_LZ4, 0)])
 def test_packed_host_output(eng, halg, calg, mode):
     """cw_hash_compress_packed: packed bytes / offsets / lens / digests equal the strided call's, across pipeline slices
     (72 MiB > one 64 MiB slice), incompressible chunks included (LZF: stored raw); a short buffer is refused"""

@@ -46,11 +46,11 @@ def test_device_hash_source_on_host(hosthash):
     for n in [0, 1, 7, 8, 31, 32, 33, 55, 56, 63, 64, 65, 127, 128, 129, 200, 1000, 4096, 8192, 65536]:
         b = rng.integers(0, 256, n + 1, dtype=np.uint8)
         bb = b[:n].tobytes()
-        for unroll in (0, 1, 2, 3):  # both round-loop shapes, without and with the next-block prefetch loop
+        for unroll in (0, 1, 2, 3, 4, 5):  # both round-loop shapes, without and with the next-block prefetch loop
             out = np.zeros(64, np.uint8)
             hosthash.host_skein512(b.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p), unroll)
             assert out.tobytes() == O.skein(512, 512, bb), (n, unroll)
-        for prefetch in (0, 1):
+        for prefetch in (0, 1, 2):
             out = np.zeros(16, np.uint8)
             hosthash.host_skein256_128(b.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p), prefetch)
             assert out.tobytes() == O.skein(256, 128, bb), (n, prefetch)
@@ -187,6 +187,60 @@ def test_lz4_fast_restatement_ratio_and_reference_decoder(golden):
             else:
                 assert O.verify_roundtrip(O.COMP_LZ4, d, chunk, blocks, lens) == 0
             assert int(lens.sum()) <= 1.01 * sum(rec["lz4_lens"]), (ent["name"], chunk)
+
+
+def _raw_where_zero(d, chunk, blocks, lens):
+    """LZF convention: length 0 = the chunk did not shrink and is kept raw (lzf.h:59-64); the decoders take it from the block"""
+    b = blocks.copy()
+    for i in np.nonzero(np.asarray(lens) == 0)[0]:
+        b[i, :chunk] = d[i * chunk: (i + 1) * chunk]
+    return b
+
+
+@pytest.mark.parametrize("lowest_lane_wins", [1, 0])
+def test_lzf_fast_parse_on_emulator(emu, golden, lowest_lane_wins):
+    """LZF fast mode (the LZF flavour of csrc/lz4_fast.cuh on the warp emulator): byte-identical to its scalar restatement in
+    the oracle whichever lane wins a store race, both table sizes, staged and in-place source, teams of 1-6 warps; blocks
+    restored by the restated lzf decoder (the reference's own decoder runs in the test below)"""
+    emu.emu_lzf_fast.restype = C.c_uint32
+    emu.emu_set_store_winner(lowest_lane_wins)
+    try:
+        cases = _cases(golden, small=True)
+        if not lowest_lane_wins:
+            cases = cases[::3]
+        for c in cases:
+            n = len(c)
+            for hl, direct in ((0, 0), (13, 0), (14, 1 if n % 4 == 0 else 0)):
+                blocks, lens = O.lzf_fast_chunks(c, n, hashlog=hl) if n else (None, [0])
+                for nteam in (1, 2, 3, 6):
+                    out = np.zeros(n + n // 32 + 64, np.uint8)
+                    r = emu.emu_lzf_fast(c.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p), hl, direct, nteam)
+                    assert r == lens[0] and (out[:r] == blocks[0, :r]).all(), (n, hl, direct, nteam)
+                if n and r:
+                    assert O.verify_roundtrip(O.COMP_LZF, c, n, out[None, :], np.array([r], np.uint32)) == 0, (n, hl)
+    finally:
+        emu.emu_set_store_winner(0)
+
+
+def test_lzf_fast_restatement_ratio_and_reference_decoder(golden):
+    """the restated LZF fast parse over the golden corpus sample: every block decodes with the reference's lzf_decompress and
+    every file stays within 1 % of the reference's compressed size at 4 K / 8 K / 64 K (chunks kept raw count in full)"""
+    ref, blob = golden["ref"], golden["blob"]
+    for ent in ref["files"]:
+        d = blob[ent["offset"]: ent["offset"] + ent["size"]]
+        for chunk in (4096, 8192, 65536):
+            rec = ref["corpus"][ent["name"]][str(chunk)]
+            if rec["n"] == 0:
+                continue
+            blocks, lens = O.lzf_fast_chunks(d, chunk)
+            full = _raw_where_zero(d, chunk, blocks, lens)
+            if O.have_ref_cli():
+                back = O.ref_decompress_chunks(O.COMP_LZF, chunk, full, lens)
+                assert (back == d[: len(back)]).all() and len(back) == rec["n"] * chunk
+            else:
+                assert O.verify_roundtrip(O.COMP_LZF, d, chunk, full, lens) == 0
+            stored = lambda ls: sum(int(x) if x else chunk for x in ls)
+            assert stored(lens) <= 1.01 * stored(rec["lzf_lens"]), (ent["name"], chunk, stored(lens), stored(rec["lzf_lens"]))
 
 
 def test_lzf_warp_algorithm_byte_identical(emu, golden):

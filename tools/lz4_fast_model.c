@@ -21,7 +21,7 @@ static uint32_t rd32(const uint8_t *s, uint32_t p)
     return v;
 }
 
-static int SW = 1, RETEST = 0, POST = 0, HL = 13, INWIN = 0, INS_IN_MATCH = 1, BACK = 1, W = 32;
+static int SW = 1, RETEST = 0, POST = 0, HL = 13, INWIN = 0, INS_IN_MATCH = 1, BACK = 1, W = 32, QUAD = 0, PER = 2;
 
 static uint32_t put_ext(uint8_t *out, uint32_t op, uint32_t r)
 {
@@ -41,13 +41,13 @@ static uint32_t model_compress(const uint8_t *s, uint32_t n, uint8_t *out)
     if (n >= 13) {
         const uint32_t last = n - 12, matchlimit = n - 5;
         for (uint32_t sbase = 0; sbase <= last; sbase += W * SW) {
-            static uint32_t cand[16][64], v[16][64], h[16][64];
-            static int ok[16][64], live[16];
-            if (ip >= sbase + W * SW) continue;  // whole group inside a match
+            static uint32_t cand[16][128], v[16][128], h[16][128];
+            static int ok[16][128], live[16];
+            if (!QUAD && ip >= sbase + W * SW) continue;  // whole group inside a match
             // phase 1: look-ups and inserts of every live window of the group, window by window
             for (int j = 0; j < SW; j++) {
                 const uint32_t base = sbase + j * W;
-                live[j] = base <= last && ip < base + W;  // windows inside a match when the group starts are skipped
+                live[j] = base <= last && (QUAD || ip < base + W);  // windows inside a match when the group starts are skipped
                 if (!live[j]) continue;
                 for (int l = 0; l < W; l++) {
                     const uint32_t p = base + l;
@@ -57,6 +57,11 @@ static uint32_t model_compress(const uint8_t *s, uint32_t n, uint8_t *out)
                     h[j][l] = (v[j][l] * 2654435761u) >> (32 - HL);
                     cand[j][l] = table[h[j][l]];
                 }
+                if (QUAD) {  // owner = minimal (p & 3, p >> 2): four store rounds k = 3..0, lowest lane wins a round
+                    for (int k = 3; k >= 0; k--)
+                        for (int l = W - 4 + k; l >= 0; l -= 4)
+                            if (base + l <= last && base + l != 0) table[h[j][l]] = (uint16_t)(base + l);
+                } else
                 for (int l = W - 1; l >= 0; l--)
                     if (base + l <= last && base + l != 0) table[h[j][l]] = (uint16_t)(base + l);  // lowest position owns the slot
                 for (int l = 0; l < W; l++) {
@@ -64,7 +69,7 @@ static uint32_t model_compress(const uint8_t *s, uint32_t n, uint8_t *out)
                     if (p > last || p == 0) continue;
                     const uint32_t w = table[h[j][l]];
                     if (w < p) cand[j][l] = w;
-                    if (p >= 2 && rd32(s, p - 2) == v[j][l]) cand[j][l] = p - 2;
+                    if (PER && p >= (uint32_t)PER && rd32(s, p - PER) == v[j][l]) cand[j][l] = p - PER;
                     ok[j][l] = rd32(s, cand[j][l]) == v[j][l];
                 }
             }
@@ -111,6 +116,8 @@ int main(int argc, char **argv)
     W = atoi(argv[6]);
     RETEST = getenv("RETEST") ? atoi(getenv("RETEST")) : 0;
     SW = getenv("SW") ? atoi(getenv("SW")) : 1;
+    QUAD = getenv("QUAD") ? atoi(getenv("QUAD")) : 0;
+    PER = getenv("PER") ? atoi(getenv("PER")) : 2;
     POST = getenv("POST") ? atoi(getenv("POST")) : 0;
     uint8_t *out = malloc(2 * chunk + 64), *ref = malloc(2 * chunk + 64), *dec = malloc(chunk);
     unsigned long long T = 0, R = 0;

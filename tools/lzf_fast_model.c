@@ -16,7 +16,7 @@ static uint32_t model(const uint8_t*s,uint32_t n){
   memset(table,0,sizeof(uint16_t)<<HL);
   uint32_t size=0,anchor=0,ip=1;
   if(n>=8){
-    const uint32_t last=n-4;   // last position hashed (3 bytes + 1 slack)
+    const uint32_t last=n-7;   // last position a match may start at: the 3 + 4 bytes it looks at lie inside the chunk
     for(uint32_t base=0;base<=last;base+=32){
       uint32_t cand[32],v[32],h[32]; int ok[32];
       for(int l=0;l<32;l++){uint32_t p=base+l; ok[l]=0; if(p>last)continue; v[l]=rd24(s,p); h[l]=(v[l]*2654435761u)>>(32-HL); cand[l]=table[h[l]];}

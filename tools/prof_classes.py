@@ -1,6 +1,6 @@
 """Per-data-class throughput of the compress / hash kernels (device resident).
 Data sets: the four classes of the synthetic stream separately, the mixed stream, and (if staged) the Canterbury
-corpus tiled.  usage: python tools/prof_classes.py [lz4|lzf|fused] [chunk]"""
+corpus tiled.  usage: python tools/prof_classes.py [lz4|lzf|fused|fusedlzf] [chunk]   (CW_MODE=1: fast mode)"""
 import ctypes as C
 import os
 import sys
@@ -47,7 +47,7 @@ dev = torch.device("cuda:0")
 st = torch.cuda.Stream(device=dev)
 torch.cuda.set_stream(st)
 s = st.cuda_stream
-comp = cw.COMP_LZF if what == "lzf" else cw.COMP_LZ4
+comp = cw.COMP_LZF if what in ("lzf", "fusedlzf") else cw.COMP_LZ4  # fusedlzf: Skein-512 + LZF in one pass
 stride = cw.compress_bound(comp, chunk)
 for name, data in sets.items():
     n = len(data) // chunk
@@ -57,7 +57,7 @@ for name, data in sets.items():
     dig = torch.empty(n * 64, dtype=torch.uint8, device=dev)
 
     def run():
-        if what == "fused":
+        if what in ("fused", "fusedlzf"):
             eng.hash_compress_dev(cw.HASH_SKEIN512, comp, MODE, src.data_ptr(), chunk, n, dig.data_ptr(), blocks.data_ptr(),
                                   stride, lens.data_ptr(), s)
         else:
@@ -74,6 +74,6 @@ for name, data in sets.items():
     ms = e0.elapsed_time(e1) / 3
     lens_h = lens.cpu().numpy().astype(np.int64)
     ratio = float(np.where(lens_h == 0, chunk, lens_h).sum()) / (n * chunk)
-    print(f"{what:5s} chunk={chunk:5d} {name:38s} {n * chunk / 2**20:7.0f} MiB  {ms:8.3f} ms  {n * chunk / ms / 1e6:8.1f} GB/s  "
+    print(f"{what:8s} chunk={chunk:5d} {name:38s} {n * chunk / 2**20:7.0f} MiB  {ms:8.3f} ms  {n * chunk / ms / 1e6:8.1f} GB/s  "
           f"ratio {ratio:.4f}", flush=True)
 eng.close()

@@ -64,17 +64,17 @@ CW_HOSTDEV int cw_lz4f_hashlog(uint32_t chunk) { return chunk <= 8192u ? 12 : ch
 // 64 KiB 0.996 / 1.008 with 14 (tools/lzf_fast_model.c against lzf_compress)
 CW_HOSTDEV int cw_lzff_hashlog(uint32_t chunk) { return chunk <= 4096u ? 13 : 14; }
 
-// per-warp scratch in shared memory (312 bytes)
+// per-warp scratch in shared memory (344 bytes)
 struct CwLz4fScratch {
     union {
-        uint16_t pos[128];    // per position of the group.  First the continuation count CNT; then N | E << 8: the verified
-                              // position the parse chooses after this one's match and the end of that match, both relative to
-                              // the group (N: CW_LZ4F_* codes below).  An open match leaves its extended end (absolute) in the
-                              // entry of the neighbour x ^ 1 (minus 1), which lies inside the match and is never looked at
+        uint16_t pos[128];    // per position of the group.  First the continuation count CNT; then N | (E - x) << 8 [| ONCHAIN]:
+                              // the verified position the parse chooses after this one's match (relative to the group, or a
+                              // CW_LZ4F_* code below) and the length of that match
         uint32_t map[32][2];  // afterwards: {output offset of literal x, minus x; first literal | end of literals << 16}
     };
     uint32_t okw[6];  // OK masks of the four windows, two zero words behind them
-    uint8_t rec[32];  // the chosen matches of the group (their positions), in order
+    uint8_t rec[32];   // the matches the speculative walk chose (their positions), in order
+    uint8_t rec2[32];  // the matches chosen from the real entry until the two chains met
 };
 static_assert(sizeof(CwLz4fScratch) % 8 == 0, "the literal map is read with 64-bit loads");
 #define CW_LZ4F_LEAVE 128u  // N >= 128: nothing more to choose in this group
@@ -232,6 +232,47 @@ CW_DEV uint32_t cw_lz4f_scan(const uint32_t *okw, uint32_t rel)
     return 32u * j + cw_lz4f_ctz(m);
 }
 
+// The greedy walk over a group's entries, from verified position x (< 128): records the chosen positions in rec[cnt..] and
+// follows N until the chain leaves the group (returns 128) or -- STOP -- reaches a position that carries CW_LZ4F_ONCHAIN
+// (returns it, not recorded).  MARK: sets that flag on every position it chooses.  ip: end of the last chosen match.
+// The fast path is the inner loop: one load per chosen match; every lane reads the same entry and stores the same record
+// byte, so nothing in it is predicated on the lane.  An open match is extended by the whole warp; its end goes to the
+// lane whose index is the match's place in rec[] (extE).
+#define CW_LZ4F_ONCHAIN 0x8000u
+template <bool DIRECT, bool MARK, bool STOP, int SWN>
+CW_DEV uint32_t cw_lz4f_walk(CwLz4fScratch *scr, uint8_t *rec, uint32_t x, uint32_t &cnt, uint32_t &ip, uint32_t &extE,
+                             const uint32_t (&c)[CW_LZ4F_SW], const uint8_t *s, uint32_t sbase, uint32_t matchlimit, uint32_t nw,
+                             unsigned lane)
+{
+    for (;;) {
+        uint32_t t, xs;
+        do {
+            t = scr->pos[x];
+            if (STOP && (t & CW_LZ4F_ONCHAIN)) return x;
+            if (MARK && lane == 0u) scr->pos[x] = (uint16_t)(t | CW_LZ4F_ONCHAIN);
+            rec[cnt++] = (uint8_t)x;
+            xs = x;
+            x = t & 255u;
+        } while (x < 128u);
+        ip = sbase + xs + ((t >> 8) & 63u);
+        if (x < 254u) return 128u;  // nothing more to choose in this group
+        if (x == CW_LZ4F_OPEN) {    // the warp extends the match
+            uint32_t cnd = 0;
+#pragma unroll
+            for (int j = 0; j < SWN; j++) {
+                const uint32_t q = cw_shfl(c[j], xs & 31u);
+                if ((xs >> 5) == (uint32_t)j) cnd = q;
+            }
+            ip = cw_lz4f_extend<DIRECT>(s, ip, sbase + xs - cnd, matchlimit, nw, lane);
+            if (lane == cnt - 1u) extE = ip;
+        }
+        const uint32_t r2 = ip - sbase;
+        if (r2 >= 128u) return 128u;
+        x = cw_lz4f_scan(scr->okw, r2);
+        if (x >= 128u) return 128u;
+    }
+}
+
 // Compress chunk s[0..n) (n <= 65536) into out, as warp `rank` of a team of `nteam` warps that all call this function
 // with the same arguments.  s: 4-byte aligned; not DIRECT: CW_LZ4_PAD readable bytes behind the chunk.  table: zeroed
 // u16[1 << HASHLOG]; team: tokens initialised, ip = 1, op = 0, visible to every warp of the team before the first one
@@ -242,7 +283,9 @@ CW_HOSTDEV uint32_t cw_lz4f_groups(uint32_t n) { return n >= 13u ? (n - 12u) / (
 CW_HOSTDEV uint32_t cw_lzff_groups(uint32_t n) { return n >= 8u ? (n - 7u) / 96u + 1u : 0u; }
 // CODEC: CW_F_LZ4 or CW_F_LZF (the LZF flavour of the same parse: 3-byte keys, lzf.h block format, see the end of this file).
 // LZF: `cap` = the most the block may take (the reference's call passes chunk - 1); 0 is returned when it does not fit.
-template <int CODEC, int HASHLOG, bool DIRECT>
+// SPEC: walk ahead of the turn (phase 3b); cw_lz4f_spec() says where the kernels do
+CW_HOSTDEV constexpr bool cw_lz4f_spec(int codec, int hashlog, bool direct) { return direct || (codec == CW_F_LZF && hashlog >= 14); }
+template <int CODEC, int HASHLOG, bool DIRECT, bool SPEC = cw_lz4f_spec(CODEC, HASHLOG, DIRECT)>
 CW_DEV uint32_t cw_lz4f_team_chunk(const uint8_t *s, uint32_t n, uint16_t *table, CwLz4fTeam *team, CwLz4fScratch *scr,
                                    uint8_t *out, uint32_t rank, uint32_t nteam, uint32_t &seen, uint32_t cap = 0xffffffffu)
 {
@@ -369,49 +412,43 @@ CW_DEV uint32_t cw_lz4f_team_chunk(const uint8_t *s, uint32_t n, uint16_t *table
                     uint32_t N = t ? E + cw_lz4f_ctz(t) : CW_LZ4F_FAR;
                     if (E >= G) N = CW_LZ4F_LEAVE;
                     if (opn) N = CW_LZ4F_OPEN;
-                    ent[j] = N | (E << 8);  // N <= 255: E <= 135, and a verified position lies at most 31 behind it
+                    ent[j] = N | ((E - (32u * j + lane)) << 8);  // N <= 255; the match ends at most 39 positions behind its start
                 }
                 cw_syncwarp();  // every lane has read the counts
 #pragma unroll
                 for (int j = 0; j < SWN; j++) scr->pos[32 * j + lane] = (uint16_t)ent[j];
+                cw_syncwarp();  // the entries are in place
             }
-            // ---- phase 3b (ordered: after the walk of group g - 1): greedy walk over the group ----
+            // ---- phase 3b: the greedy walk.  Where it enters the group depends on the group before (ip), but chains that
+            //      enter a little apart meet after a match or two.  So the warp walks AHEAD of its turn, from the group's
+            //      first verified position, and marks what it chooses; when its turn comes it walks from the real entry only
+            //      until it steps on a marked position, and takes the rest of the speculative chain from there.  The
+            //      ordered section of a group is then a few instructions instead of one step per match ----
+            //      (SPEC; worth it where few chunks fit an SM and the chain of walks is what its teams wait for -- chunks read
+            //      in place, LZF's 32 KB tables: +30 % -- and not where the kernel is issue bound: -8 % at 8 KiB LZ4)
+            uint32_t ptot = 0, sp_end = 0, extE_sp = 0, specpos = 0;
+            if (SPEC && okany) {
+                const uint32_t x0 = cw_lz4f_scan(scr->okw, 0u);
+                cw_lz4f_walk<DIRECT, true, false, SWN>(scr, scr->rec, x0, ptot, sp_end, extE_sp, c, s, sbase, matchlimit, nw, lane);
+                cw_syncwarp();  // marks and records are in the scratch
+                specpos = lane < ptot ? scr->rec[lane] : 0xffffu;
+            }
+            // (ordered: after the walk of group g - 1)
             if (g) cw_lz4f_tok_wait(&team->tok_walk[rank], seen + 1u, lane);
             ip = cw_ld_vol(&team->ip);
-            cw_syncwarp();  // every lane has read it before lane 0 writes the new value (and the entries are in place)
+            cw_syncwarp();  // every lane has read it before lane 0 writes the new value
             anchor = ip == 1u ? 0u : ip;  // the parse stands at the end of the last match (nothing chosen yet: 1 / 0)
-            uint32_t tot = 0, x = 128u;
+            uint32_t tot = 0, k = 0, jm = 0, extE_new = 0;  // k: matches chosen before the chains met, jm: where they met
             if (okany) {
                 const uint32_t rel = ip > sbase ? ip - sbase : 0u;
-                if (rel < 128u) x = cw_lz4f_scan(scr->okw, rel);
-            }
-            if (x < 128u) {
-                // the fast path is the inner loop: one load per chosen match (every lane reads the same entry and stores the
-                // same record byte, so nothing in it is predicated on the lane)
-                for (;;) {
-                    uint32_t t;
-                    do {
-                        t = scr->pos[x];
-                        scr->rec[tot++] = (uint8_t)x;
-                        x = t & 255u;
-                    } while (x < 128u);
-                    ip = sbase + (t >> 8);
-                    if (x < 254u) break;  // nothing more to choose in this group
-                    if (x == CW_LZ4F_OPEN) {  // the warp extends the match
-                        const uint32_t xs = scr->rec[tot - 1u];
-                        uint32_t cnd = 0;
-#pragma unroll
-                        for (int j = 0; j < SWN; j++) {
-                            const uint32_t q = cw_shfl(c[j], xs & 31u);
-                            if ((xs >> 5) == (uint32_t)j) cnd = q;
-                        }
-                        ip = cw_lz4f_extend<DIRECT>(s, ip, sbase + xs - cnd, matchlimit, nw, lane);
-                        if (lane == 0u) scr->pos[xs ^ 1u] = (uint16_t)(ip - 1u);  // (an LZF match may end at 65536)
-                    }
-                    const uint32_t r2 = ip - sbase;
-                    if (r2 >= 128u) break;
-                    x = cw_lz4f_scan(scr->okw, r2);
-                    if (x >= 128u) break;
+                uint32_t x = rel < 128u ? cw_lz4f_scan(scr->okw, rel) : 128u;
+                if (x < 128u)
+                    x = cw_lz4f_walk<DIRECT, false, SPEC, SWN>(scr, scr->rec2, x, k, ip, extE_new, c, s, sbase, matchlimit, nw, lane);
+                tot = k;
+                if (x < 128u) {  // met the speculative chain at x: its place there, and the rest is known
+                    jm = cw_lz4f_ctz(cw_ballot(specpos == x));
+                    tot = k + ptot - jm;
+                    ip = sp_end;
                 }
             }
             if (lane == 0u) cw_st_vol(&team->ip, ip);
@@ -431,11 +468,16 @@ CW_DEV uint32_t cw_lz4f_team_chunk(const uint8_t *s, uint32_t n, uint16_t *table
             // one lane per chosen match, in position order
             const bool mine = lane < tot;
             uint32_t P = 0, E = 0, C = 0, xr = 0;
-            if (mine) {
-                xr = scr->rec[lane];
-                const uint32_t t = scr->pos[xr];
-                P = sbase + xr;
-                E = (t & 255u) == CW_LZ4F_OPEN ? (uint32_t)scr->pos[xr ^ 1u] + 1u : sbase + (t >> 8);
+            {
+                // lane i takes match i: one of the k chosen before the chains met, else number jm + i - k of the speculative chain
+                const uint32_t src = (jm + lane - k) & 31u;
+                const uint32_t xsp = SPEC ? cw_shfl(specpos, src) : 0u, esp = SPEC ? cw_shfl(extE_sp, src) : 0u;
+                if (mine) {
+                    xr = lane < k ? (uint32_t)scr->rec2[lane] : xsp;
+                    const uint32_t t = scr->pos[xr];
+                    P = sbase + xr;
+                    E = (t & 255u) == CW_LZ4F_OPEN ? (lane < k ? extE_new : esp) : P + ((t >> 8) & 63u);
+                }
             }
             uint32_t sel[CW_LZ4F_SW];  // the chosen positions of every window
 #pragma unroll

@@ -55,7 +55,10 @@ typedef enum { CW_COMP_LZ4 = 0, CW_COMP_LZF = 1 } cw_comp_alg;
 /* COMPAT: streams byte-identical to the reference's LZ4_compress_default (liblz4 1.8.2) /
  *         lzf_compress (liblzf, zeroed table).
  * FAST  : any valid stream that the reference decoders (LZ4_decompress_safe / lzf_decompress,
- *         experiment.cpp:118,256) restore bit-exactly, ratio within 1 % of the reference. */
+ *         experiment.cpp:118,256) restore bit-exactly, ratio within 1 % of the reference.  Both codecs run a
+ *         position-parallel parse by teams of warps (csrc/lz4_fast.cuh), 1.3-1.9 x (LZ4) / 5-6 x (LZF) the
+ *         compat kernels' pace; the output is a deterministic function of the chunk.  The LZF length
+ *         convention is unchanged: 0 = the block would not fit in chunk - 1 bytes, keep the chunk raw. */
 typedef enum { CW_MODE_COMPAT = 0, CW_MODE_FAST = 1 } cw_mode;
 
 #define CW_MAX_CHUNK 65536u /* LZ4's u16-table path covers inputs < 65547 bytes */

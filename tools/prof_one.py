@@ -38,7 +38,7 @@ dev = torch.device("cuda:0")
 st = torch.cuda.Stream(device=dev)
 torch.cuda.set_stream(st)
 s = st.cuda_stream
-comp = cw.COMP_LZF if what == "lzf" else cw.COMP_LZ4
+comp = cw.COMP_LZF if what in ("lzf", "fusedlzf") else cw.COMP_LZ4
 stride = cw.compress_bound(comp, chunk)
 n = len(data) // chunk
 src = torch.from_numpy(data).to(dev)
@@ -46,7 +46,7 @@ blocks = torch.empty(n * stride, dtype=torch.uint8, device=dev)
 lens = torch.empty(n, dtype=torch.int32, device=dev)
 dig = torch.empty(n * 64, dtype=torch.uint8, device=dev)
 for _ in range(2):
-    if what == "fused":
+    if what in ("fused", "fusedlzf"):
         eng.hash_compress_dev(cw.HASH_SKEIN512, comp, MODE, src.data_ptr(), chunk, n, dig.data_ptr(), blocks.data_ptr(), stride,
                               lens.data_ptr(), s)
     else:

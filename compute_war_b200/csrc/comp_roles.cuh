@@ -188,8 +188,13 @@ __device__ __forceinline__ void cw_lz4f_team_role(uint8_t *s, uint64_t *bar, uns
                 cw_lz4f_team_sync(bar_id, nteam);
             }
         }
+        // the block's address, made opaque: left to itself the compiler recomputes dst + g * stride (a 64-bit multiply-add and
+        // four constant loads) in front of every one of the kernel's byte stores instead of holding it in two registers
+        uint8_t *outp = dst + g * stride;
+        asm volatile("" : "+l"(outp));
+        __builtin_assume(__isGlobal(outp));  // (still a global address: STG, not generic stores)
         const uint32_t len =
-            cw_lz4f_team_chunk<CODEC, HASHLOG, DIRECT>(DIRECT ? src + g * chunk : s, chunk, table, team, scr, dst + g * stride, rank, nteam,
+            cw_lz4f_team_chunk<CODEC, HASHLOG, DIRECT>(DIRECT ? src + g * chunk : s, chunk, table, team, scr, outp, rank, nteam,
                                                        seen, CODEC == CW_F_LZF ? chunk - 1u : 0xffffffffu);
         if (len != CW_LZ4_NONE && lane == 0) lens[g] = len;
         cw_lz4f_team_sync(bar_id, nteam);  // every warp is done with the slot before it is refilled

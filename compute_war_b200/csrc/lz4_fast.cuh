@@ -145,12 +145,13 @@ CW_DEV void cw_lz4f_tok_wait(uint64_t *tok, uint32_t k, unsigned lane)
         "{\n"
         ".reg .pred p;\n"
         "CW_TW_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra CW_TD_%=;\n"
         "bra CW_TW_%=;\n"
         "CW_TD_%=:\n"
         "}\n" ::"r"(a),
-        "r"(parity)
+        "r"(parity), "r"(1000000u)  // suspend-time hint (ns): an upper bound, the arrival wakes the warp; without it the
+                                    // waiting warps of a team spend 5 % of the kernel's issue slots re-polling
         : "memory");
 }
 // everything this warp wrote before becomes visible to the warp that waits for this arrival; all lanes call
@@ -246,15 +247,50 @@ CW_DEV uint32_t cw_lz4f_walk(CwLz4fScratch *scr, uint8_t *rec, uint32_t x, uint3
 {
     for (;;) {
         uint32_t t, xs;
+#if defined(__CUDACC__)
+        if constexpr (!MARK && !STOP) {
+            // the loop below as the compiler will not write it: 7 instructions per chosen match instead of 10
+            uint32_t rps = (uint32_t)__cvta_generic_to_shared(rec) + cnt;
+            const uint32_t pb = (uint32_t)__cvta_generic_to_shared(scr->pos), rp0 = rps;
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                ".reg .u32 a;\n"
+                ".reg .u16 h;\n"
+                "CW_WK_%=:\n"
+                "mad.lo.u32 a, %1, 2, %4;\n"
+                "ld.shared.u16 h, [a];\n"
+                "st.shared.u8 [%2], %1;\n"
+                "add.u32 %2, %2, 1;\n"
+                "mov.u32 %3, %1;\n"
+                "cvt.u32.u16 %0, h;\n"
+                "and.b32 %1, %0, 255;\n"
+                "setp.lt.u32 p, %1, 128;\n"
+                "@p bra CW_WK_%=;\n"
+                "}\n"
+                : "=r"(t), "+r"(x), "+r"(rps), "=r"(xs)
+                : "r"(pb)
+                : "memory");
+            cnt += rps - rp0;
+            ip = sbase + xs + ((t >> 8) & 63u);
+        } else
+#endif
+        {
+        volatile uint8_t *rp = rec + cnt;
         do {
             t = scr->pos[x];
-            if (STOP && (t & CW_LZ4F_ONCHAIN)) return x;
+            if (STOP && (t & CW_LZ4F_ONCHAIN)) {
+                cnt = (uint32_t)(rp - rec);
+                return x;
+            }
             if (MARK && lane == 0u) scr->pos[x] = (uint16_t)(t | CW_LZ4F_ONCHAIN);
-            rec[cnt++] = (uint8_t)x;
-            xs = x;
+            *rp++ = (uint8_t)x;
             x = t & 255u;
         } while (x < 128u);
+        cnt = (uint32_t)(rp - rec);
+        xs = rp[-1];  // (read back instead of carried through the loop: fewer instructions per match)
         ip = sbase + xs + ((t >> 8) & 63u);
+        }
         if (x < 254u) return 128u;  // nothing more to choose in this group
         if (x == CW_LZ4F_OPEN) {    // the warp extends the match
             uint32_t cnd = 0;

@@ -207,6 +207,24 @@ def test_compress_edge_cases(eng, alg):
         n = len(c)
         blocks, lens = eng.do_compression(alg, c, n, cw.MODE_COMPAT)
         _check_blocks(alg, c, n, blocks, lens)
+    # the same inputs in fast mode: byte-equal to the restated fast parse, restored by the restated decoder and (grouped by
+    # size, one call each) by the reference's own decoder
+    by_size = {}
+    for c in cases:
+        n = len(c)
+        blocks, lens = eng.do_compression(alg, c, n, cw.MODE_FAST)
+        fb, fl = O.lz4_fast_chunks(c, n) if alg == O.COMP_LZ4 else O.lzf_fast_chunks(c, n)
+        assert int(lens[0]) == int(fl[0]) and (blocks[0, : fl[0]] == fb[0, : fl[0]]).all(), (alg, n)
+        assert O.verify_roundtrip(alg, c, n, blocks, lens) == 0, (alg, n)
+        if lens[0] == 0:  # LZF: kept raw
+            blocks[0, :n] = c
+        by_size.setdefault(n, []).append((c, blocks[0].copy(), int(lens[0])))
+    if O.have_ref_cli():
+        for n, items in by_size.items():
+            if n < 16 and alg == O.COMP_LZF:
+                continue  # (all raw)
+            back = O.ref_decompress_chunks(alg, n, np.stack([b for _, b, _ in items]), np.array([l for _, _, l in items], np.uint32))
+            assert (back == np.concatenate([c for c, _, _ in items])).all(), (alg, n)
 
 
 @pytest.mark.parametrize("alg", [O.COMP_LZ4, O.COMP_LZF])

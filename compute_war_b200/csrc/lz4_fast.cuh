@@ -676,10 +676,10 @@ CW_DEV uint32_t cw_lz4f_team_chunk(const uint8_t *s, uint32_t n, uint16_t *table
                 for (int j = 0; j < SWN; j++) {
                     const uint32_t x = sbase + 32u * j + lane;
                     const uint32_t idx = cum + (uint32_t)cw_popc(sel[j] & lt);
-                    if (idx < tot) {
-                        const uint32_t m0 = scr->map[idx][0], m1 = scr->map[idx][1];
-                        if (x >= (m1 & 0xffffu) && x < (m1 >> 16)) out[m0 + x] = (uint8_t)v[j];
-                    }
+                    // (one predicate, one predicated store: entries at or beyond tot are stale but lie inside the map)
+                    const uint32_t m0 = scr->map[idx & 31u][0], m1 = scr->map[idx & 31u][1];
+                    const uint32_t a0 = m1 & 0xffffu;
+                    if (idx < tot && x - a0 < (m1 >> 16) - a0) out[m0 + x] = (uint8_t)v[j];
                     cum += (uint32_t)cw_popc(sel[j]);
                 }
                 cw_syncwarp();  // the map is read before the next group's counts overwrite the scratch

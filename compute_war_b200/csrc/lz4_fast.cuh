@@ -122,7 +122,7 @@ CW_DEV uint32_t cw_lz4f_extend(const uint8_t *s, uint32_t e, uint32_t d, uint32_
 // suspended by the hardware instead of polling shared memory -- a polling team mate takes the issue slots the working
 // warp needs) and a plain counter on the warp emulator.  The kernels initialise them once; every warp keeps the number
 // of arrivals it has consumed (`seen`, the same for its three tokens).
-#define CW_LZ4F_MAX_TEAM 6
+#define CW_LZ4F_MAX_TEAM 8
 struct CwLz4fTeam {
     uint64_t tok_table[CW_LZ4F_MAX_TEAM];  // the table inserts of the group before are done
     uint64_t tok_walk[CW_LZ4F_MAX_TEAM];   // its greedy walk is done; ip = where the parse stands

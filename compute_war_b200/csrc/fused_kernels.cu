@@ -38,6 +38,10 @@
 #define CW_FUSED_FAST_COMP_WARPS 26  // 30 (1024 threads, 64 registers) measured 10 % slower at 8 KiB: the hash rounds want the registers
 #endif
 #define CW_FUSED_FAST_THREADS ((CW_FUSED_HASH_WARPS_MAX + CW_FUSED_FAST_COMP_WARPS) * 32)
+#ifndef CW_FUSED_FAST_COMP_WARPS_FEW_SLOTS
+#define CW_FUSED_FAST_COMP_WARPS_FEW_SLOTS 26  // variants with 5-6 slots per SM (32 KB tables); 30 measured +5-9 % on text, -6-8 % on the mix
+                                              // (its random chunks are hash bound, and the hash rounds want the registers): profiles/r02_ab_fused_few_slots_30_vs_26_warps.txt
+#endif
 
 // measured on the synthetic mix (profiles/r01_tune_emitters_hashwarps.txt): the 9-parser compat kernel is best
 // with 1 hash warp + 3 emitters, the 13-parser fast kernel with 2 + 2
@@ -66,6 +70,13 @@ __host__ __device__ constexpr int cw_c_codec(int c) { return c >= CW_C_LZF_FAST1
 __host__ __device__ constexpr int cw_c_hashlog(int c)
 {
     return c == CW_C_LZ4_FAST ? 12 : (c == CW_C_LZ4_FAST_DIRECT || c == CW_C_LZF_FAST14 || c == CW_C_LZF_FAST_DIRECT) ? 14 : 13;
+}
+
+// compress warps of a fast-mode fused CTA: the kernels whose teams wait on each other take the 1024-thread shape
+__host__ __device__ constexpr int cw_c_fast_warps(int c)
+{
+    return (c == CW_C_LZ4_FAST_DIRECT || c == CW_C_LZF_FAST14 || c == CW_C_LZF_FAST_DIRECT) ? CW_FUSED_FAST_COMP_WARPS_FEW_SLOTS
+                                                                                            : CW_FUSED_FAST_COMP_WARPS;
 }
 
 #define CW_FUSED_EMITTERS_DEFAULT 3  // emitter warps per CTA
@@ -115,7 +126,7 @@ static bool parse_role_env(int *hs, int *es)
 
 // logical warps [0, parsers): parsers; [parsers, parsers + emitters): emitters; the rest: hash
 template <int HALG, int CALG, bool ALIGNED>
-__global__ void __launch_bounds__(cw_c_fast(CALG) ? CW_FUSED_FAST_THREADS : CW_FUSED_MAX_THREADS, 1)
+__global__ void __launch_bounds__(cw_c_fast(CALG) ? (CW_FUSED_HASH_WARPS_MAX + cw_c_fast_warps(CALG)) * 32 : CW_FUSED_MAX_THREADS, 1)
     cw_fused_kernel(const __grid_constant__ CwSkeinIV iv, const uint8_t *__restrict__ src, uint32_t chunk, uint64_t n_chunks,
                     uint8_t *__restrict__ digests, uint8_t *__restrict__ dst, uint64_t stride, uint32_t *__restrict__ lens,
                     unsigned long long *work, uint32_t slot_bytes, uint32_t parsers, uint32_t emitters,
@@ -213,7 +224,7 @@ static cudaError_t launch_one(const CwDeviceInfo &dev, int max_dyn_smem, const C
         for (int it = 0; it < 2; it++) {
             const int slots = max_dyn_smem / (int)fslot;
             if (slots < 1) return cudaErrorInvalidValue;
-            cw_lz4f_shape(slots, CW_FUSED_FAST_COMP_WARPS, &teams, &warps);
+            cw_lz4f_shape(slots, cw_c_fast_warps(CALG), &teams, &warps);
             fslot = cw_slot_bytes<CALG>(chunk, (uint32_t)((warps + teams - 1) / teams));
         }
         uint64_t fctas = (n + (uint64_t)teams - 1) / (uint64_t)teams;

@@ -29,7 +29,9 @@
 #ifndef CW_FUSED_TAIL_HELP
 #define CW_FUSED_TAIL_HELP 1  // warps without compress work left join the hash role
 #endif
+#ifndef CW_FUSED_HASH_WARPS_MAX
 #define CW_FUSED_HASH_WARPS_MAX 2  // also sizes __launch_bounds__: 19 warps leave ptxas 96 registers and no spills
+#endif
 #define CW_FUSED_MAX_COMP_WARPS 14
 #define CW_FUSED_MAX_THREADS ((CW_FUSED_HASH_WARPS_MAX + CW_FUSED_MAX_COMP_WARPS + 3) * 32)  // + emitters
 // fast mode: teams of warps per chunk (lz4_fast.cuh), no emitters: 26 compress warps + 2 hash warps = 896 threads, which

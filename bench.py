@@ -731,6 +731,20 @@ def main():
                     raise SystemExit("bench.py: digests / compressed size of the GPU pass differ from the reference run")
             s1, _, _ = run_cpu_reference(min(ncpu, 8192), 1, 2)
             line["cpu_baseline"]["one_thread"] = {"value": min(ncpu, 8192) * CHUNK / min(s1) / 1e9, "unit": "GB/s", "cores": 1}
+            # for honesty: the same job with the reference's own prebuilt, unoptimised libskein.a
+            shipped = os.path.join(ROOT, "oracle", "_ref", "ref_cli_shipped")
+            if os.access(shipped, os.X_OK):
+                try:
+                    thr = line["cpu_baseline"]["cores"]
+                    ns = min(ncpu, 32768)
+                    out = subprocess.check_output([shipped, "bench", "skein512", "lz4", str(CHUNK), str(ns), str(thr), "0", hex(SEED), "2"],
+                                                  text=True, timeout=300)
+                    recs = [json.loads(l) for l in out.strip().splitlines() if l.startswith("{")]
+                    line["cpu_baseline"]["as_shipped_libskein"] = {
+                        "value": ns * CHUNK / min(r["seconds"] for r in recs) / 1e9, "unit": "GB/s", "cores": thr,
+                        "what": "same driver linked against src/hashing_perf/skein/libskein.a as the reference ships it"}
+                except Exception as ex:  # never fail the bench line over the side figure
+                    line["cpu_baseline"]["as_shipped_libskein"] = {"error": str(ex)[:200]}
         print(json.dumps(line), flush=True)
     eng.close()
     if dist is not None:

@@ -1,7 +1,10 @@
 // lzf_fast_model.c -- development tool: what an LZF "fast mode" built like the LZ4 one (window-parallel parse, all positions
-// inserted, 3-byte keys, greedy, exact extension) would cost in LZF format against the restated reference lzf_compress.
-// Result: 12-bit table +1.5 % / worst file +2.5 % at 8 KiB, 13-bit +0.6 % / +1.2 %: outside the 1 % bound,
-// so LZF keeps its exact parse in fast mode.  gcc -O2 tools/lzf_fast_model.c -Ioracle -Loracle -loracle -Wl,-rpath,$PWD/oracle
+// inserted, 3-byte keys, greedy, exact extension) costs in LZF format against the restated reference lzf_compress.
+// Result: the table size decides -- 8 KiB chunks: 12 bits +1.5 % / worst file +2.5 %, 13 bits +0.6 % / +1.2 %,
+// 14 bits +0.2 % / +0.5 %; 4 KiB: 13 bits +0.3 % / +0.7 %; 64 KiB: 14 bits -0.4 % / +0.8 % -- so the kernels run 13 bits up to
+// 4 KiB and 14 above (cw_lzff_hashlog).  A cap of 32 matches per 128 positions (one lane per match) costs another 0.5-1.4 %,
+// which is why an LZF group has three windows.
+// gcc -O2 tools/lzf_fast_model.c -Ioracle -Loracle -loracle -Wl,-rpath,$PWD/oracle ; a.out <chunk> <bits> <per> <back> files...
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>

@@ -56,7 +56,7 @@ typedef enum { CW_COMP_LZ4 = 0, CW_COMP_LZF = 1 } cw_comp_alg;
  *         lzf_compress (liblzf, zeroed table).
  * FAST  : any valid stream that the reference decoders (LZ4_decompress_safe / lzf_decompress,
  *         experiment.cpp:118,256) restore bit-exactly, ratio within 1 % of the reference.  Both codecs run a
- *         position-parallel parse by teams of warps (csrc/lz4_fast.cuh), 1.3-1.9 x (LZ4) / 5-6 x (LZF) the
+ *         position-parallel parse by teams of warps (csrc/lz4_fast.cuh), 1.9-3.7 x (LZ4) / 5-7 x (LZF) the
  *         compat kernels' pace; the output is a deterministic function of the chunk.  The LZF length
  *         convention is unchanged: 0 = the block would not fit in chunk - 1 bytes, keep the chunk raw. */
 typedef enum { CW_MODE_COMPAT = 0, CW_MODE_FAST = 1 } cw_mode;

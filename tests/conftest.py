@@ -40,4 +40,6 @@ def golden():
     with open(os.path.join(here, "ref_outputs.json")) as f:
         ref = json.load(f)
     blob = np.fromfile(os.path.join(here, "corpus_sample.bin"), np.uint8)
-    return {"kat": kat, "ref": ref, "blob": blob}
+    with open(os.path.join(here, "fast_mode_outputs.json")) as f:
+        fast = json.load(f)  # the engine's own fast-mode parses, pinned (make_fast_mode_golden.py)
+    return {"kat": kat, "ref": ref, "blob": blob, "fast": fast}

@@ -269,6 +269,11 @@ def test_fast_mode_roundtrips_and_ratio(eng, golden, alg):
             mine = sum(int(x) if x else chunk for x in lens)
             theirs = sum(int(x) if x else chunk for x in rec[O.COMP_NAMES[alg] + "_lens"])
             assert mine <= theirs * 1.01, (ent["name"], chunk, mine, theirs)
+            # ... and equal to the pinned fast-mode outputs (tests/golden/fast_mode_outputs.json)
+            pin = golden["fast"]["corpus"][ent["name"]][str(chunk)]
+            name = O.COMP_NAMES[alg]
+            assert [int(x) for x in lens] == pin[name + "_lens"], (ent["name"], chunk)
+            assert [_sha(blocks[i, : lens[i]]) for i in range(len(lens))] == pin[name + "_sha256"], (ent["name"], chunk)
 
 
 # ------------------------------------------------------------------------------------------------

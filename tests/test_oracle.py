@@ -180,3 +180,17 @@ def test_dedup_definition():
     d = np.array([[1, 2], [3, 4], [1, 2], [0, 0], [3, 4], [1, 2]], dtype=np.uint8)
     first, uniq = O.dedup_first(d)
     assert first.tolist() == [0, 1, 0, 3, 1, 0] and uniq == 3
+
+
+def test_fast_mode_restatement_matches_pinned_outputs(golden):
+    """the restated fast parses (LZ4 and LZF) still produce the blocks recorded in tests/golden/fast_mode_outputs.json"""
+    import hashlib
+    ref, blob, fast = golden["ref"], golden["blob"], golden["fast"]
+    for ent in ref["files"]:
+        d = blob[ent["offset"]: ent["offset"] + ent["size"]]
+        for chunk, rec in fast["corpus"][ent["name"]].items():
+            chunk = int(chunk)
+            for name, fn in (("lz4", O.lz4_fast_chunks), ("lzf", O.lzf_fast_chunks)):
+                blocks, lens = fn(d, chunk)
+                assert [int(x) for x in lens] == rec[name + "_lens"], (ent["name"], chunk, name)
+                assert [hashlib.sha256(blocks[i, : lens[i]].tobytes()).hexdigest()[:32] for i in range(rec["n"])] == rec[name + "_sha256"]

@@ -25,6 +25,10 @@
 // bytes that must stay in L2 between the compress warps' bulk copy and the last hash read are
 // hash_warps * 32 lanes * chunk * 148 SMs; 1 warp keeps that window at 39 MB for 8 KB chunks (L2: 126 MB)
 // while still hashing faster than the compressors consume (measured, profiles/).
+#ifndef CW_FUSED_COMPACT_ALWAYS
+#define CW_FUSED_COMPACT_ALWAYS false  // A/B knob: the single-call-site Skein loop in the compat kernels too (measured: 72.4 -> 73.0 GB/s
+                                       // at 2 GiB, hash-bound data -1 %: left off)
+#endif
 #define CW_FUSED_HASH_WARPS_DEFAULT 1
 #ifndef CW_FUSED_TAIL_HELP
 #define CW_FUSED_TAIL_HELP 1  // warps without compress work left join the hash role
@@ -192,7 +196,7 @@ __global__ void __launch_bounds__(cw_c_fast(CALG) ? (CW_FUSED_HASH_WARPS_MAX + c
         }
         __syncwarp();
         const unsigned long long idx = first + lane;
-        if (idx < n_chunks) cw_hash_one<HALG, ALIGNED, ALIGNED, !cw_c_fast(CALG), cw_c_fast(CALG)>(iv, src + idx * chunk, chunk, digests + idx * D);
+        if (idx < n_chunks) cw_hash_one<HALG, ALIGNED, ALIGNED, !cw_c_fast(CALG) && !CW_FUSED_COMPACT_ALWAYS, cw_c_fast(CALG) || CW_FUSED_COMPACT_ALWAYS>(iv, src + idx * chunk, chunk, digests + idx * D);
     }
 }
 

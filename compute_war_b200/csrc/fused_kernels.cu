@@ -319,7 +319,12 @@ cudaError_t cw_launch_fused(const CwDeviceInfo &dev, int halg, int calg, bool fa
     if (n == 0) return cudaSuccess;
     const bool aligned = (chunk % 16u == 0) && ((reinterpret_cast<uintptr_t>(d_src) & 15u) == 0) &&
                          ((reinterpret_cast<uintptr_t>(d_digests) & 15u) == 0);
-    if (calg == CW_C_LZ4 && chunk > 16384u) {
+    // tuning knob (compat only): smaller chunks read in place too, like CW_LZ4_COMPAT_DIRECT_ABOVE of the stand-alone kernel
+    static const uint32_t compat_direct_above = [] {
+        const char *e = getenv("CW_LZ4_COMPAT_DIRECT_ABOVE");
+        return e ? (uint32_t)atoi(e) : 16384u;
+    }();
+    if (calg == CW_C_LZ4 && chunk > (fast ? 16384u : compat_direct_above)) {
         // big chunks (the 64 KiB blocks of BASELINE configs[2]) are not staged: parsers, emitters and hash warps all read
         // the chunk where it lies, which keeps 13 (fast: 6) chunks per SM in flight instead of 2, in ONE launch
         if (aligned) calg = fast ? CW_C_LZ4_FAST_DIRECT : CW_C_LZ4_DIRECT;

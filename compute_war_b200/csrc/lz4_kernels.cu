@@ -163,7 +163,13 @@ cudaError_t cw_launch_lz4(const CwDeviceInfo &dev, bool fast, const uint8_t *d_s
         return cudaGetLastError();
     }
     const int hashlog = 13;  // compat: the reference's 13-bit table
-    const uint32_t slot = (direct ? 0u : cw_lz4_chunk_pad(chunk)) + (2u << hashlog);
+    // tuning knob: smaller chunks read in place too (a slot is then only the table: more parsers per SM, bytes from L1 / L2)
+    static const uint32_t direct_above = [] {
+        const char *e = getenv("CW_LZ4_COMPAT_DIRECT_ABOVE");
+        return e ? (uint32_t)atoi(e) : CW_LZ4_DIRECT_ABOVE;
+    }();
+    const bool directc = aligned && chunk > direct_above;
+    const uint32_t slot = (directc ? 0u : cw_lz4_chunk_pad(chunk)) + (2u << hashlog);
     // a ring of 32 records instead of 64 where that buys another parser (4 KiB chunks: 11 instead of 10)
     uint32_t qlen = CW_LZ4_QLEN;
     if (g_lz4_max_smem / (int)(slot + cw_lz4_queue_bytes(32u)) > g_lz4_max_smem / (int)(slot + cw_lz4_queue_bytes(CW_LZ4_QLEN))) qlen = 32u;
@@ -191,7 +197,7 @@ cudaError_t cw_launch_lz4(const CwDeviceInfo &dev, bool fast, const uint8_t *d_s
     const CwRoleMap roles = make_role_map(parsers, emitters, 0, grouped ? none : nullptr, grouped ? es : nullptr);
 #define CW_GO(HL, AL, DI) \
     cw_lz4_kernel<HL, AL, DI><<<grid, block, dyn, st>>>(d_src, chunk, n, d_dst, stride, d_lens, work, slot, (uint32_t)parsers, (uint32_t)emitters, roles, qlen)
-    if (direct) CW_GO(13, true, true);
+    if (directc) CW_GO(13, true, true);
     else if (aligned) CW_GO(13, true, false);
     else CW_GO(13, false, false);
 #undef CW_GO

@@ -4,6 +4,7 @@
 // Reference interfaces replaced (see compute_war.h for the per-function list): initializeGpu()
 // HashAndCompress.cpp:95-98, doHashing :119-134, doCompression :111,342-355, ProcessBlock :231-261,
 // HashOffload HashOffload.h:15-64 + hashing_offload_entry_point HashAndCompress.cpp:160-183.
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -84,6 +85,7 @@ struct BatchBuf {
     size_t chunks = 0;   // chunks reserved so far
     int copying_in = 0;  // callers still copying their input in
     int readers = 0;     // callers that still have to copy their results out
+    int tasks_left = 0;  // pieces of the submitted jobs' copy-out still with the helper threads (CopyPool::mu)
     int rc = 0;
     uint64_t gen = 0;
 };
@@ -96,6 +98,22 @@ struct Batcher {
     std::thread th;
     bool started = false, stop = false, failed_alloc = false;
     std::deque<int> inflight;  // worker-private: launched, not yet complete
+};
+
+// copy-out helpers of the offload thread: a finished batch carries the results of dozens to hundreds of cw_submit jobs,
+// and one thread copying them into the callers' (pageable) buffers block by block was what the whole front-end waited for
+// (HashOffload style, 32 KiB items: 4.8 GB/s).  The offload thread cuts a batch's jobs into pieces, the helpers copy and
+// complete them, the last piece frees the batch buffer.
+struct CopyTask {
+    int buf;
+    size_t lo, hi;  // jobs [lo, hi) of the buffer
+};
+struct CopyPool {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<CopyTask> tasks;
+    std::vector<std::thread> th;
+    bool stop = false;
 };
 
 
@@ -136,6 +154,7 @@ struct cw_ctx {
     cw_ticket next_ticket = 1;
     bool stop = false;
     Batcher bat;
+    CopyPool pool;
     std::atomic<uint64_t> batches{0}, batched_calls{0};
 };
 
@@ -689,16 +708,82 @@ bool batch_submit(cw_ctx *ctx, const Job &j)
     return true;
 }
 
+// jobs [lo, hi) of a finished batch: results to the callers' buffers, then ONE pass over the ticket maps and one wake-up
+// for all of them (a notify per 32 KiB job kept 14 waiting threads busy with the mutex), then the callbacks
+void finish_job_range(cw_ctx *ctx, BatchBuf &b, size_t lo, size_t hi)
+{
+    if (b.rc == CW_OK)
+        for (size_t k = lo; k < hi; k++) {
+            const Job &j = b.jobs[k].first;
+            batch_copy_out(b, b.jobs[k].second, j.n, j.digests, j.dst, j.stride, j.lens);
+        }
+    {
+        std::lock_guard<std::mutex> lk(ctx->q_mu);
+        for (size_t k = lo; k < hi; k++) {
+            const Job &j = b.jobs[k].first;
+            if (!j.cb) ctx->finished[j.ticket] = b.rc;
+            ctx->pending.erase(j.ticket);
+        }
+    }
+    ctx->done_cv.notify_all();
+    for (size_t k = lo; k < hi; k++) {
+        const Job &j = b.jobs[k].first;
+        if (j.cb) j.cb(j.ticket, b.rc, j.user);
+    }
+}
+
+void copy_helper(cw_ctx *ctx)
+{
+    CopyPool &P = ctx->pool;
+    for (;;) {
+        CopyTask t;
+        {
+            std::unique_lock<std::mutex> lk(P.mu);
+            P.cv.wait(lk, [&] { return P.stop || !P.tasks.empty(); });
+            if (P.tasks.empty()) return;  // stop requested and nothing left
+            t = P.tasks.front();
+            P.tasks.pop_front();
+        }
+        BatchBuf &b = ctx->bat.bufs[t.buf];
+        finish_job_range(ctx, b, t.lo, t.hi);
+        bool last;
+        {
+            std::lock_guard<std::mutex> lk(P.mu);
+            last = --b.tasks_left == 0;
+        }
+        if (last) {
+            ctx->batched_calls += b.jobs.size();
+            batch_release(ctx, &b);
+        }
+    }
+}
+
 // offload thread: a batch that carries submitted jobs is complete
 void finish_batch_jobs(cw_ctx *ctx, int i)
 {
     BatchBuf &b = ctx->bat.bufs[i];
-    for (auto &jf : b.jobs) {
-        if (b.rc == CW_OK) batch_copy_out(b, jf.second, jf.first.n, jf.first.digests, jf.first.dst, jf.first.stride, jf.first.lens);
-        complete_job(ctx, jf.first, b.rc);
+    static const int n_helpers = [] {
+        const char *e = getenv("CW_COPY_THREADS");  // 0: the offload thread copies everything itself
+        int v = e ? atoi(e) : (int)std::thread::hardware_concurrency() / 2;
+        return v < 0 ? 0 : (v > 8 ? 8 : v);
+    }();
+    const size_t nj = b.jobs.size();
+    if (n_helpers < 2 || nj < 8) {
+        finish_job_range(ctx, b, 0, nj);
+        ctx->batched_calls += nj;
+        batch_release(ctx, &b);
+        return;
     }
-    ctx->batched_calls += b.jobs.size();
-    batch_release(ctx, &b);
+    CopyPool &P = ctx->pool;
+    const size_t pieces = std::min<size_t>(nj / 4, (size_t)n_helpers * 2);
+    {
+        std::lock_guard<std::mutex> lk(P.mu);
+        if (P.th.empty())
+            for (int t = 0; t < n_helpers; t++) P.th.emplace_back(copy_helper, ctx);
+        b.tasks_left = (int)pieces;
+        for (size_t k = 0; k < pieces; k++) P.tasks.push_back(CopyTask{i, nj * k / pieces, nj * (k + 1) / pieces});
+    }
+    P.cv.notify_all();
 }
 
 void worker_loop(cw_ctx *ctx)
@@ -796,6 +881,14 @@ void cw_shutdown(cw_ctx *ctx)
         }
         ctx->q_cv.notify_all();
         ctx->worker.join();
+    }
+    if (!ctx->pool.th.empty()) {  // (the offload thread is gone: nobody adds tasks any more)
+        {
+            std::lock_guard<std::mutex> lk(ctx->pool.mu);
+            ctx->pool.stop = true;
+        }
+        ctx->pool.cv.notify_all();
+        for (auto &t : ctx->pool.th) t.join();
     }
     if (ctx->bat.started) {
         {

@@ -12,6 +12,8 @@
 #include <cstring>
 #include <condition_variable>
 #include <deque>
+#include <functional>
+#include <memory>
 #include <map>
 #include <mutex>
 #include <string>
@@ -27,6 +29,7 @@ namespace {
 constexpr int kSlots = 4;                     // pipeline slots: H2D / kernel / D2H of different slices in flight
 constexpr size_t kSliceBytesDefault = 64u << 20;  // input bytes per pipeline slice (CW_SLICE_MB overrides); 64 MiB x 4 slots measured best
 constexpr int kWorkRing = 256;
+constexpr size_t kStageSliceBytes = 16u << 20;  // slice size for callers with pageable memory (staged through pinned buffers)
 
 struct Slot {
     cudaStream_t st = nullptr;
@@ -43,6 +46,12 @@ struct Slot {
     cudaEvent_t ready = nullptr;  // kernels of the slice done, h_total valid
     size_t lo = 0, cnt = 0;       // chunks of the slice
     unsigned long long base = 0;  // where the slice starts in the caller's packed buffer
+    // pinned staging buffers for callers with pageable memory (host_pass): the slice's input on its way in, its results
+    // on their way out
+    uint8_t *h_in = nullptr, *h_out = nullptr, *h_dig = nullptr;
+    uint32_t *h_lens = nullptr;
+    size_t cap_h_in = 0, cap_h_out = 0, cap_h_dig = 0, cap_h_lens = 0;
+    bool staged_out = false;  // the slice's results still sit in the staging buffers
 };
 
 struct Job {
@@ -65,7 +74,7 @@ struct Job {
 // copy in / one launch / one set of copies out serves them all. ----
 constexpr size_t kBatchBytes = 16u << 20;  // input bytes per batch buffer
 constexpr int kBatchBufs = 3;
-constexpr size_t kSmallCall = 4u << 20;    // host-buffer calls up to this many input bytes go through the batcher
+constexpr size_t kSmallCall = 8u << 20;    // host-buffer calls up to this many input bytes go through the batcher
 constexpr size_t kBatchMinChunk = 512;     // smaller chunks: direct path (digest / length arrays would dominate)
 
 struct BatchBuf {
@@ -103,15 +112,12 @@ struct Batcher {
 // copy-out helpers of the offload thread: a finished batch carries the results of dozens to hundreds of cw_submit jobs,
 // and one thread copying them into the callers' (pageable) buffers block by block was what the whole front-end waited for
 // (HashOffload style, 32 KiB items: 4.8 GB/s).  The offload thread cuts a batch's jobs into pieces, the helpers copy and
-// complete them, the last piece frees the batch buffer.
-struct CopyTask {
-    int buf;
-    size_t lo, hi;  // jobs [lo, hi) of the buffer
-};
+// complete them, the last piece frees the batch buffer.  The same threads stage the slices of callers with pageable
+// memory into and out of pinned buffers (host_pass).
 struct CopyPool {
     std::mutex mu;
     std::condition_variable cv;
-    std::deque<CopyTask> tasks;
+    std::deque<std::function<void()>> tasks;
     std::vector<std::thread> th;
     bool stop = false;
 };
@@ -305,8 +311,126 @@ int ensure(cw_ctx *ctx, void **p, size_t *cap, size_t need)
     return CW_OK;
 }
 
-// Pipelined host-buffer pass: slices of ~32 MiB rotate through three slots, each with its own stream, so
+// ---------------- copy helpers ----------------
+int pool_threads()
+{
+    static const int n = [] {
+        const char *e = getenv("CW_COPY_THREADS");  // 0: no helpers (the calling / offload thread copies everything itself)
+        int v = e ? atoi(e) : (int)std::thread::hardware_concurrency() / 2;
+        return v < 0 ? 0 : (v > 8 ? 8 : v);
+    }();
+    return n;
+}
+
+void copy_helper(cw_ctx *ctx)
+{
+    CopyPool &P = ctx->pool;
+    for (;;) {
+        std::function<void()> t;
+        {
+            std::unique_lock<std::mutex> lk(P.mu);
+            P.cv.wait(lk, [&] { return P.stop || !P.tasks.empty(); });
+            if (P.tasks.empty()) return;  // stop requested and nothing left
+            t = std::move(P.tasks.front());
+            P.tasks.pop_front();
+        }
+        t();
+    }
+}
+
+// P.mu held
+void pool_start(cw_ctx *ctx)
+{
+    CopyPool &P = ctx->pool;
+    if (P.th.empty())
+        for (int t = 0; t < pool_threads(); t++) P.th.emplace_back(copy_helper, ctx);
+}
+
+// fn(k) for every k in [0, pieces), on the helpers and the calling thread; returns when all pieces are done
+void pool_for(cw_ctx *ctx, size_t pieces, const std::function<void(size_t)> &fn)
+{
+    if (pool_threads() < 2 || pieces < 2) {
+        for (size_t k = 0; k < pieces; k++) fn(k);
+        return;
+    }
+    // shared state: a helper that gets to its task late (everything already done, the caller gone) finds no piece left
+    // and touches nothing of the caller's
+    struct State {
+        std::atomic<size_t> next{0};
+        size_t pieces = 0, left = 0;
+        std::mutex m;
+        std::condition_variable c;
+        const std::function<void(size_t)> *fn = nullptr;
+    };
+    auto st = std::make_shared<State>();
+    st->pieces = st->left = pieces;
+    st->fn = &fn;
+    auto body = [st] {
+        for (;;) {
+            const size_t k = st->next.fetch_add(1);
+            if (k >= st->pieces) return;
+            (*st->fn)(k);
+            std::lock_guard<std::mutex> lk(st->m);
+            if (--st->left == 0) st->c.notify_all();
+        }
+    };
+    CopyPool &P = ctx->pool;
+    const size_t helpers = std::min<size_t>(pieces - 1, (size_t)pool_threads());
+    {
+        std::lock_guard<std::mutex> lk(P.mu);
+        pool_start(ctx);
+        for (size_t h = 0; h < helpers; h++) P.tasks.emplace_back(body);
+    }
+    P.cv.notify_all();
+    body();
+    std::unique_lock<std::mutex> lk(st->m);
+    st->c.wait(lk, [&] { return st->left == 0; });
+}
+
+void pool_memcpy(cw_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    constexpr size_t kPiece = 2u << 20;
+    const size_t pieces = (bytes + kPiece - 1) / kPiece;
+    pool_for(ctx, pieces, [&](size_t k) {
+        const size_t lo = k * kPiece, len = std::min(kPiece, bytes - lo);
+        memcpy((uint8_t *)dst + lo, (const uint8_t *)src + lo, len);
+    });
+}
+
+int ensure_host(cw_ctx *ctx, void **p, size_t *cap, size_t need)
+{
+    if (*cap >= need) return CW_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+    *cap = 0;
+    cudaError_t e = cudaHostAlloc(p, need, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        fail(ctx, e, "cudaHostAlloc(staging buffer)");
+        return CW_ERR_NOMEM;
+    }
+    *cap = need;
+    return CW_OK;
+}
+
+// true for ordinary (pageable) host memory: not page-locked by cudaHostAlloc / cw_host_register
+bool is_pageable(const void *p)
+{
+    static const bool off = getenv("CW_NO_STAGING") != nullptr;  // A/B knob: leave pageable buffers to the driver
+    if (off || !p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+// Pipelined host-buffer pass: slices of 64 MiB rotate through four slots, each with its own stream, so
 // the H2D copy of slice k+1, the kernels of slice k and the D2H copy of slice k-1 overlap.
+// Callers with PAGEABLE buffers (the reference's tools read their files into ordinary memory): the driver stages such
+// copies itself, synchronously and on one thread (6 GB/s for a whole-file call on the 16-thread box).  Instead, slices of
+// 16 MiB are staged through pinned buffers of the slot by the copy helpers -- input before the slice's copy-in,
+// results (only the bytes that exist) when the slot comes round again -- while the GPU works on the slices in between.
 int host_pass(cw_ctx *ctx, bool want_hash, bool want_comp, cw_hash_alg halg, cw_comp_alg calg, cw_mode mode,
               const void *src, size_t chunk, size_t n, void *digests, void *dst, size_t stride, uint32_t *lens)
 {
@@ -323,24 +447,65 @@ int host_pass(cw_ctx *ctx, bool want_hash, bool want_comp, cw_hash_alg halg, cw_
         int v = e ? atoi(e) : kSlots;
         return v < 1 ? 1 : (v > kSlots ? kSlots : v);
     }();
-    size_t per = slice_bytes / chunk;
+    const bool stage_in = is_pageable(src);
+    const bool stage_out = (want_comp && (is_pageable(dst) || is_pageable(lens))) || (want_hash && is_pageable(digests));
+    size_t per = ((stage_in || stage_out) ? kStageSliceBytes : slice_bytes) / chunk;
     if (per < 1) per = 1;
+    if (per > n) per = n;  // (a small call allocates what it needs)
     int rc = CW_OK;
+    // results of a finished slice: from the staging buffers to the caller's arrays
+    auto drain = [&](Slot &s) -> int {
+        if (!s.busy) return CW_OK;
+        s.busy = false;
+        cudaError_t e = cudaEventSynchronize(s.done);
+        if (e != cudaSuccess) {
+            s.staged_out = false;
+            return fail(ctx, e, "cudaEventSynchronize(slot)");
+        }
+        if (!s.staged_out) return CW_OK;
+        s.staged_out = false;
+        const size_t lo = s.lo, cnt = s.cnt;
+        const size_t kPieceChunks = std::max<size_t>(1, (1u << 20) / chunk);  // ~1 MiB of input per piece
+        pool_for(ctx, (cnt + kPieceChunks - 1) / kPieceChunks, [&](size_t k) {
+            const size_t a = k * kPieceChunks, m = std::min(kPieceChunks, cnt - a);
+            if (want_hash) memcpy((uint8_t *)digests + (lo + a) * D, s.h_dig + a * D, m * D);
+            if (want_comp) {
+                memcpy(lens + lo + a, s.h_lens + a, m * sizeof(uint32_t));
+                for (size_t i = a; i < a + m; i++)  // only the bytes that exist (LZF: 0 = "store raw", nothing to copy)
+                    memcpy((uint8_t *)dst + (lo + i) * stride, s.h_out + i * stride, s.h_lens[i]);
+            }
+        });
+        return CW_OK;
+    };
+    auto cu = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess) rc = fail(ctx, e, what);
+        return e == cudaSuccess;
+    };
     size_t k = 0;
     for (size_t lo = 0; lo < n && rc == CW_OK; lo += per, k++) {
         const size_t cnt = (n - lo < per) ? n - lo : per;
         Slot &s = ctx->slots[k % n_slots];
-        if (s.busy) {
-            CW_CUDA(ctx, cudaEventSynchronize(s.done));
-            s.busy = false;
-        }
+        if ((rc = drain(s)) != CW_OK) break;
         if ((rc = ensure(ctx, (void **)&s.d_in, &s.cap_in, per * chunk)) != CW_OK) break;
         if (want_comp) {
             if ((rc = ensure(ctx, (void **)&s.d_out, &s.cap_out, per * stride)) != CW_OK) break;
             if ((rc = ensure(ctx, (void **)&s.d_lens, &s.cap_lens, per * sizeof(uint32_t))) != CW_OK) break;
         }
         if (want_hash && (rc = ensure(ctx, (void **)&s.d_dig, &s.cap_dig, per * D)) != CW_OK) break;
-        CW_CUDA(ctx, cudaMemcpyAsync(s.d_in, (const uint8_t *)src + lo * chunk, cnt * chunk, cudaMemcpyHostToDevice, s.st));
+        const uint8_t *in = (const uint8_t *)src + lo * chunk;
+        if (stage_in) {
+            if ((rc = ensure_host(ctx, (void **)&s.h_in, &s.cap_h_in, per * chunk)) != CW_OK) break;
+            pool_memcpy(ctx, s.h_in, in, cnt * chunk);
+            in = s.h_in;
+        }
+        if (stage_out) {
+            if (want_comp) {
+                if ((rc = ensure_host(ctx, (void **)&s.h_out, &s.cap_h_out, per * stride)) != CW_OK) break;
+                if ((rc = ensure_host(ctx, (void **)&s.h_lens, &s.cap_h_lens, per * sizeof(uint32_t))) != CW_OK) break;
+            }
+            if (want_hash && (rc = ensure_host(ctx, (void **)&s.h_dig, &s.cap_h_dig, per * D)) != CW_OK) break;
+        }
+        if (!cu(cudaMemcpyAsync(s.d_in, in, cnt * chunk, cudaMemcpyHostToDevice, s.st), "cudaMemcpyAsync(slice in)")) break;
         if (want_hash && want_comp)
             rc = do_fused_dev(ctx, halg, calg, mode, s.d_in, chunk, cnt, s.d_dig, s.d_out, stride, s.d_lens, s.st);
         else if (want_hash)
@@ -348,21 +513,27 @@ int host_pass(cw_ctx *ctx, bool want_hash, bool want_comp, cw_hash_alg halg, cw_
         else
             rc = do_compress_dev(ctx, calg, mode, s.d_in, chunk, cnt, s.d_out, stride, s.d_lens, s.st);
         if (rc != CW_OK) break;
+        s.busy = true;  // (from here on the slot has copies into host memory in flight)
+        s.staged_out = false;
         if (want_comp) {
-            CW_CUDA(ctx, cudaMemcpyAsync((uint8_t *)dst + lo * stride, s.d_out, cnt * stride, cudaMemcpyDeviceToHost, s.st));
-            CW_CUDA(ctx, cudaMemcpyAsync(lens + lo, s.d_lens, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.st));
+            if (!cu(cudaMemcpyAsync(stage_out ? s.h_out : (uint8_t *)dst + lo * stride, s.d_out, cnt * stride, cudaMemcpyDeviceToHost, s.st), "cudaMemcpyAsync(blocks out)")) break;
+            if (!cu(cudaMemcpyAsync(stage_out ? (void *)s.h_lens : (void *)(lens + lo), s.d_lens, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.st), "cudaMemcpyAsync(lengths out)")) break;
         }
-        if (want_hash)
-            CW_CUDA(ctx, cudaMemcpyAsync((uint8_t *)digests + lo * D, s.d_dig, cnt * D, cudaMemcpyDeviceToHost, s.st));
-        CW_CUDA(ctx, cudaEventRecord(s.done, s.st));
-        s.busy = true;
+        if (want_hash &&
+            !cu(cudaMemcpyAsync(stage_out ? s.h_dig : (uint8_t *)digests + lo * D, s.d_dig, cnt * D, cudaMemcpyDeviceToHost, s.st), "cudaMemcpyAsync(digests out)"))
+            break;
+        if (!cu(cudaEventRecord(s.done, s.st), "cudaEventRecord(slot)")) break;
+        s.staged_out = stage_out;
+        s.lo = lo;
+        s.cnt = cnt;
     }
-    for (int i = 0; i < kSlots; i++) {
-        Slot &s = ctx->slots[i];
-        if (s.busy) {
-            cudaError_t e = cudaEventSynchronize(s.done);
-            s.busy = false;
-            if (e != cudaSuccess && rc == CW_OK) rc = fail(ctx, e, "cudaEventSynchronize(slot)");
+    // the slices still in flight, oldest first
+    for (int i = 0; i < n_slots && rc == CW_OK; i++) rc = drain(ctx->slots[(k + i) % n_slots]);
+    if (rc != CW_OK) {  // error path: nothing is delivered any more, but every copy into host memory ends before we return
+        for (int i = 0; i < kSlots; i++) {
+            Slot &s = ctx->slots[i];
+            if (s.busy) cudaStreamSynchronize(s.st);
+            s.busy = s.staged_out = false;
         }
     }
     return rc;
@@ -732,56 +903,39 @@ void finish_job_range(cw_ctx *ctx, BatchBuf &b, size_t lo, size_t hi)
     }
 }
 
-void copy_helper(cw_ctx *ctx)
-{
-    CopyPool &P = ctx->pool;
-    for (;;) {
-        CopyTask t;
-        {
-            std::unique_lock<std::mutex> lk(P.mu);
-            P.cv.wait(lk, [&] { return P.stop || !P.tasks.empty(); });
-            if (P.tasks.empty()) return;  // stop requested and nothing left
-            t = P.tasks.front();
-            P.tasks.pop_front();
-        }
-        BatchBuf &b = ctx->bat.bufs[t.buf];
-        finish_job_range(ctx, b, t.lo, t.hi);
-        bool last;
-        {
-            std::lock_guard<std::mutex> lk(P.mu);
-            last = --b.tasks_left == 0;
-        }
-        if (last) {
-            ctx->batched_calls += b.jobs.size();
-            batch_release(ctx, &b);
-        }
-    }
-}
-
 // offload thread: a batch that carries submitted jobs is complete
 void finish_batch_jobs(cw_ctx *ctx, int i)
 {
     BatchBuf &b = ctx->bat.bufs[i];
-    static const int n_helpers = [] {
-        const char *e = getenv("CW_COPY_THREADS");  // 0: the offload thread copies everything itself
-        int v = e ? atoi(e) : (int)std::thread::hardware_concurrency() / 2;
-        return v < 0 ? 0 : (v > 8 ? 8 : v);
-    }();
     const size_t nj = b.jobs.size();
-    if (n_helpers < 2 || nj < 8) {
+    if (pool_threads() < 2 || nj < 8) {
         finish_job_range(ctx, b, 0, nj);
         ctx->batched_calls += nj;
         batch_release(ctx, &b);
         return;
     }
     CopyPool &P = ctx->pool;
-    const size_t pieces = std::min<size_t>(nj / 4, (size_t)n_helpers * 2);
+    const size_t pieces = std::min<size_t>(nj / 4, (size_t)pool_threads() * 2);
     {
         std::lock_guard<std::mutex> lk(P.mu);
-        if (P.th.empty())
-            for (int t = 0; t < n_helpers; t++) P.th.emplace_back(copy_helper, ctx);
+        pool_start(ctx);
         b.tasks_left = (int)pieces;
-        for (size_t k = 0; k < pieces; k++) P.tasks.push_back(CopyTask{i, nj * k / pieces, nj * (k + 1) / pieces});
+        for (size_t k = 0; k < pieces; k++) {
+            const size_t lo = nj * k / pieces, hi = nj * (k + 1) / pieces;
+            P.tasks.emplace_back([ctx, i, lo, hi] {
+                BatchBuf &bb = ctx->bat.bufs[i];
+                finish_job_range(ctx, bb, lo, hi);
+                bool last;
+                {
+                    std::lock_guard<std::mutex> lk2(ctx->pool.mu);
+                    last = --bb.tasks_left == 0;
+                }
+                if (last) {
+                    ctx->batched_calls += bb.jobs.size();
+                    batch_release(ctx, &bb);
+                }
+            });
+        }
     }
     P.cv.notify_all();
 }
@@ -910,6 +1064,10 @@ void cw_shutdown(cw_ctx *ctx)
         if (s.d_offsets) cudaFree(s.d_offsets);
         if (s.d_scan) cudaFree(s.d_scan);
         if (s.h_total) cudaFreeHost(s.h_total);
+        if (s.h_in) cudaFreeHost(s.h_in);
+        if (s.h_out) cudaFreeHost(s.h_out);
+        if (s.h_dig) cudaFreeHost(s.h_dig);
+        if (s.h_lens) cudaFreeHost(s.h_lens);
         if (s.ready) cudaEventDestroy(s.ready);
         if (s.done) cudaEventDestroy(s.done);
         if (s.st) cudaStreamDestroy(s.st);

@@ -311,6 +311,41 @@ def test_large_batch_spans_pipeline_slices(eng):
     assert (dig == dig2).all() and (lens == lens2).all()
 
 
+def test_pinned_and_pageable_callers_agree(eng):
+    """host-buffer pass: page-locked caller buffers go to the copy engines as they are (64 MiB slices), ordinary memory is
+    staged through pinned slot buffers by the copy helpers (16 MiB slices, results copied out when a slot comes round
+    again) -- same digests, lengths and block bytes either way; hash-only and compress-only calls too (LZF: length 0 =
+    nothing copied)"""
+    chunk, n = 8192, 36864  # 288 MiB: 5 slices of 64 MiB, 18 of 16 MiB
+    d = O.synth(chunk, 9000, n)
+    dig_a, blocks_a, lens_a = eng.process_block(cw.HASH_SKEIN512, cw.COMP_LZ4, d, chunk)  # pageable
+    stride = cw.compress_bound(cw.COMP_LZ4, chunk)
+    dp = d.copy()
+    out = (np.zeros((n, 64), np.uint8), np.zeros((n, stride), np.uint8), np.zeros(n, np.uint32))
+    regs = [dp, *out]
+    for a in regs:
+        eng.host_register(a)
+    try:
+        dig_b, blocks_b, lens_b = eng.process_block(cw.HASH_SKEIN512, cw.COMP_LZ4, dp, chunk, out=out)
+    finally:
+        for a in regs:
+            eng.host_unregister(a)
+    assert (dig_a == dig_b).all() and (lens_a == lens_b).all()
+    mask = np.arange(stride)[None, :] < lens_a[:, None]
+    assert (blocks_a[mask] == blocks_b[mask]).all()
+    idx = np.r_[0:32, 2040:2056, n - 32:n]
+    sub = np.concatenate([d[i * chunk:(i + 1) * chunk] for i in idx])
+    assert (dig_a[idx] == O.hash_chunks(O.HASH_SKEIN512, sub, chunk)).all()
+    assert O.verify_roundtrip(O.COMP_LZ4, d, chunk, blocks_a, lens_a) == 0
+    # hash-only and compress-only through the staged path, several slices each
+    m = 6000
+    assert (eng.do_hashing(cw.HASH_SHA256, d[: m * chunk], chunk)[idx[:48]] == O.hash_chunks(O.HASH_SHA256, sub[: 48 * chunk], chunk)).all()
+    bl, ll = eng.do_compression(cw.COMP_LZF, d[: m * chunk], chunk)
+    ob, ol = O.compress_chunks(O.COMP_LZF, d[: 64 * chunk], chunk)
+    assert (ll[:64] == ol).all() and all((bl[i, : ol[i]] == ob[i, : ol[i]]).all() for i in range(64))
+    assert O.verify_roundtrip(O.COMP_LZF, d[: m * chunk], chunk, bl, ll) == 0
+
+
 def test_async_offload_tickets(eng):
     chunk, n = 4096, 2048
     d = O.synth(chunk, 0, n)

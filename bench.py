@@ -370,6 +370,43 @@ def run_configs(eng, cw, O, torch, np, dev, stream, peaks, int_peak, steps: int)
             comp_entry(f"configs[3]: {tag} 8 KiB, synthetic mix", syn8, 8192, calg, mode, halg, {})
     return out
 
+def run_small_items(O, np):
+    """The reference's calling pattern through the product's own host tool (compute_war_b200/hashandcompress --work-items:
+    --c-threads workers, one cw_hash_compress call -- or HashOffload-style cw_submit / cw_wait -- per work item of
+    readBlockFactor chunks; HashAndCompress.cpp:160-183,263-272, run_tests:14), from ordinary pageable buffers like the
+    reference's, 256 MiB of the synthetic stream in 4 KiB chunks.  Reported next to the whole-file call."""
+    exe = os.path.join(ROOT, "compute_war_b200", "hashandcompress")
+    if not os.access(exe, os.X_OK):
+        return {"error": "host tool not built"}
+    import re
+    import tempfile
+    chunk, n = 4096, 65536
+    rows = []
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "items.bin")
+        O.synth(chunk, 0, n).tofile(path)
+
+        def run(label, *flags):
+            try:
+                out = subprocess.run([exe, "-H", "skein512", "-C", "lz4", "-k", str(chunk), "-i", "3", *flags, path],
+                                     capture_output=True, text=True, timeout=120)
+                m = re.search(r"MBps=([0-9.]+)", out.stdout + out.stderr)
+                rows.append({"call": label, "GBps": float(m.group(1)) * 1048576 / 1e9 if m else None})  # the tool prints MiB/s
+            except Exception as ex:  # noqa: BLE001 -- a side figure never fails the bench line
+                rows.append({"call": label, "error": str(ex)[:120]})
+
+        run("one call per file, page-locked buffers")
+        run("one call per file, pageable buffers", "--no-pin")
+        for r in (8, 64, 256, 2048):
+            run(f"blocking calls of {r * chunk // 1024} KiB from 14 threads, pageable", "--no-pin", "--work-items", "-c", "14", "-r", str(r))
+        for r in (8, 64):
+            run(f"HashOffload style (cw_submit / cw_wait, 64 tickets per thread) items of {r * chunk // 1024} KiB from 14 threads, pageable",
+                "--no-pin", "--work-items", "--gpu-offload", "1", "-c", "14", "-r", str(r))
+    return {"workload": f"{n} chunks x {chunk} B of the synthetic stream, fused skein512+lz4 compat, host tool, best-effort side figure",
+            "host_threads": host_threads(), "rows": rows}
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -745,6 +782,11 @@ def main():
                         "what": "same driver linked against src/hashing_perf/skein/libskein.a as the reference ships it"}
                 except Exception as ex:  # never fail the bench line over the side figure
                     line["cpu_baseline"]["as_shipped_libskein"] = {"error": str(ex)[:200]}
+        if world == 1 and not args.no_configs:
+            try:
+                line["small_items"] = run_small_items(O, np)
+            except Exception as ex:  # noqa: BLE001
+                line["small_items"] = {"error": f"{type(ex).__name__}: {ex}"}
         print(json.dumps(line), flush=True)
     eng.close()
     if dist is not None:

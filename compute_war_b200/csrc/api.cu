@@ -72,8 +72,12 @@ struct Job {
 // Work items of equal (hash, codec, mode, chunk size) that arrive while the GPU is busy are gathered in one pinned
 // batch buffer -- every caller copies its own bytes in and, afterwards, its own results out, in parallel -- and one
 // copy in / one launch / one set of copies out serves them all. ----
-constexpr size_t kBatchBytes = 16u << 20;  // input bytes per batch buffer
-constexpr int kBatchBufs = 3;
+constexpr size_t kBatchBytes = 8u << 20;   // input bytes per batch buffer
+constexpr size_t kBatchSoftBytes = kBatchBytes / 2;  // a batch that holds this much is sealed while another buffer is free:
+                                                     // callers that arrive together (14 threads x 1 MiB) are spread over
+                                                     // several batches whose copies and kernels overlap, instead of all
+                                                     // riding -- and waiting -- in one
+constexpr int kBatchBufs = 6;
 constexpr size_t kSmallCall = 8u << 20;    // host-buffer calls up to this many input bytes go through the batcher
 constexpr size_t kBatchMinChunk = 512;     // smaller chunks: direct path (digest / length arrays would dominate)
 
@@ -449,7 +453,10 @@ int host_pass(cw_ctx *ctx, bool want_hash, bool want_comp, cw_hash_alg halg, cw_
     }();
     const bool stage_in = is_pageable(src);
     const bool stage_out = (want_comp && (is_pageable(dst) || is_pageable(lens))) || (want_hash && is_pageable(digests));
-    size_t per = ((stage_in || stage_out) ? kStageSliceBytes : slice_bytes) / chunk;
+    // staged calls: at least four slices per call where the call is big enough (a 16 MiB call in one slice would run its
+    // staging, its copies and its kernel one after the other)
+    size_t stage_slice = std::min(kStageSliceBytes, std::max<size_t>(2u << 20, (n * chunk / 4 + 0xfffffu) & ~(size_t)0xfffffu));
+    size_t per = ((stage_in || stage_out) ? stage_slice : slice_bytes) / chunk;
     if (per < 1) per = 1;
     if (per > n) per = n;  // (a small call allocates what it needs)
     int rc = CW_OK;
@@ -558,6 +565,10 @@ int host_pass_packed(cw_ctx *ctx, cw_hash_alg halg, cw_comp_alg calg, cw_mode mo
     if (per < 1) per = 1;
     int rc = CW_OK;
     unsigned long long base = 0;
+    auto cu = [&](cudaError_t e, const char *what) {  // (no early return: slices in flight are drained below)
+        if (e != cudaSuccess) rc = fail(ctx, e, what);
+        return e == cudaSuccess;
+    };
     // a finished slice's offsets become offsets into the caller's buffer
     auto finish = [&](Slot &s) -> int {
         if (!s.busy) return CW_OK;
@@ -576,11 +587,11 @@ int host_pass_packed(cw_ctx *ctx, cw_hash_alg halg, cw_comp_alg calg, cw_mode mo
             return CW_ERR_ARG;
         }
         s.base = base;
-        CW_CUDA(ctx, cudaMemcpyAsync((uint8_t *)packed + base, s.d_packed, total, cudaMemcpyDeviceToHost, s.st));
-        CW_CUDA(ctx, cudaMemcpyAsync(offsets + s.lo, s.d_offsets, s.cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, s.st));
-        CW_CUDA(ctx, cudaMemcpyAsync(lens + s.lo, s.d_lens, s.cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.st));
-        CW_CUDA(ctx, cudaMemcpyAsync((uint8_t *)digests + s.lo * D, s.d_dig, s.cnt * D, cudaMemcpyDeviceToHost, s.st));
-        CW_CUDA(ctx, cudaEventRecord(s.done, s.st));
+        if (!cu(cudaMemcpyAsync((uint8_t *)packed + base, s.d_packed, total, cudaMemcpyDeviceToHost, s.st), "cudaMemcpyAsync")) return rc;
+        if (!cu(cudaMemcpyAsync(offsets + s.lo, s.d_offsets, s.cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, s.st), "cudaMemcpyAsync")) return rc;
+        if (!cu(cudaMemcpyAsync(lens + s.lo, s.d_lens, s.cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.st), "cudaMemcpyAsync")) return rc;
+        if (!cu(cudaMemcpyAsync((uint8_t *)digests + s.lo * D, s.d_dig, s.cnt * D, cudaMemcpyDeviceToHost, s.st), "cudaMemcpyAsync")) return rc;
+        if (!cu(cudaEventRecord(s.done, s.st), "cudaEventRecord")) return rc;
         s.busy = true;
         base += total;
         return CW_OK;
@@ -598,17 +609,18 @@ int host_pass_packed(cw_ctx *ctx, cw_hash_alg halg, cw_comp_alg calg, cw_mode mo
         if ((rc = ensure(ctx, (void **)&s.d_packed, &s.cap_packed, per * stride)) != CW_OK) break;
         if ((rc = ensure(ctx, (void **)&s.d_offsets, &s.cap_offsets, (per + 1) * sizeof(uint64_t))) != CW_OK) break;
         if ((rc = ensure(ctx, (void **)&s.d_scan, &s.cap_scan, ((per + 1023) / 1024 + 1) * sizeof(uint64_t))) != CW_OK) break;
-        if (!s.h_total) CW_CUDA(ctx, cudaHostAlloc((void **)&s.h_total, sizeof(uint64_t), cudaHostAllocDefault));
-        if (!s.ready) CW_CUDA(ctx, cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
+        if (!s.h_total) if (!cu(cudaHostAlloc((void **)&s.h_total, sizeof(uint64_t), cudaHostAllocDefault), "cudaHostAlloc")) break;
+        if (!s.ready) if (!cu(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming), "cudaEventCreateWithFlags")) break;
         s.lo = lo;
         s.cnt = cnt;
-        CW_CUDA(ctx, cudaMemcpyAsync(s.d_in, (const uint8_t *)src + lo * chunk, cnt * chunk, cudaMemcpyHostToDevice, s.st));
+        if (!cu(cudaMemcpyAsync(s.d_in, (const uint8_t *)src + lo * chunk, cnt * chunk, cudaMemcpyHostToDevice, s.st), "cudaMemcpyAsync")) break;
         if ((rc = do_fused_dev(ctx, halg, calg, mode, s.d_in, chunk, cnt, s.d_dig, s.d_out, stride, s.d_lens, s.st)) != CW_OK) break;
-        CW_CUDA(ctx, cw_launch_pack(s.d_out, stride, s.d_lens, s.d_in, (uint32_t)chunk, cnt, s.d_packed, per * stride, s.d_offsets,
-                                    s.d_scan, s.st));
+        if (!cu(cw_launch_pack(s.d_out, stride, s.d_lens, s.d_in, (uint32_t)chunk, cnt, s.d_packed, per * stride, s.d_offsets, s.d_scan, s.st),
+                "cw_launch_pack"))
+            break;
         ctx->launches += 3;
-        CW_CUDA(ctx, cudaMemcpyAsync(s.h_total, s.d_offsets + cnt, sizeof(uint64_t), cudaMemcpyDeviceToHost, s.st));
-        CW_CUDA(ctx, cudaEventRecord(s.ready, s.st));
+        if (!cu(cudaMemcpyAsync(s.h_total, s.d_offsets + cnt, sizeof(uint64_t), cudaMemcpyDeviceToHost, s.st), "cudaMemcpyAsync")) break;
+        if (!cu(cudaEventRecord(s.ready, s.st), "cudaEventRecord")) break;
         if (prev && (rc = stage_b(*prev)) != CW_OK) break;
         prev = &s;
     }
@@ -748,8 +760,11 @@ BatchBuf *batch_reserve(cw_ctx *ctx, std::unique_lock<std::mutex> &lk, cw_hash_a
     for (;;) {
         if (B.open >= 0) {
             BatchBuf &b = B.bufs[B.open];
+            bool soft_full = false;
+            if (b.chunks * b.chunk >= kBatchSoftBytes)
+                for (int i = 0; i < kBatchBufs && !soft_full; i++) soft_full = B.bufs[i].state == BatchBuf::FREE;
             if (b.state == BatchBuf::OPEN && b.halg == halg && b.calg == calg && b.mode == mode && b.chunk == chunk &&
-                b.chunks + n <= b.cap_chunks) {
+                b.chunks + n <= b.cap_chunks && !soft_full) {
                 *first = b.chunks;
                 b.chunks += n;
                 b.copying_in++;

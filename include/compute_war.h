@@ -78,11 +78,13 @@ size_t cw_compress_bound(cw_comp_alg alg, size_t chunk_bytes);
 
 /* ---- host-buffer calls: the reference's two function slots and ProcessBlock ----
  * Blocking.  Buffers are the caller's (the library never frees or keeps them); pinned host memory makes
- * the internal H2D/D2H copies asynchronous and overlapped with the kernels, pageable memory also works. */
+ * the internal H2D/D2H copies asynchronous and overlapped with the kernels.  Ordinary (pageable) memory works too:
+ * the library stages it through pinned buffers of its own with a few helper threads (CW_COPY_THREADS, default
+ * min(8, host threads / 2)), at roughly a third of the pinned rate. */
 
 /* Page-locks (and later releases) a caller-owned buffer so that the copies of the host-buffer calls run asynchronously at
  * full PCIe rate; the reference allocates its buffers with malloc / std::string (HashAndCompress.cpp:233-239), which
- * works here too but is staged through the driver's bounce buffers.  Registration is slow (about a second per GiB):
+ * works here too but is staged through the library's pinned buffers by helper threads.  Registration is slow (about a second per GiB):
  * do it once for buffers that are reused.  No counterpart in the reference. */
 int cw_host_register(cw_ctx *ctx, void *ptr, size_t bytes);
 int cw_host_unregister(cw_ctx *ctx, void *ptr);

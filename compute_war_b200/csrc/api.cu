@@ -73,7 +73,7 @@ struct Job {
 // batch buffer -- every caller copies its own bytes in and, afterwards, its own results out, in parallel -- and one
 // copy in / one launch / one set of copies out serves them all. ----
 constexpr size_t kBatchBytes = 8u << 20;   // input bytes per batch buffer
-constexpr size_t kBatchSoftBytes = kBatchBytes / 2;  // a batch that holds this much is sealed while another buffer is free:
+constexpr size_t kBatchSoftBytes = kBatchBytes / 8;  // a batch that holds this much is sealed while another buffer is free:
                                                      // callers that arrive together (14 threads x 1 MiB) are spread over
                                                      // several batches whose copies and kernels overlap, instead of all
                                                      // riding -- and waiting -- in one

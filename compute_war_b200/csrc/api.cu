@@ -50,7 +50,9 @@ struct Slot {
     // on their way out
     uint8_t *h_in = nullptr, *h_out = nullptr, *h_dig = nullptr;
     uint32_t *h_lens = nullptr;
-    size_t cap_h_in = 0, cap_h_out = 0, cap_h_dig = 0, cap_h_lens = 0;
+    unsigned long long *h_offsets = nullptr;
+    size_t cap_h_in = 0, cap_h_out = 0, cap_h_dig = 0, cap_h_lens = 0, cap_h_offsets = 0;
+    unsigned long long total = 0;  // packed bytes of the slice
     bool staged_out = false;  // the slice's results still sit in the staging buffers
 };
 
@@ -561,7 +563,11 @@ int host_pass_packed(cw_ctx *ctx, cw_hash_alg halg, cw_comp_alg calg, cw_mode mo
         size_t mb = e ? (size_t)atoi(e) : 0;
         return mb ? mb << 20 : kSliceBytesDefault;
     }();
-    size_t per = slice_bytes / chunk;
+    // callers with pageable memory: staged through pinned slot buffers by the copy helpers, like host_pass
+    const bool stage_in = is_pageable(src);
+    const bool stage_out = is_pageable(packed) || is_pageable(offsets) || is_pageable(lens) || is_pageable(digests);
+    const size_t stage_slice = std::min(kStageSliceBytes, std::max<size_t>(2u << 20, (n * chunk / 4 + 0xfffffu) & ~(size_t)0xfffffu));
+    size_t per = ((stage_in || stage_out) ? stage_slice : slice_bytes) / chunk;
     if (per < 1) per = 1;
     int rc = CW_OK;
     unsigned long long base = 0;
@@ -575,7 +581,15 @@ int host_pass_packed(cw_ctx *ctx, cw_hash_alg halg, cw_comp_alg calg, cw_mode mo
         s.busy = false;
         cudaError_t e = cudaEventSynchronize(s.done);
         if (e != cudaSuccess) return fail(ctx, e, "cudaEventSynchronize(slot)");
-        for (size_t i = 0; i < s.cnt; i++) offsets[s.lo + i] += s.base;
+        if (!s.staged_out) {
+            for (size_t i = 0; i < s.cnt; i++) offsets[s.lo + i] += s.base;
+            return CW_OK;
+        }
+        s.staged_out = false;
+        pool_memcpy(ctx, (uint8_t *)packed + s.base, s.h_out, s.total);
+        for (size_t i = 0; i < s.cnt; i++) offsets[s.lo + i] = s.h_offsets[i] + s.base;
+        memcpy(lens + s.lo, s.h_lens, s.cnt * sizeof(uint32_t));
+        memcpy((uint8_t *)digests + s.lo * D, s.h_dig, s.cnt * D);
         return CW_OK;
     };
     auto stage_b = [&](Slot &s) -> int {
@@ -587,12 +601,15 @@ int host_pass_packed(cw_ctx *ctx, cw_hash_alg halg, cw_comp_alg calg, cw_mode mo
             return CW_ERR_ARG;
         }
         s.base = base;
-        if (!cu(cudaMemcpyAsync((uint8_t *)packed + base, s.d_packed, total, cudaMemcpyDeviceToHost, s.st), "cudaMemcpyAsync")) return rc;
-        if (!cu(cudaMemcpyAsync(offsets + s.lo, s.d_offsets, s.cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, s.st), "cudaMemcpyAsync")) return rc;
-        if (!cu(cudaMemcpyAsync(lens + s.lo, s.d_lens, s.cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.st), "cudaMemcpyAsync")) return rc;
-        if (!cu(cudaMemcpyAsync((uint8_t *)digests + s.lo * D, s.d_dig, s.cnt * D, cudaMemcpyDeviceToHost, s.st), "cudaMemcpyAsync")) return rc;
+        s.total = total;
+        s.busy = true;  // (copies into host memory in flight from here on)
+        s.staged_out = false;
+        if (!cu(cudaMemcpyAsync(stage_out ? s.h_out : (uint8_t *)packed + base, s.d_packed, total, cudaMemcpyDeviceToHost, s.st), "cudaMemcpyAsync(packed out)")) return rc;
+        if (!cu(cudaMemcpyAsync(stage_out ? (void *)s.h_offsets : (void *)(offsets + s.lo), s.d_offsets, s.cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, s.st), "cudaMemcpyAsync(offsets out)")) return rc;
+        if (!cu(cudaMemcpyAsync(stage_out ? (void *)s.h_lens : (void *)(lens + s.lo), s.d_lens, s.cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.st), "cudaMemcpyAsync(lengths out)")) return rc;
+        if (!cu(cudaMemcpyAsync(stage_out ? s.h_dig : (uint8_t *)digests + s.lo * D, s.d_dig, s.cnt * D, cudaMemcpyDeviceToHost, s.st), "cudaMemcpyAsync(digests out)")) return rc;
         if (!cu(cudaEventRecord(s.done, s.st), "cudaEventRecord")) return rc;
-        s.busy = true;
+        s.staged_out = stage_out;
         base += total;
         return CW_OK;
     };
@@ -613,7 +630,19 @@ int host_pass_packed(cw_ctx *ctx, cw_hash_alg halg, cw_comp_alg calg, cw_mode mo
         if (!s.ready) if (!cu(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming), "cudaEventCreateWithFlags")) break;
         s.lo = lo;
         s.cnt = cnt;
-        if (!cu(cudaMemcpyAsync(s.d_in, (const uint8_t *)src + lo * chunk, cnt * chunk, cudaMemcpyHostToDevice, s.st), "cudaMemcpyAsync")) break;
+        const uint8_t *in = (const uint8_t *)src + lo * chunk;
+        if (stage_in) {
+            if ((rc = ensure_host(ctx, (void **)&s.h_in, &s.cap_h_in, per * chunk)) != CW_OK) break;
+            pool_memcpy(ctx, s.h_in, in, cnt * chunk);
+            in = s.h_in;
+        }
+        if (stage_out) {
+            if ((rc = ensure_host(ctx, (void **)&s.h_out, &s.cap_h_out, per * stride)) != CW_OK) break;
+            if ((rc = ensure_host(ctx, (void **)&s.h_lens, &s.cap_h_lens, per * sizeof(uint32_t))) != CW_OK) break;
+            if ((rc = ensure_host(ctx, (void **)&s.h_dig, &s.cap_h_dig, per * D)) != CW_OK) break;
+            if ((rc = ensure_host(ctx, (void **)&s.h_offsets, &s.cap_h_offsets, (per + 1) * sizeof(uint64_t))) != CW_OK) break;
+        }
+        if (!cu(cudaMemcpyAsync(s.d_in, in, cnt * chunk, cudaMemcpyHostToDevice, s.st), "cudaMemcpyAsync(slice in)")) break;
         if ((rc = do_fused_dev(ctx, halg, calg, mode, s.d_in, chunk, cnt, s.d_dig, s.d_out, stride, s.d_lens, s.st)) != CW_OK) break;
         if (!cu(cw_launch_pack(s.d_out, stride, s.d_lens, s.d_in, (uint32_t)chunk, cnt, s.d_packed, per * stride, s.d_offsets, s.d_scan, s.st),
                 "cw_launch_pack"))
@@ -629,8 +658,8 @@ int host_pass_packed(cw_ctx *ctx, cw_hash_alg halg, cw_comp_alg calg, cw_mode mo
         Slot &s = ctx->slots[i];
         if (rc == CW_OK) rc = finish(s);
         else if (s.busy) {  // error path: let the copies into the caller's buffers end before returning
-            cudaEventSynchronize(s.done);
-            s.busy = false;
+            cudaStreamSynchronize(s.st);
+            s.busy = s.staged_out = false;
         }
     }
     if (rc != CW_OK) cudaDeviceSynchronize();  // slices whose visit B never ran
@@ -1083,6 +1112,7 @@ void cw_shutdown(cw_ctx *ctx)
         if (s.h_out) cudaFreeHost(s.h_out);
         if (s.h_dig) cudaFreeHost(s.h_dig);
         if (s.h_lens) cudaFreeHost(s.h_lens);
+        if (s.h_offsets) cudaFreeHost(s.h_offsets);
         if (s.ready) cudaEventDestroy(s.ready);
         if (s.done) cudaEventDestroy(s.done);
         if (s.st) cudaStreamDestroy(s.st);

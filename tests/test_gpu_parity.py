@@ -346,6 +346,38 @@ def test_pinned_and_pageable_callers_agree(eng):
     assert O.verify_roundtrip(O.COMP_LZF, d[: m * chunk], chunk, bl, ll) == 0
 
 
+def test_packed_output_pinned_and_pageable_callers_agree(eng):
+    """cw_hash_compress_packed: ordinary memory is staged through pinned slot buffers (several slices, slots reused),
+    page-locked buffers are copied as they are -- same packed stream, offsets, lengths and digests, and the stream is the
+    strided call's blocks back to back"""
+    chunk, n = 4096, 40000  # 156 MiB: ten staged slices of 16 MiB, three of 64 MiB
+    d = O.synth(chunk, 12000, n)
+    dig_a, packed_a, off_a, lens_a = eng.process_block_packed(cw.HASH_SKEIN256_128, cw.COMP_LZ4, d, chunk)  # pageable
+    cap = n * cw.compress_bound(cw.COMP_LZ4, chunk)
+    dp = d.copy()
+    dig_b, packed_b = np.zeros((n, 16), np.uint8), np.zeros(cap, np.uint8)
+    off_b, lens_b = np.zeros(n + 1, np.uint64), np.zeros(n, np.uint32)
+    regs = [dp, dig_b, packed_b, off_b, lens_b]
+    for a in regs:
+        eng.host_register(a)
+    try:
+        eng.process_block_packed_ptr(cw.HASH_SKEIN256_128, cw.COMP_LZ4, cw.MODE_COMPAT, dp.ctypes.data, chunk, n, dig_b.ctypes.data,
+                                     packed_b.ctypes.data, cap, off_b.ctypes.data, lens_b.ctypes.data)
+    finally:
+        for a in regs:
+            eng.host_unregister(a)
+    total = int(off_a[n])
+    assert total == int(lens_a.sum(dtype=np.int64)) == int(off_b[n])
+    assert (off_a == off_b).all() and (lens_a == lens_b).all() and (dig_a == dig_b).all()
+    assert (off_a[:-1] == np.concatenate([[0], np.cumsum(lens_a[:-1], dtype=np.uint64)])).all()
+    assert (packed_a == packed_b[:total]).all()
+    _, blocks, lens = eng.process_block(cw.HASH_SKEIN256_128, cw.COMP_LZ4, d, chunk)
+    assert (lens == lens_a).all()
+    mask = np.arange(blocks.shape[1])[None, :] < lens[:, None]
+    assert (blocks[mask] == packed_a).all()  # row-major order of the mask = blocks back to back
+    assert (dig_a[:64] == O.hash_chunks(O.HASH_SKEIN256_128, d[: 64 * chunk], chunk)).all()
+
+
 def test_async_offload_tickets(eng):
     chunk, n = 4096, 2048
     d = O.synth(chunk, 0, n)

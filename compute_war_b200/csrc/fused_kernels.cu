@@ -319,12 +319,16 @@ cudaError_t cw_launch_fused(const CwDeviceInfo &dev, int halg, int calg, bool fa
     if (n == 0) return cudaSuccess;
     const bool aligned = (chunk % 16u == 0) && ((reinterpret_cast<uintptr_t>(d_src) & 15u) == 0) &&
                          ((reinterpret_cast<uintptr_t>(d_digests) & 15u) == 0);
-    // tuning knob (compat only): smaller chunks read in place too, like CW_LZ4_COMPAT_DIRECT_ABOVE of the stand-alone kernel
+    // compat reads chunks above 8 KiB in place, like the stand-alone kernel (cw_launch_lz4: 16 KiB chunks +21 % on the mix,
+    // +40 % on text); CW_LZ4_COMPAT_DIRECT_ABOVE: the threshold, for A/B runs.  Unaligned buffers / ragged sizes of up to
+    // 16 KiB keep the staged kernel
     static const uint32_t compat_direct_above = [] {
         const char *e = getenv("CW_LZ4_COMPAT_DIRECT_ABOVE");
-        return e ? (uint32_t)atoi(e) : 16384u;
+        return e ? (uint32_t)atoi(e) : 8192u;
     }();
-    if (calg == CW_C_LZ4 && chunk > (fast ? 16384u : compat_direct_above)) {
+    if (calg == CW_C_LZ4 && !fast && aligned && chunk > compat_direct_above && chunk <= 16384u)
+        calg = CW_C_LZ4_DIRECT;
+    else if (calg == CW_C_LZ4 && chunk > 16384u) {
         // big chunks (the 64 KiB blocks of BASELINE configs[2]) are not staged: parsers, emitters and hash warps all read
         // the chunk where it lies, which keeps 13 (fast: 6) chunks per SM in flight instead of 2, in ONE launch
         if (aligned) calg = fast ? CW_C_LZ4_FAST_DIRECT : CW_C_LZ4_DIRECT;

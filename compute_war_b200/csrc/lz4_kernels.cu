@@ -21,6 +21,7 @@
 #define CW_LZ4_MAX_EMITTERS 4
 #define CW_LZ4_EMITTERS_DEFAULT 3
 #define CW_LZ4_DIRECT_ABOVE 16384u  // chunks larger than this are read from global memory instead of being staged
+#define CW_LZ4_COMPAT_DIRECT_ABOVE 8192u  // ... compat mode: already above 8 KiB (cw_launch_lz4)
 
 static int lz4_emitters()
 {
@@ -163,10 +164,12 @@ cudaError_t cw_launch_lz4(const CwDeviceInfo &dev, bool fast, const uint8_t *d_s
         return cudaGetLastError();
     }
     const int hashlog = 13;  // compat: the reference's 13-bit table
-    // tuning knob: smaller chunks read in place too (a slot is then only the table: more parsers per SM, bytes from L1 / L2)
+    // compat reads chunks above 8 KiB in place (a slot is then only the table: 13 parsers per SM instead of 6 at 16 KiB,
+    // bytes from L1 / L2): 16 KiB chunks +22 % on the mix, +40 % on text; 12 KiB +7 / +23 %; at 8 KiB and below staging wins by
+    // 3-16 % (profiles/r02_ab_compat_read_in_place.txt).  CW_LZ4_COMPAT_DIRECT_ABOVE: the threshold, for A/B runs
     static const uint32_t direct_above = [] {
         const char *e = getenv("CW_LZ4_COMPAT_DIRECT_ABOVE");
-        return e ? (uint32_t)atoi(e) : CW_LZ4_DIRECT_ABOVE;
+        return e ? (uint32_t)atoi(e) : CW_LZ4_COMPAT_DIRECT_ABOVE;
     }();
     const bool directc = aligned && chunk > direct_above;
     const uint32_t slot = (directc ? 0u : cw_lz4_chunk_pad(chunk)) + (2u << hashlog);

@@ -283,7 +283,7 @@ def test_fast_mode_roundtrips_and_ratio(eng, golden, alg):
 @pytest.mark.parametrize("halg,calg", [(O.HASH_SKEIN512, O.COMP_LZ4), (O.HASH_SKEIN256_128, O.COMP_LZ4),
                                        (O.HASH_SKEIN256_128, O.COMP_LZF), (O.HASH_SHA256, O.COMP_LZ4),
                                        (O.HASH_SKEIN512, O.COMP_LZF), (O.HASH_SHA256, O.COMP_LZF)])
-@pytest.mark.parametrize("chunk", [4096, 8192, 32768])
+@pytest.mark.parametrize("chunk", [4096, 8192, 12288, 16384, 32768])
 def test_process_block_fused(eng, golden, halg, calg, chunk):
     """hc_sklz4 / hc_sklzf / hc_shlz4 ... : the fused pass equals the two separate primitives and the reference"""
     ref, blob = golden["ref"], golden["blob"]
@@ -291,6 +291,30 @@ def test_process_block_fused(eng, golden, halg, calg, chunk):
     dig, blocks, lens = eng.process_block(halg, calg, d, chunk)
     assert (dig == O.hash_chunks(halg, d, chunk)).all()
     _check_blocks(calg, d, chunk, blocks, lens)
+
+
+@pytest.mark.parametrize("chunk", [8208, 10240, 12288, 16368, 16384])
+def test_lz4_compat_chunks_read_in_place_above_8k(eng, golden, chunk):
+    """compat LZ4 reads chunks above 8 KiB where they lie (13 parsers per SM instead of 6-8): the stand-alone and the
+    fused kernel stay byte-identical to the reference's parse on corpus text and the synthetic stream; a ragged size next
+    to it takes the staged kernel"""
+    blob = golden["blob"]
+    d = np.concatenate([blob[: 48 * 8192], O.synth(chunk, 31, 40)])
+    d = d[: len(d) // chunk * chunk]
+    blocks, lens = eng.do_compression(O.COMP_LZ4, d, chunk, cw.MODE_COMPAT)
+    _check_blocks(O.COMP_LZ4, d, chunk, blocks, lens)
+    dig, blocks2, lens2 = eng.process_block(O.HASH_SKEIN512, O.COMP_LZ4, d, chunk)
+    assert (dig == O.hash_chunks(O.HASH_SKEIN512, d, chunk)).all()
+    assert (lens2 == lens).all()
+    mask = np.arange(blocks.shape[1])[None, :] < lens[:, None]
+    assert (blocks2[mask] == blocks[mask]).all()
+    # a ragged chunk size next to it (not a multiple of 16) is not eligible for the in-place parser: staged kernel, same rule
+    rag = chunk + 2
+    dr = d[: len(d) // rag * rag]
+    blocks3, lens3 = eng.do_compression(O.COMP_LZ4, dr, rag, cw.MODE_COMPAT)
+    _check_blocks(O.COMP_LZ4, dr, rag, blocks3, lens3)
+    dig3, blocks4, lens4 = eng.process_block(O.HASH_SHA256, O.COMP_LZ4, dr, rag)
+    assert (dig3 == O.hash_chunks(O.HASH_SHA256, dr, rag)).all() and (lens4 == lens3).all()
 
 
 def test_large_batch_spans_pipeline_slices(eng):

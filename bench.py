@@ -440,7 +440,13 @@ def main():
     numa = bind_to_gpu_numa_node(torch.cuda.get_device_properties(local)) if world > 1 else None
     dist = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner out of stdout: one JSON line only
+        # stdout carries ONE JSON line: NCCL's own lines (the "NCCL version ..." banner it prints at NCCL_DEBUG=VERSION and
+        # above, warnings) go to stderr
+        # (measured on the box: with NCCL_DEBUG unset / VERSION the banner lands on stdout whatever NCCL_DEBUG_FILE says;
+        # at WARN it follows NCCL_DEBUG_FILE)
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 

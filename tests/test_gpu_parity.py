@@ -318,7 +318,8 @@ def test_lz4_compat_chunks_read_in_place_above_8k(eng, golden, chunk):
 
 
 def test_large_batch_spans_pipeline_slices(eng):
-    """5 slices of 64 MiB through the 4 pipeline slots, so a slot is reused; sampled + order-independent checks"""
+    """320 MiB from ordinary memory: 20 staged slices of 16 MiB through the 4 pipeline slots (slots reused five times;
+    page-locked buffers, 64 MiB slices: test_pinned_and_pageable_callers_agree); sampled + order-independent checks"""
     chunk, n = 8192, 40960  # 320 MiB
     d = O.synth(chunk, 5000, n)
     dig, blocks, lens = eng.process_block(cw.HASH_SKEIN512, cw.COMP_LZ4, d, chunk)

@@ -516,7 +516,7 @@ CW_DEV void cw_lz4_parse_warp(const uint8_t *s, uint32_t n, uint16_t *table, CwL
                 restart = true;
                 break;
             }
-            if (qh - pub >= CW_LZ4_PUB_BATCH) {  // publishing costs a fence: not after every window
+            if (qh - pub >= cw_umin(CW_LZ4_PUB_BATCH, qlen >> 1)) {  // publishing costs a fence: not after every window (a ring of 16: every 8)
                 cw_lz4_q_publish(q, qh, lane);
                 pub = qh;
             }

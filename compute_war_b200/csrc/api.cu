@@ -395,7 +395,7 @@ void pool_for(cw_ctx *ctx, size_t pieces, const std::function<void(size_t)> &fn)
 
 void pool_memcpy(cw_ctx *ctx, void *dst, const void *src, size_t bytes)
 {
-    constexpr size_t kPiece = 2u << 20;
+    constexpr size_t kPiece = 512u << 10;  // (a 4 MiB slice of a small staged call still spreads over 8 threads)
     const size_t pieces = (bytes + kPiece - 1) / kPiece;
     pool_for(ctx, pieces, [&](size_t k) {
         const size_t lo = k * kPiece, len = std::min(kPiece, bytes - lo);

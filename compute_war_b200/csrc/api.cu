@@ -735,13 +735,19 @@ void batch_worker(cw_ctx *ctx)
     Batcher &B = ctx->bat;
     cudaSetDevice(ctx->device);
     std::unique_lock<std::mutex> lk(B.mu);
+    bool left_wait = false;
     for (;;) {
         // a buffer is ready when it is sealed (full, or of another kind than the next caller) or simply holds what arrived
         // while the GPU was busy -- an idle worker takes whatever there is -- and nobody is still copying into it
         int ready = -1;
-        for (int i = 0; i < kBatchBufs && ready < 0; i++) {
+        for (int i = 0; i < kBatchBufs && ready < 0; i++) {  // sealed buffers first
             BatchBuf &b = B.bufs[i];
-            if (b.copying_in == 0 && b.chunks > 0 && (b.state == BatchBuf::SEALED || b.state == BatchBuf::OPEN)) ready = i;
+            if (b.copying_in == 0 && b.chunks > 0 && b.state == BatchBuf::SEALED) ready = i;
+        }
+        // (left_wait: the worker only interrupted its wait for a launch to take a sealed buffer -- the open one goes on gathering)
+        for (int i = 0; i < kBatchBufs && ready < 0 && !left_wait; i++) {
+            BatchBuf &b = B.bufs[i];
+            if (b.copying_in == 0 && b.chunks > 0 && b.state == BatchBuf::OPEN) ready = i;
         }
         if (ready >= 0) {
             BatchBuf &b = B.bufs[ready];
@@ -760,11 +766,29 @@ void batch_worker(cw_ctx *ctx)
         }
         if (!B.inflight.empty()) {  // nothing to launch: finish the oldest launch
             const int i = B.inflight.front();
-            B.inflight.pop_front();
             BatchBuf &b = B.bufs[i];
-            lk.unlock();
-            const cudaError_t e = cudaEventSynchronize(b.done);
-            lk.lock();
+            // CW_BATCH_POLL=1: poll the launch instead of blocking on it, and launch a buffer that is sealed meanwhile first.
+            // Measured (profiles/r02_small_batch_sweep.txt): blocking 256 KiB items 4.4 -> 8.9 GiB/s, but 1 MiB items
+            // 13.0 -> 10.0 and HashOffload 32 KiB items 10.1 -> 9.5: not the default
+            static const bool block = getenv("CW_BATCH_POLL") == nullptr;
+            cudaError_t e;
+            for (;;) {
+                lk.unlock();
+                e = block ? cudaEventSynchronize(b.done) : cudaEventQuery(b.done);
+                if (e == cudaErrorNotReady) std::this_thread::yield();
+                lk.lock();
+                if (e != cudaErrorNotReady) break;
+                bool more = false;
+                for (int k = 0; k < kBatchBufs && !more; k++) {
+                    const BatchBuf &o = B.bufs[k];
+                    // (sealed ones only: the open buffer goes on gathering callers while the GPU is busy, as before)
+                    more = o.copying_in == 0 && o.chunks > 0 && o.state == BatchBuf::SEALED;
+                }
+                if (more) break;
+            }
+            left_wait = e == cudaErrorNotReady;
+            if (left_wait) continue;  // launch what became ready, then come back
+            B.inflight.pop_front();
             if (e != cudaSuccess) b.rc = fail(ctx, e, "cudaEventSynchronize(batch)");
             batch_done(ctx, i);
             continue;
